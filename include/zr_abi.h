@@ -1,0 +1,448 @@
+/*
+ * zr_abi.h -- C-ABI of the B200-native ReSTIR path-tracing core (libzetaray_b200.so).
+ *
+ * Every entry point replaces one piece of ZetaRay's render-pass interface for the hot path
+ * (G-buffer -> pre-lighting/alias table -> ReSTIR DI -> ReSTIR PT -> compositing/firefly/TAA).
+ * Citations are relative to the reference tree (alipbcs/ZetaRay @ 6fd82f1e).
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; all "d_" pointers are CUDA device pointers, "h_" host pointers
+ *  - every function returns zr_status (0 = ok) and never throws; the reference aborts through
+ *    Check/CheckHR (ZetaCore/Utility/Error.h:33-92) -- here the failing call returns an error
+ *    code and zr_last_error() carries the message
+ *  - `stream` is a cudaStream_t passed as void*; all GPU work of a call is enqueued on it and the
+ *    call returns without synchronising (== recording into a CommandList,
+ *    ZetaCore/Core/RenderGraph.cpp:494-518)
+ *  - a pass handle is thread-compatible: concurrent calls on different handles are allowed
+ *    (ZetaCore/Core/RenderGraph.cpp:541-558)
+ */
+#ifndef ZR_ABI_H
+#define ZR_ABI_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ZR_API __declspec(dllexport)
+#else
+#define ZR_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t zr_status;
+enum
+{
+    ZR_OK = 0,
+    ZR_ERR_INVALID_ARG = 1,
+    ZR_ERR_CUDA = 2,
+    ZR_ERR_NOT_INITIALIZED = 3,
+    ZR_ERR_UNSUPPORTED = 4,
+    ZR_ERR_OUT_OF_MEMORY = 5
+};
+
+/* Last error message of the calling thread ("" if none). */
+ZR_API const char* zr_last_error(void);
+/* Library/ABI version: (major << 16) | minor. */
+ZR_API uint32_t zr_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Scene data layouts -- bit-identical to the reference's GPU structs
+ * ------------------------------------------------------------------------------------------ */
+
+/* Vertex: ZetaRenderPass/Common/Common.hlsli:5-11, ZetaCore/Core/Vertex.h:8-14 (28 bytes) */
+typedef struct zr_vertex
+{
+    float pos[3];
+    float uv[2];
+    uint16_t normal[2];     /* octahedral, 2 x UNORM16 */
+    uint16_t tangent[2];
+} zr_vertex;
+
+/* Material: ZetaCore/Core/Material.h:29-427 (8 x u32 with bit fields, 32 bytes) */
+typedef struct zr_material
+{
+    uint32_t BaseColorFactor;
+    uint32_t BaseColorTex_Subsurf_CoatWeight;
+    uint32_t NormalTex_TrDepth;
+    uint32_t MRTex_SpecRoughness_CoatRoughness;
+    uint32_t EmissiveFactor_NormalScale;
+    uint32_t EmissiveStrength_IOR;
+    uint32_t EmissiveTex_AlphaCutoff_CoatIOR;
+    uint32_t CoatColor_Flags;
+} zr_material;
+
+/* RT::MeshInstance: ZetaCore/RayTracing/RtCommon.h:47-64 (64 bytes) */
+typedef struct zr_mesh_instance
+{
+    uint32_t BaseVtxOffset;
+    uint32_t BaseIdxOffset;
+    uint16_t Rotation[4];       /* unorm4 quaternion */
+    uint16_t Scale[3];          /* half3 */
+    uint16_t MatIdx;
+    uint32_t BaseEmissiveTriOffset;
+    float Translation[3];
+    uint16_t PrevRotation[4];
+    uint16_t PrevScale[3];
+    uint16_t dTranslation[3];   /* half3 */
+    uint16_t BaseColorTex;
+    uint16_t AlphaFactor_Cutoff;
+} zr_mesh_instance;
+
+/* RT::EmissiveTriangle: RtCommon.h:66-114 (ENCODE_EMISSIVE_POS 1, EMISSIVE_UV_HALF 1; 48 bytes) */
+typedef struct zr_emissive_tri
+{
+    float Vtx0[3];
+    uint16_t V0V1[2];           /* oct-encoded unit edge, UNORM16 */
+    uint16_t V0V2[2];
+    uint16_t EdgeLengths[2];    /* half2 */
+    uint32_t ID;
+    uint32_t PackedA;           /* [0,24) emissive factor RGB8, bit 24 id-patched, bit 25 double sided */
+    uint32_t PackedB;           /* [0,16) texture, [16,32) strength (half) */
+    uint16_t UV0[2];
+    uint16_t UV1[2];
+    uint16_t UV2[2];
+} zr_emissive_tri;
+
+/* RT::EmissiveLumenAliasTableEntry: RtCommon.h:302-310 (16 bytes) */
+typedef struct zr_alias_entry
+{
+    float CachedP_Orig;
+    float CachedP_Alias;
+    float P_Curr;
+    uint32_t Alias;
+} zr_alias_entry;
+
+/* cbFrameConstants: ZetaRenderPass/Common/FrameConstants.h:10-78 (same field order and offsets;
+ * matrices are the reference's row_major float3x4 / float4x4). The *DescHeapOffset fields are
+ * kept for layout compatibility and ignored. */
+typedef struct zr_frame_constants
+{
+    float CurrView[3][4];
+    float PrevView[3][4];
+    float CurrViewInv[3][4];
+    float PrevViewInv[3][4];
+    float CurrViewProj[4][4];
+    float PrevViewProj[4][4];
+
+    float CameraPos[3];
+    float CameraNear;
+
+    float AspectRatio;
+    float PixelSpreadAngle;
+    float TanHalfFOV;
+    float dt;
+
+    uint32_t FrameNum;
+    uint32_t CurrGBufferDescHeapOffset;
+    uint32_t PrevGBufferDescHeapOffset;
+    uint32_t BaseColorMapsDescHeapOffset;
+
+    uint32_t NormalMapsDescHeapOffset;
+    uint32_t MetallicRoughnessMapsDescHeapOffset;
+    uint32_t EmissiveMapsDescHeapOffset;
+    uint32_t EnvMapDescHeapOffset;
+
+    uint32_t RenderWidth;
+    uint32_t RenderHeight;
+    uint32_t DisplayWidth;
+    uint32_t DisplayHeight;
+
+    float CurrCameraJitter[2];
+    float PrevCameraJitter[2];
+
+    float PlanetRadius;
+    float SunCosAngularRadius;
+    float SunSinAngularRadius;
+    float pad;
+
+    float SunDir[3];
+    float SunIlluminance;
+
+    float RayleighSigmaSColor[3];
+    float RayleighSigmaSScale;
+
+    float OzoneSigmaAColor[3];
+    float OzoneSigmaAScale;
+
+    float MieSigmaS;
+    float MieSigmaA;
+    float AtmosphereAltitude;
+    float g;
+
+    uint32_t NumFramesCameraStatic;
+    uint32_t CameraStatic;
+    uint32_t Accumulate;
+    uint32_t SunMoved;
+
+    float CameraRayUVGradsScale;
+    float MipBias;
+    float OneDivNumEmissiveTriangles;
+    uint32_t NumEmissiveTriangles;
+
+    float FocusDepth;
+    float LensRadius;
+    uint32_t DoF;
+    uint32_t pad2;
+} zr_frame_constants;
+
+/* ------------------------------------------------------------------------------------------
+ * Per-pixel state layouts in HBM (B200-native: AoS records sized for 128-bit accesses)
+ * ------------------------------------------------------------------------------------------ */
+
+/* G-buffer. The reference keeps 10 textures (ZetaRenderer/Default/DefaultRendererImpl.h:97-109);
+ * here the planes every consumer reads together share one 16-byte record:
+ *   core[i]   = { depth (f32 bits), normal (2 x UNORM16 oct), baseColor (RGBA8),
+ *                 flags | roughness(UNORM8) << 8 | ior(UNORM8) << 16 }
+ *   motion_emissive[i] = { motion (2 x SNORM16), emissive (R11G11B10_FLOAT) }
+ *   coat[i]   = { coatColor.rg | ..., see GBuffers.hlsli:110-121 } (3 x u16 in a uint2)
+ *   tridiff[i]= 12 halves (dpdu, dpdv, dndu, dndv), GBufferRT.hlsli:159-175; optional (may be NULL)
+ * Quantisation is identical to the reference formats. */
+typedef struct zr_gbuffer
+{
+    void* d_core;               /* uint4[w*h] */
+    void* d_motion_emissive;    /* uint2[w*h] */
+    void* d_coat;               /* uint2[w*h] */
+    void* d_tridiff;            /* 3 x uint2[w*h] or NULL */
+} zr_gbuffer;
+
+#define ZR_GBUFFER_FLAG_TRANSMISSIVE 0x01u
+#define ZR_GBUFFER_FLAG_EMISSIVE     0x02u
+#define ZR_GBUFFER_FLAG_INVALID      0x04u
+#define ZR_GBUFFER_FLAG_TRDEPTH_GT0  0x08u
+#define ZR_GBUFFER_FLAG_SUBSURFACE   0x10u
+#define ZR_GBUFFER_FLAG_COATED       0x20u
+#define ZR_GBUFFER_FLAG_METALLIC     0x80u
+
+/* ReSTIR PT reservoir: the reference's 7 planes A..G (IndirectLighting.h:128-144,
+ * ReSTIR_PT/Reservoir.hlsli:267-463; 62 B/px) as one 64-byte record = 4 x 128-bit. */
+typedef struct zr_rpt_reservoir
+{
+    /* q0 */
+    uint32_t meta;      /* A: byte0 = (k-2 | EMPTY=0xf) | M << 4, byte1 = lobe_{k-1} | lobe_k << 3 | lt_k << 6,
+                              byte2 = lt_{k+1} | x_k_in_motion << 2 */
+    float w_sum;        /* B.x */
+    float W;            /* B.y */
+    uint32_t L_b;       /* E: half L.b (low 16 bits) */
+    /* q1 = C */
+    uint32_t jacobian_or_seed_nee;
+    uint32_t seed_replay;
+    uint32_t ID;
+    uint32_t x_k_x;
+    /* q2 = D */
+    uint32_t x_k_y;
+    uint32_t x_k_z;
+    uint32_t w_k;       /* oct32: w_k | light normal | w_sky */
+    uint32_t L_rg;      /* half2 */
+    /* q3 = F, G */
+    float lightPdf;     /* sign bit = one-sided (Shift.hlsli:131) */
+    float dwdA;
+    uint32_t seed_nee;
+    uint32_t meshIdx;
+} zr_rpt_reservoir;
+
+/* ReSTIR DI reservoir: A RGBA32_UINT + B RG32F (DirectLighting/Emissive/Reservoir.hlsli:134-199)
+ * as one 32-byte record = 2 x 128-bit. */
+typedef struct zr_rdi_reservoir
+{
+    uint32_t bary;          /* 2 x UNORM16 */
+    uint32_t le_rg;         /* half2 */
+    uint32_t le_b_meta;     /* half le.b | M(5 bits) << 16 */
+    uint32_t lightIdx;
+    float w_sum;
+    float W;
+    uint32_t pad[2];
+} zr_rdi_reservoir;
+
+typedef struct zr_image2d
+{
+    void* d_ptr;
+    uint32_t width;
+    uint32_t height;
+    uint32_t pitch_bytes;
+    uint32_t texel_bytes;
+} zr_image2d;
+
+/* ------------------------------------------------------------------------------------------
+ * Scene: flat buffers named in ZetaCore/Scene/SceneRenderer.h:15-33 + the acceleration structure
+ * that replaces the DXR TLAS (ZetaCore/RayTracing/RtAccelerationStructure.cpp).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zr_scene zr_scene;
+
+typedef struct zr_scene_desc
+{
+    const zr_vertex* h_vertices;            uint32_t num_vertices;
+    const uint32_t* h_indices;              uint32_t num_indices;
+    const zr_mesh_instance* h_instances;    uint32_t num_instances;
+    /* triangles per instance (instances index consecutive ranges of the index buffer) */
+    const uint32_t* h_instance_num_tris;
+    const zr_material* h_materials;         uint32_t num_materials;
+    /* emissive triangles already in world space with hashed IDs (SceneCore.cpp:199-235) */
+    const zr_emissive_tri* h_emissives;     uint32_t num_emissives;
+} zr_scene_desc;
+
+/* Uploads the buffers, builds the 8-wide compressed BVH on the host and uploads it. */
+ZR_API zr_status zr_scene_create(const zr_scene_desc* desc, zr_scene** out);
+ZR_API void zr_scene_destroy(zr_scene* scene);
+/* BVH statistics for tests: {num_nodes, num_tris, max_depth, bytes}. */
+ZR_API zr_status zr_scene_bvh_stats(const zr_scene* scene, uint32_t out[4]);
+
+/* Ray queries through the product traversal kernel, for parity tests against the oracle's brute
+ * force (mirrors RtRayQuery::Hit::FindClosest / Visibility_Segment, Common/RayQuery.hlsli:15-144,
+ * 337-406). rays: n x {origin xyz, tmin, dir xyz, tmax}; hits: n x {t, bary.x, bary.y, triGlobal(u32)}. */
+ZR_API zr_status zr_scene_trace_closest(const zr_scene* scene, const float* d_rays, uint32_t n,
+    float* d_hits, void* stream);
+ZR_API zr_status zr_scene_trace_any(const zr_scene* scene, const float* d_rays, uint32_t n,
+    uint32_t* d_hit_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pre-lighting: power estimate + alias table (replaces EstimateTriEmissivePower.hlsl and the CPU
+ * BuildAliasTable round trip, PreLighting/PreLighting.cpp:27-158, 512-585)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Math::AliasTable_Normalize + BuildAliasTable on the device. d_weights is normalised in place
+ * (as the reference does to its readback buffer). d_scratch: 2*n u32. Bit-exact with the CPU
+ * reference for 32-byte aligned input (the production case). */
+ZR_API zr_status zr_alias_table_build(float* d_weights, uint32_t n, zr_alias_entry* d_table,
+    uint32_t* d_scratch, void* stream);
+/* Light::AliasTableSample::get (Common/LightSource.hlsli:72-97) for `num_draws` consecutive draws
+ * of one RNG stream seeded RNG::Init(seed). */
+ZR_API zr_status zr_alias_table_sample(const zr_alias_entry* d_table, uint32_t n, uint32_t seed,
+    uint32_t num_draws, uint32_t* d_out_idx, float* d_out_pdf, void* stream);
+/* EstimateTriEmissivePower (PreLighting/EstimateTriEmissivePower.hlsl:30-79): d_power[n]. */
+ZR_API zr_status zr_estimate_emissive_power(const zr_scene* scene, float* d_power, void* stream);
+/* Convenience used by the pre-lighting node: power estimate + alias build into the scene's own
+ * alias table (frame-1 protocol, ZetaRenderer/Default/PathTracer.cpp:195-240). */
+ZR_API zr_status zr_prelighting_render(zr_scene* scene, void* stream);
+ZR_API zr_status zr_scene_get_alias_table(const zr_scene* scene, const zr_alias_entry** d_table, uint32_t* n);
+
+/* ------------------------------------------------------------------------------------------
+ * Frame inputs shared by the passes (== the global resources a pass looks up by name)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zr_frame_inputs
+{
+    zr_frame_constants frame;
+    zr_gbuffer curr;
+    zr_gbuffer prev;
+    const zr_scene* scene;
+} zr_frame_inputs;
+
+ZR_API zr_status zr_gbuffer_alloc(uint32_t width, uint32_t height, int with_tridiff, zr_gbuffer* out);
+ZR_API void zr_gbuffer_free(zr_gbuffer* g);
+
+/* Render-graph node metadata (Core/RenderGraph.h:81-105): ids are zr_resource_id below. */
+typedef enum zr_resource_id
+{
+    ZR_RES_GBUFFER_CURR = 1, ZR_RES_GBUFFER_PREV, ZR_RES_SCENE_BVH, ZR_RES_ALIAS_TABLE,
+    ZR_RES_DI_FINAL, ZR_RES_INDIRECT_FINAL, ZR_RES_COMPOSITED, ZR_RES_TAA_OUT
+} zr_resource_id;
+typedef struct zr_resource_use { uint32_t id; uint32_t write; } zr_resource_use;
+
+/* ---- GBufferRT (GBuffer/GBufferRT.h, GBufferRT.cpp:99-160) ---- */
+typedef struct zr_gbuffer_pass zr_gbuffer_pass;
+ZR_API zr_status zr_gbuffer_pass_create(zr_gbuffer_pass** out);
+ZR_API zr_status zr_gbuffer_pass_render(zr_gbuffer_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_gbuffer_pass_describe_io(zr_gbuffer_pass* p, zr_resource_use* uses, int* n);
+ZR_API void zr_gbuffer_pass_destroy(zr_gbuffer_pass* p);
+
+/* ---- DirectLighting (ReSTIR DI, DirectLighting/Emissive/DirectLighting.h:36-57) ---- */
+typedef struct zr_direct_pass zr_direct_pass;
+typedef struct zr_direct_params
+{
+    uint32_t temporal_resample;     /* CB_RDI_FLAGS::TEMPORAL_RESAMPLE */
+    uint32_t spatial_resample;
+    uint32_t stochastic_spatial;
+    uint32_t extra_disocclusion_sampling;
+    uint32_t M_max;                 /* default 20, DirectLighting.h:95 */
+    float alpha_min;                /* default 0.05^2 */
+} zr_direct_params;
+typedef enum zr_direct_output { ZR_DIRECT_FINAL = 0, ZR_DIRECT_RESERVOIR_CURR, ZR_DIRECT_TARGET } zr_direct_output;
+ZR_API zr_status zr_direct_pass_create(uint32_t width, uint32_t height, zr_direct_pass** out);
+ZR_API zr_status zr_direct_pass_resize(zr_direct_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_direct_pass_reset_temporal(zr_direct_pass* p);
+ZR_API zr_status zr_direct_pass_default_params(zr_direct_params* out);
+ZR_API zr_status zr_direct_pass_set_params(zr_direct_pass* p, const zr_direct_params* params);
+ZR_API zr_status zr_direct_pass_render(zr_direct_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_direct_pass_get_output(zr_direct_pass* p, zr_direct_output id, zr_image2d* out);
+ZR_API zr_status zr_direct_pass_describe_io(zr_direct_pass* p, zr_resource_use* uses, int* n);
+ZR_API void zr_direct_pass_destroy(zr_direct_pass* p);
+
+/* ---- IndirectLighting (ReSTIR PT, IndirectLighting/IndirectLighting.h:72-108) ---- */
+typedef struct zr_indirect_pass zr_indirect_pass;
+typedef struct zr_indirect_params
+{
+    uint32_t max_non_tr_bounces;    /* default 3, IndirectLighting.h:231-244 */
+    uint32_t max_glossy_tr_bounces; /* default 4 */
+    uint32_t russian_roulette;      /* default 1 */
+    uint32_t temporal_resample;     /* default 1 */
+    uint32_t num_spatial_passes;    /* default 1 */
+    uint32_t M_max_temporal;        /* default 10 */
+    uint32_t M_max_spatial;         /* default 8 */
+    uint32_t boiling_suppression;   /* default 1 */
+    uint32_t sort_temporal;         /* default 1 */
+    uint32_t sort_spatial;          /* default 1 */
+    float alpha_min;                /* default 0.175^2 */
+} zr_indirect_params;
+typedef enum zr_indirect_output
+{
+    ZR_INDIRECT_FINAL = 0, ZR_INDIRECT_RESERVOIR_CURR, ZR_INDIRECT_RESERVOIR_PREV, ZR_INDIRECT_TARGET,
+    ZR_INDIRECT_NEIGHBOR, ZR_INDIRECT_THREADMAP_CTN, ZR_INDIRECT_THREADMAP_NTC
+} zr_indirect_output;
+/* stages for parity tests: stop the frame after a stage (0 = whole frame) */
+typedef enum zr_indirect_stage
+{
+    ZR_RPT_STAGE_ALL = 0, ZR_RPT_STAGE_PATHTRACE = 1, ZR_RPT_STAGE_TEMPORAL = 2, ZR_RPT_STAGE_SPATIAL = 3
+} zr_indirect_stage;
+ZR_API zr_status zr_indirect_pass_create(uint32_t width, uint32_t height, zr_indirect_pass** out);
+ZR_API zr_status zr_indirect_pass_resize(zr_indirect_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_indirect_pass_reset_temporal(zr_indirect_pass* p);
+ZR_API zr_status zr_indirect_pass_default_params(zr_indirect_params* out);
+ZR_API zr_status zr_indirect_pass_set_params(zr_indirect_pass* p, const zr_indirect_params* params);
+ZR_API zr_status zr_indirect_pass_render(zr_indirect_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_indirect_pass_render_until(zr_indirect_pass* p, const zr_frame_inputs* in,
+    zr_indirect_stage last_stage, void* stream);
+ZR_API zr_status zr_indirect_pass_get_output(zr_indirect_pass* p, zr_indirect_output id, zr_image2d* out);
+ZR_API zr_status zr_indirect_pass_describe_io(zr_indirect_pass* p, zr_resource_use* uses, int* n);
+/* multi-GPU: rows [y0, y1) this rank owns; halo rows are read from the (all-gathered) planes */
+ZR_API zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1);
+ZR_API void zr_indirect_pass_destroy(zr_indirect_pass* p);
+
+/* ---- Compositing + FireflyFilter (Compositing/Compositing.cpp:83-145) ---- */
+typedef struct zr_compositing_pass zr_compositing_pass;
+typedef struct zr_compositing_params { uint32_t emissive_di; uint32_t indirect; uint32_t firefly_filter; } zr_compositing_params;
+ZR_API zr_status zr_compositing_pass_create(uint32_t width, uint32_t height, zr_compositing_pass** out);
+ZR_API zr_status zr_compositing_pass_resize(zr_compositing_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_compositing_pass_set_params(zr_compositing_pass* p, const zr_compositing_params* params);
+/* d_direct / d_indirect: float4[w*h] (outputs of the lighting passes) or NULL */
+ZR_API zr_status zr_compositing_pass_render(zr_compositing_pass* p, const zr_frame_inputs* in,
+    const void* d_direct, const void* d_indirect, void* stream);
+ZR_API zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out);
+ZR_API void zr_compositing_pass_destroy(zr_compositing_pass* p);
+
+/* ---- TAA (TAA/TAA.cpp:87-123) ---- */
+typedef struct zr_taa_pass zr_taa_pass;
+ZR_API zr_status zr_taa_pass_create(uint32_t width, uint32_t height, zr_taa_pass** out);
+ZR_API zr_status zr_taa_pass_resize(zr_taa_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_taa_pass_set_blend_weight(zr_taa_pass* p, float w);  /* default 0.1, TAA.h:72 */
+/* d_signal: float4[w*h]; output RGBA16F (half4, 8 B/px) */
+ZR_API zr_status zr_taa_pass_render(zr_taa_pass* p, const zr_frame_inputs* in, const void* d_signal, void* stream);
+ZR_API zr_status zr_taa_pass_get_output(zr_taa_pass* p, zr_image2d* out);
+ZR_API void zr_taa_pass_destroy(zr_taa_pass* p);
+
+/* ---- host <-> device helpers so callers need no CUDA runtime of their own ---- */
+ZR_API zr_status zr_device_malloc(void** d_ptr, size_t bytes);
+ZR_API void zr_device_free(void* d_ptr);
+ZR_API zr_status zr_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+ZR_API zr_status zr_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+ZR_API zr_status zr_memset_d(void* d_dst, int value, size_t bytes, void* stream);
+ZR_API zr_status zr_stream_synchronize(void* stream);
+/* number of kernels this library launched since load (for bench.py's gpu_launches) */
+ZR_API uint64_t zr_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ZR_ABI_H */
