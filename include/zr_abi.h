@@ -196,6 +196,8 @@ typedef struct zr_frame_constants
  * here the planes every consumer reads together share one 16-byte record:
  *   core[i]   = { depth (f32 bits), normal (2 x UNORM16 oct), baseColor (RGBA8),
  *                 flags | roughness(UNORM8) << 8 | ior(UNORM8) << 16 }
+ *   depth[i]  = view depth again as its own 4-byte plane, so the depth-only stencil taps
+ *               (firefly, TAA dilation) do not drag the 16-byte record through HBM
  *   motion_emissive[i] = { motion (2 x SNORM16), emissive (R11G11B10_FLOAT) }
  *   coat[i]   = { coatColor.rg | ..., see GBuffers.hlsli:110-121 } (3 x u16 in a uint2)
  *   tridiff[i]= 12 halves (dpdu, dpdv, dndu, dndv), GBufferRT.hlsli:159-175; optional (may be NULL)
@@ -203,6 +205,7 @@ typedef struct zr_frame_constants
 typedef struct zr_gbuffer
 {
     void* d_core;               /* uint4[w*h] */
+    void* d_depth;              /* float[w*h]: copy of core.x for depth-only consumers (stencils) */
     void* d_motion_emissive;    /* uint2[w*h] */
     void* d_coat;               /* uint2[w*h] */
     void* d_tridiff;            /* 3 x uint2[w*h] or NULL */
@@ -417,6 +420,10 @@ ZR_API zr_status zr_compositing_pass_resize(zr_compositing_pass* p, uint32_t wid
 ZR_API zr_status zr_compositing_pass_set_params(zr_compositing_pass* p, const zr_compositing_params* params);
 /* d_direct / d_indirect: float4[w*h] (outputs of the lighting passes) or NULL */
 ZR_API zr_status zr_compositing_pass_render(zr_compositing_pass* p, const zr_frame_inputs* in,
+    const void* d_direct, const void* d_indirect, void* stream);
+/* the reference's two-dispatch sequence (compositing, then firefly on the stored image); the default
+ * render() fuses both -- kept so tests can check the fusion changes nothing */
+ZR_API zr_status zr_compositing_pass_render_unfused(zr_compositing_pass* p, const zr_frame_inputs* in,
     const void* d_direct, const void* d_indirect, void* stream);
 ZR_API zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out);
 ZR_API void zr_compositing_pass_destroy(zr_compositing_pass* p);

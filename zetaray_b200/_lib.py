@@ -51,7 +51,7 @@ class FrameConstants(C.Structure):
 
 
 class GBuffer(C.Structure):
-    _fields_ = [("d_core", vp), ("d_motion_emissive", vp), ("d_coat", vp), ("d_tridiff", vp)]
+    _fields_ = [("d_core", vp), ("d_depth", vp), ("d_motion_emissive", vp), ("d_coat", vp), ("d_tridiff", vp)]
 
 
 class FrameInputs(C.Structure):

@@ -1,0 +1,468 @@
+// post.cu -- compositing, firefly filter and TAA stencils (HBM-bound kernels).
+//
+// Replaces Compositing/Compositing.hlsl:30-126, Compositing/FireflyFilter.hlsl:35-124 and
+// TAA/TAA.hlsl:29-189 (+ Common.hlsli:65-102 Catmull-Rom history fetch) and their host passes
+// (Compositing.cpp:83-145, TAA.cpp:87-123).
+//
+// B200 notes: these kernels move bytes and nothing else. Compositing is elementwise, so when the
+// firefly filter is on it is fused into the 3x3 stencil (each tap recomposites from the two lighting
+// images; the neighbour taps are L1/L2 hits) which removes one 16 B/px write + one 16 B/px read of
+// the reference's two-dispatch sequence. The filter writes a second image instead of filtering in
+// place (the reference's in-place UAV update races with its own neighbour reads).
+#include "zr_common.cuh"
+
+namespace zr
+{
+namespace
+{
+    struct PostParams
+    {
+        uint32_t W, H;
+        uint32_t accumulate;            // Accumulate && CameraStatic
+        uint32_t numFramesAccumulated;
+        float blendWeight;
+        uint32_t temporalIsValid;
+    };
+
+    ZR_D float3 composite_px(const uint4* __restrict__ core, const float4* __restrict__ direct,
+        const float4* __restrict__ indirect, size_t i, const PostParams& p)
+    {
+        const uint32_t flags = __ldg(&core[i].w) & 0xffu;
+        if ((flags & ZR_GBUFFER_FLAG_INVALID) && !p.accumulate)
+            return f3(0);
+        float3 color = f3(0);
+        if (direct)
+        {
+            float4 d = __ldg(&direct[i]);
+            color += f3(d.x, d.y, d.z);
+        }
+        if (indirect && !(flags & ZR_GBUFFER_FLAG_EMISSIVE))
+        {
+            float4 d = __ldg(&indirect[i]);
+            color += f3(d.x, d.y, d.z);
+        }
+        return color / (float)p.numFramesAccumulated;
+    }
+
+    __global__ void __launch_bounds__(256) k_compositing(const uint4* __restrict__ core,
+        const float4* __restrict__ direct, const float4* __restrict__ indirect, float4* __restrict__ out, PostParams p)
+    {
+        const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
+        const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
+        if (x >= p.W || y >= p.H) return;
+        const size_t i = (size_t)y * p.W + x;
+        float3 c = composite_px(core, direct, indirect, i, p);
+        out[i] = f4(c.x, c.y, c.z, 0.0f);
+    }
+
+    // Firefly filter over an image produced by `Load` (either a stored composited image or the
+    // on-the-fly composite).
+    template<bool Fused>
+    __global__ void __launch_bounds__(256) k_firefly(const uint4* __restrict__ core, const float* __restrict__ depth,
+        const float4* __restrict__ inOrDirect, const float4* __restrict__ indirect, float4* __restrict__ out,
+        PostParams p)
+    {
+        const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+        const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+        const int W = (int)p.W, H = (int)p.H;
+        if (x >= W || y >= H) return;
+        const size_t idx = (size_t)y * W + x;
+        auto load = [&](size_t i) -> float3 {
+            if (Fused)
+                return composite_px(core, inOrDirect, indirect, i, p);
+            float4 c = __ldg(&inOrDirect[i]);
+            return f3(c.x, c.y, c.z);
+        };
+        const float z_view = __ldg(&depth[idx]);
+        const float3 currColor = load(idx);
+        if (z_view == FLT_MAX_)
+        {
+            out[idx] = f4(currColor.x, currColor.y, currColor.z, 0.0f);
+            return;
+        }
+        float minLum = FLT_MAX_;
+        float maxLum = 0.0f;
+        float3 minColor = currColor;
+        float3 maxColor = f3(0);
+        const float currLum = Math::Luminance(currColor);
+#pragma unroll
+        for (int i = -1; i <= 1; i++)
+        {
+#pragma unroll
+            for (int j = -1; j <= 1; j++)
+            {
+                if (i == 0 && j == 0) continue;
+                const int ax = x + j, ay = y + i;
+                if ((uint32_t)ax >= (uint32_t)W || (uint32_t)ay >= (uint32_t)H) continue;
+                const size_t n = (size_t)ay * W + ax;
+                if (__ldg(&depth[n]) == FLT_MAX_) continue;
+                const float3 neighborColor = load(n);
+                const float neighborLum = Math::Luminance(neighborColor);
+                if (neighborLum < minLum) { minLum = neighborLum; minColor = neighborColor; }
+                else if (neighborLum > maxLum) { maxLum = neighborLum; maxColor = neighborColor; }
+            }
+        }
+        float3 ret = currLum < minLum ? minColor : (currLum > maxLum ? maxColor : currColor);
+        ret = minLum <= maxLum ? ret : currColor;
+        out[idx] = f4(ret.x, ret.y, ret.z, 0.0f);
+    }
+
+    ZR_D float Mitchell1D(float x, float B, float C)
+    {
+        x = fabsf(2.0f * x);
+        const float oneDivSix = 1.0f / 6.0f;
+        if (x > 1)
+            return ((-B - 6.0f * C) * x * x * x + (6.0f * B + 30.0f * C) * x * x +
+                (-12.0f * B - 48.0f * C) * x + (8.0f * B + 24.0f * C)) * oneDivSix;
+        else
+            return ((12.0f - 9.0f * B - 6.0f * C) * x * x * x + (-18.0f + 12.0f * B + 6.0f * C) * x * x +
+                (6.0f - 2.0f * B)) * oneDivSix;
+    }
+
+    ZR_D float3 LoadHalf4(const uint2* __restrict__ img, int W, int H, int x, int y)
+    {
+        x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+        y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+        const uint2 p = __ldg(&img[(size_t)y * W + x]);
+        return f3(half_lo(p.x), half_hi(p.x), half_lo(p.y));
+    }
+
+    ZR_D float3 SampleBilinearClamp(const uint2* __restrict__ img, int W, int H, float2 uv)
+    {
+        const float px = uv.x * (float)W - 0.5f;
+        const float py = uv.y * (float)H - 0.5f;
+        const float fx0 = floorf(px), fy0 = floorf(py);
+        const float fx = px - fx0, fy = py - fy0;
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float3 c00 = LoadHalf4(img, W, H, x0, y0), c10 = LoadHalf4(img, W, H, x0 + 1, y0);
+        const float3 c01 = LoadHalf4(img, W, H, x0, y0 + 1), c11 = LoadHalf4(img, W, H, x0 + 1, y0 + 1);
+        const float3 top = c00 * (1.0f - fx) + c10 * fx;
+        const float3 bot = c01 * (1.0f - fx) + c11 * fx;
+        return top * (1.0f - fy) + bot * fy;
+    }
+
+    ZR_D float3 SampleTextureCatmullRom(const uint2* __restrict__ img, int W, int H, float2 uv, float2 texSize)
+    {
+        const float2 samplePos = uv * texSize;
+        const float2 texPos1 = f2(floorf(samplePos.x - 0.5f) + 0.5f, floorf(samplePos.y - 0.5f) + 0.5f);
+        const float2 f = samplePos - texPos1;
+        const float2 w0 = f2(f.x * (-0.5f + f.x * (1.0f - 0.5f * f.x)), f.y * (-0.5f + f.y * (1.0f - 0.5f * f.y)));
+        const float2 w1 = f2(1.0f + f.x * f.x * (-2.5f + 1.5f * f.x), 1.0f + f.y * f.y * (-2.5f + 1.5f * f.y));
+        const float2 w2 = f2(f.x * (0.5f + f.x * (2.0f - 1.5f * f.x)), f.y * (0.5f + f.y * (2.0f - 1.5f * f.y)));
+        const float2 w3 = f2(f.x * f.x * (-0.5f + 0.5f * f.x), f.y * f.y * (-0.5f + 0.5f * f.y));
+        const float2 w12 = w1 + w2;
+        const float2 offset12 = w2 / (w1 + w2);
+        float2 texPos0 = texPos1 - 1.0f;
+        float2 texPos3 = texPos1 + 2.0f;
+        float2 texPos12 = texPos1 + offset12;
+        texPos0 = texPos0 / texSize;
+        texPos3 = texPos3 / texSize;
+        texPos12 = texPos12 / texSize;
+        float3 result = f3(0);
+        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos0.y)) * w0.x * w0.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos0.y)) * w12.x * w0.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos0.y)) * w3.x * w0.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos12.y)) * w0.x * w12.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos12.y)) * w12.x * w12.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos12.y)) * w3.x * w12.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos3.y)) * w0.x * w3.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos3.y)) * w12.x * w3.y;
+        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos3.y)) * w3.x * w3.y;
+        return result;
+    }
+
+    ZR_D float3 ClipAABB(float3 aabbMin, float3 aabbMax, float3 histSample)
+    {
+        const float3 center = 0.5f * (aabbMax + aabbMin);
+        const float3 extents = 0.5f * (aabbMax - aabbMin);
+        const float3 rayToCenter = histSample - center;
+        const float3 u = abs3(rayToCenter / extents);
+        const float m = fmaxf(u.x, fmaxf(u.y, u.z));
+        if (m > 1.0f)
+            return center + rayToCenter / m;
+        return histSample;
+    }
+
+    __global__ void __launch_bounds__(256) k_taa(const float* __restrict__ depthPlane,
+        const uint2* __restrict__ motionEmissive, const float4* __restrict__ signal,
+        const uint2* __restrict__ prevOut, uint2* __restrict__ out, PostParams p)
+    {
+        const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+        const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+        const int W = (int)p.W, H = (int)p.H;
+        if (x >= W || y >= H) return;
+        const size_t idx = (size_t)y * W + x;
+        const float depth = __ldg(&depthPlane[idx]);
+        const float4 s4 = __ldg(&signal[idx]);
+        const float3 currColor = f3(s4.x, s4.y, s4.z);
+        if (!p.temporalIsValid || depth == FLT_MAX_)
+        {
+            out[idx] = make_uint2(pack_half2(currColor.x, currColor.y), pack_half2(currColor.z, 0.0f));
+            return;
+        }
+        float weightSum = Mitchell1D(0, 0.33f, 0.33f) * Mitchell1D(0, 0.33f, 0.33f);
+        float3 reconstructed = currColor * weightSum;
+        float3 firstMoment = currColor;
+        float3 secondMoment = currColor * currColor;
+        float closestDepth = depth;
+        int cdx = 0, cdy = 0;
+        int numNeighbors = 1;
+#pragma unroll
+        for (int i = -1; i < 2; i++)
+        {
+#pragma unroll
+            for (int j = -1; j < 2; j++)
+            {
+                if (i == 0 && j == 0) continue;
+                const int nx = x + i, ny = y + j;
+                if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+                const size_t n = (size_t)ny * W + nx;
+                const float4 c4 = __ldg(&signal[n]);
+                const float3 neighborColor = max3(f3(c4.x, c4.y, c4.z), 0.0f);
+                float weight = Mitchell1D((float)i, 0.33f, 0.33f) * Mitchell1D((float)j, 0.33f, 0.33f);
+                weight *= 1.0f / (1.0f + Math::Luminance(neighborColor));
+                reconstructed += neighborColor * weight;
+                weightSum += weight;
+                firstMoment += neighborColor;
+                secondMoment += neighborColor * neighborColor;
+                const float neighborDepth = __ldg(&depthPlane[n]);
+                if (neighborDepth < closestDepth) { closestDepth = neighborDepth; cdx = i; cdy = j; }
+                numNeighbors += 1;
+            }
+        }
+        reconstructed = reconstructed / fmaxf(weightSum, 1e-5f);
+        const float2 motionVec = unpack_snorm16x2(__ldg(&motionEmissive[(size_t)(y + cdy) * W + (x + cdx)].x));
+        const float2 renderDim = f2((float)W, (float)H);
+        const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / renderDim;
+        const float2 prevUV = currUV - motionVec;
+        if (prevUV.x < 0.0f || prevUV.y < 0.0f || prevUV.x > 1.0f || prevUV.y > 1.0f)
+        {
+            out[idx] = make_uint2(pack_half2(reconstructed.x, reconstructed.y), pack_half2(reconstructed.z, 0.0f));
+            return;
+        }
+        const float3 history = SampleTextureCatmullRom(prevOut, W, H, prevUV, renderDim);
+        const float3 mean = firstMoment / (float)numNeighbors;
+        float3 std = abs3(secondMoment - (firstMoment * firstMoment) / (float)numNeighbors);
+        std = std / ((float)numNeighbors - 1.0f);
+        std = sqrt3(std);
+        const float3 clippedHistory = ClipAABB(mean - std, mean + std, history);
+        const float currWeight = saturate(p.blendWeight * (1.0f / (1.0f + Math::Luminance(reconstructed))));
+        const float histWeight = saturate((1.0f - p.blendWeight) * (1.0f / (1.0f + Math::Luminance(clippedHistory))));
+        float3 result = (currWeight * reconstructed + histWeight * clippedHistory) / (currWeight + histWeight);
+        result = isnan3(result) ? reconstructed : result;
+        out[idx] = make_uint2(pack_half2(result.x, result.y), pack_half2(result.z, 0.0f));
+    }
+
+    PostParams make_params(const zr_frame_constants& fc)
+    {
+        PostParams p;
+        p.W = fc.RenderWidth;
+        p.H = fc.RenderHeight;
+        p.accumulate = (fc.Accumulate && fc.CameraStatic) ? 1u : 0u;
+        p.numFramesAccumulated = p.accumulate ? fc.NumFramesCameraStatic : 1u;
+        p.blendWeight = 0.1f;
+        p.temporalIsValid = 0;
+        return p;
+    }
+}
+} // namespace zr
+
+// ------------------------------------------------------------------------------------------------
+// Host-side pass objects: same verbs as the reference's structs
+// ------------------------------------------------------------------------------------------------
+struct zr_compositing_pass
+{
+    // Compositing (Compositing/Compositing.h): owns the LIGHT_ACCUM image (RGBA32F)
+    uint32_t width = 0, height = 0;
+    float4* d_composited = nullptr;     // output of compositing (and of the fused firefly variant)
+    float4* d_scratch = nullptr;        // unfused path: compositing result before the filter
+    zr_compositing_params params{ 1, 1, 1 };
+
+    zr_status Init(uint32_t w, uint32_t h) { return OnWindowResized(w, h); }
+    zr_status OnWindowResized(uint32_t w, uint32_t h)
+    {
+        Release();
+        width = w; height = h;
+        ZR_CUDA(cudaMalloc(&d_composited, (size_t)w * h * sizeof(float4)));
+        ZR_CUDA(cudaMalloc(&d_scratch, (size_t)w * h * sizeof(float4)));
+        return ZR_OK;
+    }
+    void Release()
+    {
+        if (d_composited) cudaFree(d_composited);
+        if (d_scratch) cudaFree(d_scratch);
+        d_composited = d_scratch = nullptr;
+    }
+    zr_status Render(const zr_frame_inputs* in, const void* d_direct, const void* d_indirect, cudaStream_t stream)
+    {
+        using namespace zr;
+        if (!in || !in->curr.d_core || !in->curr.d_depth)
+        {
+            set_error("zr_compositing_pass_render: missing G-buffer");
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (in->frame.RenderWidth != width || in->frame.RenderHeight != height)
+        {
+            set_error("zr_compositing_pass_render: frame is %ux%u but the pass was sized %ux%u",
+                in->frame.RenderWidth, in->frame.RenderHeight, width, height);
+            return ZR_ERR_INVALID_ARG;
+        }
+        PostParams p = make_params(in->frame);
+        const float4* direct = params.emissive_di ? (const float4*)d_direct : nullptr;
+        const float4* indirect = params.indirect ? (const float4*)d_indirect : nullptr;
+        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        if (params.firefly_filter)
+        {
+            k_firefly<true><<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
+                direct, indirect, d_composited, p);
+            ZR_LAUNCH_CHECK();
+        }
+        else
+        {
+            k_compositing<<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, direct, indirect, d_composited, p);
+            ZR_LAUNCH_CHECK();
+        }
+        return ZR_OK;
+    }
+    // reference-shaped two-dispatch sequence (used by tests to check the fusion)
+    zr_status RenderUnfused(const zr_frame_inputs* in, const void* d_direct, const void* d_indirect, cudaStream_t stream)
+    {
+        using namespace zr;
+        PostParams p = make_params(in->frame);
+        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        k_compositing<<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float4*)d_direct,
+            (const float4*)d_indirect, d_scratch, p);
+        ZR_LAUNCH_CHECK();
+        k_firefly<false><<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
+            d_scratch, nullptr, d_composited, p);
+        ZR_LAUNCH_CHECK();
+        return ZR_OK;
+    }
+};
+
+struct zr_taa_pass
+{
+    // TAA (TAA/TAA.h): two RGBA16F images, ping-ponged every Render (TAA.cpp:99-104)
+    uint32_t width = 0, height = 0;
+    uint2* d_tex[2] = { nullptr, nullptr };
+    int outIdx = 0;
+    bool isTemporalTexValid = false;
+    float blendWeight = 0.1f;       // DefaultParamVals::BlendWeight
+
+    zr_status OnWindowResized(uint32_t w, uint32_t h)
+    {
+        Release();
+        width = w; height = h;
+        for (int i = 0; i < 2; i++)
+        {
+            ZR_CUDA(cudaMalloc(&d_tex[i], (size_t)w * h * sizeof(uint2)));
+            ZR_CUDA(cudaMemset(d_tex[i], 0, (size_t)w * h * sizeof(uint2)));
+        }
+        isTemporalTexValid = false;
+        return ZR_OK;
+    }
+    void Release()
+    {
+        for (int i = 0; i < 2; i++) { if (d_tex[i]) cudaFree(d_tex[i]); d_tex[i] = nullptr; }
+    }
+    zr_status Render(const zr_frame_inputs* in, const void* d_signal, cudaStream_t stream)
+    {
+        using namespace zr;
+        if (!in || !in->curr.d_depth || !in->curr.d_motion_emissive || !d_signal)
+        {
+            set_error("zr_taa_pass_render: missing input");
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (in->frame.RenderWidth != width || in->frame.RenderHeight != height)
+        {
+            set_error("zr_taa_pass_render: frame/pass size mismatch");
+            return ZR_ERR_INVALID_ARG;
+        }
+        PostParams p = make_params(in->frame);
+        p.blendWeight = blendWeight;
+        p.temporalIsValid = isTemporalTexValid ? 1u : 0u;
+        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        outIdx ^= 1;
+        k_taa<<<grid, 256, 0, stream>>>((const float*)in->curr.d_depth, (const uint2*)in->curr.d_motion_emissive,
+            (const float4*)d_signal, d_tex[outIdx ^ 1], d_tex[outIdx], p);
+        ZR_LAUNCH_CHECK();
+        isTemporalTexValid = true;
+        return ZR_OK;
+    }
+};
+
+extern "C"
+{
+    zr_status zr_compositing_pass_create(uint32_t width, uint32_t height, zr_compositing_pass** out)
+    {
+        if (!out || !width || !height) { zr::set_error("zr_compositing_pass_create: bad args"); return ZR_ERR_INVALID_ARG; }
+        zr_compositing_pass* p = new zr_compositing_pass();
+        zr_status s = p->Init(width, height);
+        if (s != ZR_OK) { delete p; return s; }
+        *out = p;
+        return ZR_OK;
+    }
+    zr_status zr_compositing_pass_resize(zr_compositing_pass* p, uint32_t width, uint32_t height)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->OnWindowResized(width, height);
+    }
+    zr_status zr_compositing_pass_set_params(zr_compositing_pass* p, const zr_compositing_params* params)
+    {
+        if (!p || !params) return ZR_ERR_INVALID_ARG;
+        p->params = *params;
+        return ZR_OK;
+    }
+    zr_status zr_compositing_pass_render(zr_compositing_pass* p, const zr_frame_inputs* in, const void* d_direct,
+        const void* d_indirect, void* stream)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->Render(in, d_direct, d_indirect, (cudaStream_t)stream);
+    }
+    zr_status zr_compositing_pass_render_unfused(zr_compositing_pass* p, const zr_frame_inputs* in, const void* d_direct,
+        const void* d_indirect, void* stream)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->RenderUnfused(in, d_direct, d_indirect, (cudaStream_t)stream);
+    }
+    zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out)
+    {
+        if (!p || !out) return ZR_ERR_INVALID_ARG;
+        *out = zr_image2d{ p->d_composited, p->width, p->height, p->width * 16u, 16u };
+        return ZR_OK;
+    }
+    void zr_compositing_pass_destroy(zr_compositing_pass* p) { if (p) { p->Release(); delete p; } }
+
+    zr_status zr_taa_pass_create(uint32_t width, uint32_t height, zr_taa_pass** out)
+    {
+        if (!out || !width || !height) { zr::set_error("zr_taa_pass_create: bad args"); return ZR_ERR_INVALID_ARG; }
+        zr_taa_pass* p = new zr_taa_pass();
+        zr_status s = p->OnWindowResized(width, height);
+        if (s != ZR_OK) { delete p; return s; }
+        *out = p;
+        return ZR_OK;
+    }
+    zr_status zr_taa_pass_resize(zr_taa_pass* p, uint32_t width, uint32_t height)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->OnWindowResized(width, height);
+    }
+    zr_status zr_taa_pass_set_blend_weight(zr_taa_pass* p, float w)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->blendWeight = w;
+        return ZR_OK;
+    }
+    zr_status zr_taa_pass_render(zr_taa_pass* p, const zr_frame_inputs* in, const void* d_signal, void* stream)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->Render(in, d_signal, (cudaStream_t)stream);
+    }
+    zr_status zr_taa_pass_get_output(zr_taa_pass* p, zr_image2d* out)
+    {
+        if (!p || !out) return ZR_ERR_INVALID_ARG;
+        *out = zr_image2d{ p->d_tex[p->outIdx], p->width, p->height, p->width * 8u, 8u };
+        return ZR_OK;
+    }
+    void zr_taa_pass_destroy(zr_taa_pass* p) { if (p) { p->Release(); delete p; } }
+}
