@@ -1,0 +1,60 @@
+"""Loads scene fixtures and builds the oracle-side scene (CPU) for tests, smoke() and bench.py's cpu_baseline."""
+import ctypes as C
+import os
+import numpy as np
+
+from zetaray_b200 import scene as zscene
+from tests import orc
+from tests.orc import ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ALIAS = np.dtype([("CachedP_Orig", "<f4"), ("CachedP_Alias", "<f4"), ("P_Curr", "<f4"), ("Alias", "<u4")])
+
+
+def cornell():
+    return zscene.FlatScene.load(os.path.join(GOLDEN, "cornell_emissive.npz"))
+
+
+def glossy_cornell():
+    """Cornell variant exercising k > 2 reconnections, metals, coat and glass (not a reference asset)."""
+    s = cornell()
+    m = s.materials.copy()
+    # short box: rough metal; tall box: glossy dielectric below alpha_min; back wall: coated
+    m[7] = zscene.make_material(base_color=(0.95, 0.64, 0.54, 1), metallic=1.0, roughness=0.25, double_sided=True)
+    m[8] = zscene.make_material(base_color=(0.725, 0.71, 0.68, 1), roughness=0.1, double_sided=True)
+    m[3] = zscene.make_material(base_color=(0.2, 0.3, 0.7, 1), roughness=0.6, coat_weight=1.0, coat_roughness=0.1,
+                                coat_color=(0.9, 0.9, 0.9), double_sided=True)
+    s.materials = m
+    return s
+
+
+class OracleScene:
+    def __init__(self, flat):
+        self.o = orc.load()
+        self.flat = flat
+        lut_path = os.path.join(ROOT, "zetaray_b200", "assets", "rho_lut.bin")
+        self.lut = np.fromfile(lut_path, dtype=np.uint16)
+        assert self.lut.size == 64 * 32 * 16
+        self.o.orc_set_rho_lut(ptr(self.lut))
+        self.alias = np.zeros(max(len(flat.emissives), 1), dtype=ALIAS)
+        self.o.orc_scene_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.o.orc_scene_create(ptr(flat.vertices), ptr(flat.indices), ptr(flat.instances),
+                                                    len(flat.instances), ptr(flat.instance_num_tris), ptr(flat.materials),
+                                                    ptr(flat.emissives) if len(flat.emissives) else None, len(flat.emissives),
+                                                    ptr(self.alias)))
+        if len(flat.emissives):
+            self.power = np.zeros(len(flat.emissives), dtype=np.float32)
+            self.o.orc_estimate_power(self.h, ptr(self.power))
+            w = self.power.copy()
+            self.o.orc_alias_build_emissive(ptr(w), C.c_int64(len(w)), 0, ptr(self.alias))
+
+    def gbuffer(self, fc, tridiff=False, nthreads=8):
+        n = fc.RenderWidth * fc.RenderHeight
+        core = np.zeros((n, 4), dtype=np.uint32)
+        depth = np.zeros(n, dtype=np.float32)
+        me = np.zeros((n, 2), dtype=np.uint32)
+        coat = np.zeros((n, 2), dtype=np.uint32)
+        td = np.zeros((n, 6), dtype=np.uint32) if tridiff else None
+        self.o.orc_gbuffer(self.h, C.byref(fc), ptr(core), ptr(depth), ptr(me), ptr(coat), ptr(td) if tridiff else None, nthreads)
+        return core, depth, me, coat, td

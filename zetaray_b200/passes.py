@@ -1,0 +1,230 @@
+"""Host-side mirrors of the reference's pass objects over the C-ABI (thin; no compute here).
+
+Names follow ZetaRenderPass: GBufferRT, PreLighting, DirectLighting, IndirectLighting, Compositing,
+TAA -- each with the reference's verbs (Init in the constructor, OnWindowResized, Render, GetOutput)."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    """Flat scene buffers + BVH on the device (zr_scene)."""
+
+    def __init__(self, flat):
+        self.flat = flat
+        d = _lib.SceneDesc()
+        self._keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances,
+                                                        flat.instance_num_tris, flat.materials, flat.emissives)]
+        v, i, inst, nt, m, e = self._keep
+        d.h_vertices, d.num_vertices = _vp(v), len(v)
+        d.h_indices, d.num_indices = _vp(i), len(i)
+        d.h_instances, d.num_instances = _vp(inst), len(inst)
+        d.h_instance_num_tris = _vp(nt)
+        d.h_materials, d.num_materials = _vp(m), len(m)
+        d.h_emissives, d.num_emissives = (_vp(e) if len(e) else None), len(e)
+        self.handle = C.c_void_p()
+        check(lib.zr_scene_create(C.byref(d), C.byref(self.handle)))
+
+    def bvh_stats(self):
+        out = (C.c_uint32 * 4)()
+        check(lib.zr_scene_bvh_stats(self.handle, out))
+        return dict(nodes=out[0], tris=out[1], max_depth=out[2], bytes=out[3])
+
+    def prelighting(self, stream=None):
+        check(lib.zr_prelighting_render(self.handle, stream))
+
+    def alias_table(self):
+        p = C.c_void_p()
+        n = C.c_uint32()
+        check(lib.zr_scene_get_alias_table(self.handle, C.byref(p), C.byref(n)))
+        out = np.zeros(n.value, dtype=np.dtype([("CachedP_Orig", "<f4"), ("CachedP_Alias", "<f4"), ("P_Curr", "<f4"), ("Alias", "<u4")]))
+        if n.value:
+            check(lib.zr_memcpy_d2h(_vp(out), p, C.c_size_t(out.nbytes), None))
+            check(lib.zr_stream_synchronize(None))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib.zr_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GBuffers:
+    """The renderer-owned, double-buffered G-buffer planes (DefaultRendererImpl.h:111-121)."""
+
+    def __init__(self, w, h, with_tridiff=False):
+        self.w, self.h = w, h
+        self.g = [_lib.GBuffer(), _lib.GBuffer()]
+        for g in self.g:
+            check(lib.zr_gbuffer_alloc(w, h, int(with_tridiff), C.byref(g)))
+        self.curr = 0
+
+    def flip(self):
+        self.curr ^= 1
+
+    def fill_inputs(self, fi):
+        fi.curr = self.g[self.curr]
+        fi.prev = self.g[self.curr ^ 1]
+
+    def download(self, which="curr"):
+        g = self.g[self.curr if which == "curr" else self.curr ^ 1]
+        n = self.w * self.h
+        core = np.zeros((n, 4), dtype=np.uint32)
+        depth = np.zeros(n, dtype=np.float32)
+        me = np.zeros((n, 2), dtype=np.uint32)
+        coat = np.zeros((n, 2), dtype=np.uint32)
+        for arr, p in ((core, g.d_core), (depth, g.d_depth), (me, g.d_motion_emissive), (coat, g.d_coat)):
+            check(lib.zr_memcpy_d2h(_vp(arr), C.c_void_p(p), C.c_size_t(arr.nbytes), None))
+        td = None
+        if g.d_tridiff:
+            td = np.zeros((n, 6), dtype=np.uint32)
+            check(lib.zr_memcpy_d2h(_vp(td), C.c_void_p(g.d_tridiff), C.c_size_t(td.nbytes), None))
+        check(lib.zr_stream_synchronize(None))
+        return core, depth, me, coat, td
+
+    def close(self):
+        for g in self.g:
+            lib.zr_gbuffer_free(C.byref(g))
+
+
+def download_image(img, dtype, comps):
+    out = np.zeros((img.width * img.height, comps), dtype=dtype)
+    assert out.nbytes == img.height * img.pitch_bytes, (out.nbytes, img.height, img.pitch_bytes)
+    check(lib.zr_memcpy_d2h(_vp(out), C.c_void_p(img.d_ptr), C.c_size_t(out.nbytes), None))
+    check(lib.zr_stream_synchronize(None))
+    return out
+
+
+class _Pass:
+    prefix = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                getattr(lib, self.prefix + "_destroy")(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class GBufferRT(_Pass):
+    prefix = "zr_gbuffer_pass"
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        check(lib.zr_gbuffer_pass_create(C.byref(self.handle)))
+
+    def Render(self, fi, stream=None):
+        check(lib.zr_gbuffer_pass_render(self.handle, C.byref(fi), stream))
+
+
+class DirectLighting(_Pass):
+    prefix = "zr_direct_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_direct_pass_create(w, h, C.byref(self.handle)))
+        self.params = _lib.DirectParams()
+        check(lib.zr_direct_pass_default_params(C.byref(self.params)))
+
+    def SetParams(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        check(lib.zr_direct_pass_set_params(self.handle, C.byref(self.params)))
+
+    def OnWindowResized(self, w, h):
+        check(lib.zr_direct_pass_resize(self.handle, w, h))
+
+    def ResetTemporal(self):
+        check(lib.zr_direct_pass_reset_temporal(self.handle))
+
+    def Render(self, fi, stream=None):
+        check(lib.zr_direct_pass_render(self.handle, C.byref(fi), stream))
+
+    def GetOutput(self, which=0):
+        img = _lib.Image2D()
+        check(lib.zr_direct_pass_get_output(self.handle, which, C.byref(img)))
+        return img
+
+
+class IndirectLighting(_Pass):
+    prefix = "zr_indirect_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_indirect_pass_create(w, h, C.byref(self.handle)))
+        self.params = _lib.IndirectParams()
+        check(lib.zr_indirect_pass_default_params(C.byref(self.params)))
+
+    def SetParams(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        check(lib.zr_indirect_pass_set_params(self.handle, C.byref(self.params)))
+
+    def OnWindowResized(self, w, h):
+        check(lib.zr_indirect_pass_resize(self.handle, w, h))
+
+    def ResetTemporal(self):
+        check(lib.zr_indirect_pass_reset_temporal(self.handle))
+
+    def SetRows(self, y0, y1):
+        check(lib.zr_indirect_pass_set_rows(self.handle, y0, y1))
+
+    def Render(self, fi, stream=None, until=0):
+        if until:
+            check(lib.zr_indirect_pass_render_until(self.handle, C.byref(fi), until, stream))
+        else:
+            check(lib.zr_indirect_pass_render(self.handle, C.byref(fi), stream))
+
+    def GetOutput(self, which=0):
+        img = _lib.Image2D()
+        check(lib.zr_indirect_pass_get_output(self.handle, which, C.byref(img)))
+        return img
+
+
+class Compositing(_Pass):
+    prefix = "zr_compositing_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_compositing_pass_create(w, h, C.byref(self.handle)))
+
+    def SetParams(self, emissive_di=1, indirect=1, firefly_filter=1):
+        p = _lib.CompositingParams(emissive_di, indirect, firefly_filter)
+        check(lib.zr_compositing_pass_set_params(self.handle, C.byref(p)))
+
+    def Render(self, fi, d_direct, d_indirect, stream=None):
+        check(lib.zr_compositing_pass_render(self.handle, C.byref(fi), C.c_void_p(d_direct), C.c_void_p(d_indirect), stream))
+
+    def GetOutput(self):
+        img = _lib.Image2D()
+        check(lib.zr_compositing_pass_get_output(self.handle, C.byref(img)))
+        return img
+
+
+class TAA(_Pass):
+    prefix = "zr_taa_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_taa_pass_create(w, h, C.byref(self.handle)))
+
+    def Render(self, fi, d_signal, stream=None):
+        check(lib.zr_taa_pass_render(self.handle, C.byref(fi), C.c_void_p(d_signal), stream))
+
+    def GetOutput(self):
+        img = _lib.Image2D()
+        check(lib.zr_taa_pass_get_output(self.handle, C.byref(img)))
+        return img
