@@ -1,0 +1,101 @@
+"""Drives the CPU oracle through whole frames (G-buffer -> ReSTIR DI / PT -> post) for parity tests,
+smoke() and bench.py's cpu_baseline leg."""
+import ctypes as C
+import os
+import numpy as np
+
+from tests import scene_util, synth
+from tests.orc import ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RES = np.dtype([("meta", "<u4"), ("w_sum", "<f4"), ("W", "<f4"), ("L_b", "<u4"),
+                ("jacobian_or_seed_nee", "<u4"), ("seed_replay", "<u4"), ("ID", "<u4"), ("x_k_x", "<u4"),
+                ("x_k_y", "<u4"), ("x_k_z", "<u4"), ("w_k", "<u4"), ("L_rg", "<u4"),
+                ("lightPdf", "<f4"), ("dwdA", "<f4"), ("seed_nee", "<u4"), ("meshIdx", "<u4")])
+assert RES.itemsize == 64
+
+
+class RptParams(C.Structure):
+    _fields_ = [("max_non_tr_bounces", C.c_uint32), ("max_glossy_tr_bounces", C.c_uint32), ("russian_roulette", C.c_uint32),
+                ("temporal_resample", C.c_uint32), ("num_spatial_passes", C.c_uint32), ("M_max_temporal", C.c_uint32),
+                ("M_max_spatial", C.c_uint32), ("boiling_suppression", C.c_uint32), ("sort_temporal", C.c_uint32),
+                ("sort_spatial", C.c_uint32), ("alpha_min", C.c_float)]
+
+
+def default_rpt_params():
+    # IndirectLighting.h:231-244, IndirectLighting.cpp:146-165
+    return RptParams(3, 4, 1, 1, 1, 10, 8, 1, 1, 1, np.float32(0.175) * np.float32(0.175))
+
+
+class RptBuffers(C.Structure):
+    _fields_ = [("res0", C.c_void_p), ("res1", C.c_void_p), ("target", C.c_void_p), ("final", C.c_void_p),
+                ("neighbor", C.c_void_p), ("tmCtN", C.c_void_p), ("tmNtC", C.c_void_p)]
+
+
+def halton(i, b):
+    f = np.float32(1.0); r = np.float32(0.0); bf = np.float32(b)
+    while i > 0:
+        f = np.float32(f / bf)
+        r = np.float32(r + f * np.float32(i % b))
+        i = int(np.float32(i) / bf)
+    return r
+
+
+class FrameSequence:
+    """cbFrameConstants for consecutive frames of a static camera: jitter = Halton(2,3) - 0.5
+    over an 8-phase cycle, prev* = last frame's curr*."""
+
+    def __init__(self, w, h, jitter=True, first_frame=1):
+        self.w, self.h, self.jitter = w, h, jitter
+        self.frame = first_frame - 1
+        self.prev_jitter = (0.0, 0.0)
+
+    def next(self):
+        self.frame += 1
+        j = (0.0, 0.0)
+        if self.jitter:
+            ph = self.frame % 8
+            j = (float(halton(ph + 1, 2) - np.float32(0.5)), float(halton(ph + 1, 3) - np.float32(0.5)))
+        fc = synth.look_at_frame_constants(self.w, self.h, frame=self.frame, jitter=j, prev_jitter=self.prev_jitter)
+        self.prev_jitter = j
+        return fc
+
+
+class OracleRenderer:
+    """Reference-shaped frame loop on the CPU oracle."""
+
+    def __init__(self, flat, w, h, nthreads=8):
+        self.osc = scene_util.OracleScene(flat)
+        self.o = self.osc.o
+        self.w, self.h, self.nthreads = w, h, nthreads
+        n = w * h
+        self.pattern = np.fromfile(os.path.join(ROOT, "zetaray_b200", "assets", "disk512.bin"), dtype=np.float32)
+        assert self.pattern.size == 1024
+        self.o.orc_rpt_set_sample_pattern(ptr(self.pattern))
+        self.cur = 0
+        self.res = [np.zeros(n, dtype=RES), np.zeros(n, dtype=RES)]
+        self.target = np.zeros((n, 4), dtype=np.float32)
+        self.final = np.zeros((n, 4), dtype=np.float32)
+        self.neighbor = np.zeros(n, dtype=np.uint16)
+        self.tmCtN = np.zeros(n, dtype=np.uint16)
+        self.tmNtC = np.zeros(n, dtype=np.uint16)
+        self.state = np.array([0, 0, 1], dtype=np.uint32)     # currTemporalIdx, temporalValid, resetFlag
+        self.params = default_rpt_params()
+        empty = (np.zeros((n, 4), np.uint32), np.zeros(n, np.float32), np.zeros((n, 2), np.uint32), np.zeros((n, 2), np.uint32), None)
+        self.gb = [empty, empty]
+
+    def gbuffer(self, fc):
+        self.cur ^= 1
+        self.gb[self.cur] = self.osc.gbuffer(fc, tridiff=False, nthreads=self.nthreads)
+        return self.gb[self.cur]
+
+    def rpt(self, fc, last_stage=0):
+        c = self.gb[self.cur]; p = self.gb[self.cur ^ 1]
+        b = RptBuffers(self.res[0].ctypes.data, self.res[1].ctypes.data, self.target.ctypes.data, self.final.ctypes.data,
+                       self.neighbor.ctypes.data, self.tmCtN.ctypes.data, self.tmNtC.ctypes.data)
+        self.o.orc_rpt_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]),
+                              C.byref(self.params), C.byref(b), ptr(self.state), last_stage, self.nthreads)
+
+    def curr_reservoirs(self):
+        """The buffer holding this frame's output == next frame's 'previous' (state[0] was advanced)."""
+        return self.res[1 - int(self.state[0])]
