@@ -27,6 +27,21 @@ def default_rpt_params():
     return RptParams(3, 4, 1, 1, 1, 10, 8, 1, 1, 1, np.float32(0.175) * np.float32(0.175))
 
 
+RDI = np.dtype([("bary", "<u4"), ("le_rg", "<u4"), ("le_b_meta", "<u4"), ("lightIdx", "<u4"), ("w_sum", "<f4"), ("W", "<f4"),
+                ("pad0", "<u4"), ("pad1", "<u4")])
+assert RDI.itemsize == 32
+
+
+class RdiParams(C.Structure):
+    _fields_ = [("temporal_resample", C.c_uint32), ("spatial_resample", C.c_uint32), ("stochastic_spatial", C.c_uint32),
+                ("extra_disocclusion_sampling", C.c_uint32), ("M_max", C.c_uint32), ("alpha_min", C.c_float)]
+
+
+def default_rdi_params():
+    # DirectLighting.cpp:99-107, DirectLighting.h:93-98
+    return RdiParams(1, 1, 1, 1, 20, np.float32(0.05) * np.float32(0.05))
+
+
 class RptBuffers(C.Structure):
     _fields_ = [("res0", C.c_void_p), ("res1", C.c_void_p), ("target", C.c_void_p), ("final", C.c_void_p),
                 ("neighbor", C.c_void_p), ("tmCtN", C.c_void_p), ("tmNtC", C.c_void_p)]
@@ -81,6 +96,14 @@ class OracleRenderer:
         self.tmNtC = np.zeros(n, dtype=np.uint16)
         self.state = np.array([0, 0, 1], dtype=np.uint32)     # currTemporalIdx, temporalValid, resetFlag
         self.params = default_rpt_params()
+        self.pattern32 = np.fromfile(os.path.join(ROOT, "zetaray_b200", "assets", "disk32.bin"), dtype=np.float32)
+        assert self.pattern32.size == 64
+        self.o.orc_rdi_set_sample_pattern(ptr(self.pattern32))
+        self.di_res = [np.zeros(n, dtype=RDI), np.zeros(n, dtype=RDI)]
+        self.di_target = np.zeros((n, 2), dtype=np.uint32)
+        self.di_final = np.zeros((n, 4), dtype=np.float32)
+        self.di_state = np.array([0, 0, 1], dtype=np.uint32)
+        self.di_params = default_rdi_params()
         empty = (np.zeros((n, 4), np.uint32), np.zeros(n, np.float32), np.zeros((n, 2), np.uint32), np.zeros((n, 2), np.uint32), None)
         self.gb = [empty, empty]
 
@@ -95,6 +118,29 @@ class OracleRenderer:
                        self.neighbor.ctypes.data, self.tmCtN.ctypes.data, self.tmNtC.ctypes.data)
         self.o.orc_rpt_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]),
                               C.byref(self.params), C.byref(b), ptr(self.state), last_stage, self.nthreads)
+
+    def rdi(self, fc):
+        c = self.gb[self.cur]; p = self.gb[self.cur ^ 1]
+        self.o.orc_rdi_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]), C.byref(self.di_params),
+                              ptr(self.di_res[0]), ptr(self.di_res[1]), ptr(self.di_target), ptr(self.di_final), ptr(self.di_state),
+                              self.nthreads)
+
+    def di_curr_reservoirs(self):
+        return self.di_res[1 - int(self.di_state[0])]
+
+    def post(self, fc, taa_prev, taa_valid, firefly=True):
+        """Compositing (+ firefly) and TAA on the oracle; returns (composited float4, taa half4)."""
+        n = self.w * self.h
+        c = self.gb[self.cur]
+        comp = np.zeros((n, 4), dtype=np.float32)
+        self.o.orc_compositing(C.byref(fc), ptr(c[0]), ptr(self.di_final), ptr(self.final), ptr(comp))
+        if firefly:
+            out = np.zeros((n, 4), dtype=np.float32)
+            self.o.orc_firefly(C.byref(fc), ptr(c[0]), ptr(comp), ptr(out))
+            comp = out
+        taa = np.zeros((n, 2), dtype=np.uint32)
+        self.o.orc_taa(C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(comp), ptr(taa_prev), ptr(taa), C.c_float(0.1), int(taa_valid))
+        return comp, taa
 
     def curr_reservoirs(self):
         """The buffer holding this frame's output == next frame's 'previous' (state[0] was advanced)."""

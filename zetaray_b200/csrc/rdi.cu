@@ -1,0 +1,793 @@
+// rdi.cu -- ReSTIR DI for emissive triangles and the DirectLighting pass.
+//
+// Replaces DirectLighting/Emissive/ReSTIR_DI_Temporal.hlsl:29-390, ReSTIR_DI_Spatial.hlsl:27-192,
+// Resampling.hlsli:36-519, PairwiseMIS.hlsli:10-232, Reservoir.hlsli:10-213, Util.hlsli:9-120 and the host
+// sequencing of DirectLighting.cpp:166-284 (compiled configuration: USE_HALF_VECTOR_COPY_SHIFT 0, alias-table
+// candidates, no presampled sets).
+//
+// Layout: the reservoir's two textures (RGBA32UI + RG32F, 24 B/px) are one 32-byte record = 2 x 128-bit;
+// the RGBA16F target plane is a uint2 (8 B/px). k_di_spatial keeps the reference's 8x8 group / swizzle so one
+// warp is one reference wave (the disocclusion vote is a wave op) and the group RNG is seeded by the block id.
+#include "zr_pixel.cuh"
+
+namespace zr
+{
+namespace
+{
+    struct DIParams { uint32_t temporal, spatial, stochasticSpatial, extraDisocclusion, M_max; float alpha_min; uint32_t reset; };
+
+    __constant__ float c_disk32[64];
+
+struct Reservoir
+{
+    float w_sum, W; float3 le; uint32_t lightIdx; float2 bary; uint32_t M;
+    float3 target; uint32_t lightID; float3 lightPos, lightNormal; bool doubleSided;
+
+    static ZR_D Reservoir Init()
+    {
+        Reservoir r;
+        r.le = f3(0); r.M = 0; r.w_sum = 0; r.W = 0; r.lightIdx = UINT32_MAX_; r.bary = f2(0, 0);
+        r.target = f3(0); r.lightID = UINT32_MAX_; r.lightPos = f3(0); r.lightNormal = f3(0); r.doubleSided = false;
+        return r;
+    }
+    ZR_D bool Update(float weight, float3 le_, uint32_t lightIdx_, float2 bary_, RNG& rng)
+    {
+        if (weight != weight) return false;
+        M += 1;
+        if (weight == 0) return false;
+        w_sum += weight;
+        if (rng.Uniform() < (weight / w_sum))
+        {
+            le = le_; lightIdx = lightIdx_; bary = bary_;
+            return true;
+        }
+        return false;
+    }
+    static ZR_D Reservoir Load(const zr_rdi_reservoir& s)
+    {
+        Reservoir r = Init();
+        r.le = f3(half_lo(s.le_rg), half_hi(s.le_rg), half_lo(s.le_b_meta));
+        r.M = (s.le_b_meta >> 16) & 0x1f;
+        r.w_sum = s.w_sum; r.W = s.W;
+        r.lightIdx = s.lightIdx;
+        r.bary = Math::DecodeUNorm2(s.bary);
+        return r;
+    }
+    ZR_D void Write(zr_rdi_reservoir& s, uint32_t M_max) const
+    {
+        uint32_t M_capped = M < M_max ? M : M_max;
+        s.bary = Math::EncodeUNorm2(bary);
+        s.le_rg = pack_half2(le.x, le.y);
+        s.le_b_meta = (uint32_t)zr_f32_to_f16(le.z) | (M_capped << 16);
+        s.lightIdx = lightIdx;
+        s.w_sum = w_sum; s.W = W;
+        s.pad[0] = 0; s.pad[1] = 0;
+    }
+};
+
+// RGBA16F target plane
+ZR_D void WriteTarget(uint2* target, size_t idx, float3 t)
+{
+    t = Math::Sanitize(t);
+    target[idx] = make_uint2(pack_half2(t.x, t.y), pack_half2(t.z, 0.0f));
+}
+ZR_D float3 LoadTarget(const uint2* target, size_t idx)
+{
+    uint2 p = target[idx];
+    return f3(half_lo(p.x), half_hi(p.x), half_lo(p.y));
+}
+
+struct BSDFHitInfo { uint32_t emissiveTriIdx; float2 bary; float3 lightPos; float t; bool hit; };
+
+// Util.hlsli:68-120
+ZR_D BSDFHitInfo FindClosestHitDI(const SceneDev& sc, float3 pos, float3 normal, float3 wi, bool transmissive)
+{
+    BSDFHitInfo ret;
+    ret.hit = false; ret.emissiveTriIdx = UINT32_MAX_; ret.bary = f2(0, 0); ret.lightPos = f3(0); ret.t = 0;
+    float ndotwi = dot(normal, wi);
+    if (ndotwi == 0) return ret;
+    bool wiBackface = ndotwi < 0;
+    if (wiBackface)
+    {
+        if (transmissive) normal = -normal;
+        else return ret;
+    }
+    const float3 adjustedOrigin = RTU::OffsetRayRTG(pos, normal);
+    RayHit h = TraceClosest(sc, adjustedOrigin, wi, wiBackface ? 3e-4f : 0.0f, FLT_MAX_);
+    if (h.hit)
+    {
+        const uint32_t meshIdx = __ldg(&sc.triMesh[h.tri]);
+        const uint32_t baseEmissive = __ldg(&sc.instances[meshIdx].BaseEmissiveTriOffset);
+        if (baseEmissive == UINT32_MAX_)
+            return ret;
+        ret.emissiveTriIdx = baseEmissive + (h.tri - __ldg(&sc.meshFirstTri[meshIdx]));
+        ret.bary = h.bary;
+        ret.lightPos = mad(h.t, wi, adjustedOrigin);
+        ret.t = h.t;
+        ret.hit = true;
+    }
+    return ret;
+}
+
+// Util.hlsli:9-57
+struct EmissiveData
+{
+    float3 wi; float t; uint32_t ID; float3 lightPos, lightNormal; bool doubleSided;
+    static ZR_D EmissiveData Init(const SceneDev& sc, uint32_t lightIdx, float2 bary)
+    {
+        EmissiveData ret;
+        const zr_emissive_tri& tri = sc.emissives[lightIdx];
+        ret.ID = tri.ID;
+        const float3 vtx0 = Light::Vtx0(tri);
+        const float3 vtx1 = Light::DecodeEmissiveTriV1(tri);
+        const float3 vtx2 = Light::DecodeEmissiveTriV2(tri);
+        ret.lightPos = (1.0f - bary.x - bary.y) * vtx0 + bary.x * vtx1 + bary.y * vtx2;
+        ret.lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
+        ret.lightNormal = dot(ret.lightNormal, ret.lightNormal) == 0 ? ret.lightNormal : normalize(ret.lightNormal);
+        ret.doubleSided = Light::IsDoubleSided(tri);
+        ret.wi = f3(0); ret.t = 0;
+        return ret;
+    }
+    ZR_D void SetSurfacePos(float3 pos)
+    {
+        wi = lightPos - pos;
+        t = dot(wi, wi) == 0 ? 0 : length(wi);
+        wi = t == 0 ? f3(0) : wi / t;
+        lightNormal = doubleSided && dot(-wi, lightNormal) < 0 ? -lightNormal : lightNormal;
+    }
+    ZR_D float dWdA() const
+    {
+        float cosThetaPrime = saturate(dot(lightNormal, -wi));
+        return t == 0 ? 0 : cosThetaPrime / (t * t);
+    }
+};
+
+ZR_D Reservoir RIS_InitialCandidates(const SceneDev& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface,
+    int numBsdfSamples, RNG& rng)
+{
+    Reservoir r = Reservoir::Init();
+    const bool specular = surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
+    const int numLightSamples = !specular ? 3 : 0;
+    for (int s_b = 0; s_b < numBsdfSamples; s_b++)
+    {
+        BSDF::BSDFSample bsdfSample = BSDF::SampleBSDF_NoDiffuse(normal, surface, rng);
+        float3 wi = bsdfSample.wi;
+        float pdf_w = bsdfSample.pdf;
+        BSDFHitInfo hitInfo = FindClosestHitDI(sc, pos, normal, wi, surface.Transmissive());
+        float w_b = 0;
+        float3 le = f3(0), lightNormal = f3(0), target = f3(0);
+        uint32_t emissiveID = UINT32_MAX_;
+        bool doubleSided = false;
+        if (hitInfo.hit)
+        {
+            const zr_emissive_tri& emissive = sc.emissives[hitInfo.emissiveTriIdx];
+            le = Light::Le_EmissiveTriangle(emissive);
+            const float3 vtx0 = Light::Vtx0(emissive);
+            const float3 vtx1 = Light::DecodeEmissiveTriV1(emissive);
+            const float3 vtx2 = Light::DecodeEmissiveTriV2(emissive);
+            lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
+            float twoArea = length(lightNormal);
+            lightNormal = dot(lightNormal, lightNormal) == 0 ? f3(0) : lightNormal / twoArea;
+            lightNormal = Light::IsDoubleSided(emissive) && dot(-wi, lightNormal) < 0 ? -lightNormal : lightNormal;
+            doubleSided = Light::IsDoubleSided(emissive);
+            emissiveID = emissive.ID;
+            if (dot(-wi, lightNormal) > 0)
+            {
+                const float lightSourcePdf = sc.aliasTable[hitInfo.emissiveTriIdx].CachedP_Orig;
+                const float pdf_light = lightSourcePdf * (1.0f / (0.5f * twoArea));
+                const float dwdA = saturate(dot(lightNormal, -wi)) / (hitInfo.t * hitInfo.t);
+                pdf_w *= dwdA;
+                const bool sampleIsSpecular = (surface.GlossSpecular() && bsdfSample.lobe == BSDF::GLOSSY_R) ||
+                    (surface.CoatSpecular() && bsdfSample.lobe == BSDF::COAT);
+                float denom = (float)numBsdfSamples * pdf_w + (!sampleIsSpecular ? 1.0f : 0.0f) * (float)numLightSamples * pdf_light;
+                const float m_i = 1.0f / denom;
+                target = le * bsdfSample.f * dwdA;
+                w_b = m_i * Math::Luminance(target);
+            }
+        }
+        if (r.Update(w_b, le, hitInfo.emissiveTriIdx, hitInfo.bary, rng))
+        {
+            r.target = target; r.lightID = emissiveID; r.lightPos = hitInfo.lightPos; r.lightNormal = lightNormal; r.doubleSided = doubleSided;
+        }
+    }
+    for (int s_l = 0; s_l < numLightSamples; s_l++)
+    {
+        Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+        const zr_emissive_tri& tri = sc.emissives[entry.idx];
+        Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
+        float3 le = Light::Le_EmissiveTriangle(tri);
+        const float pdf_light = entry.pdf * lightSample.pdf;
+        const uint32_t emissiveIdx = entry.idx;
+        const uint32_t lightID = tri.ID;
+        const bool doubleSided = Light::IsDoubleSided(tri);
+        float3 target = f3(0);
+        float3 wi = lightSample.pos - pos;
+        const bool isZero = dot(wi, wi) == 0;
+        const float t = isZero ? 0 : length(wi);
+        wi = isZero ? wi : wi / t;
+        const float dwdA = isZero ? 0 : saturate(dot(lightSample.normal, -wi)) / (t * t);
+        surface.SetWi(wi, normal);
+        if (dot(lightSample.normal, -wi) > 0)
+        {
+            target = le * BSDF::Unified(surface).f * dwdA;
+            if (dot(target, target) > 0)
+                target *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
+        }
+        const float denom = (float)numLightSamples * pdf_light + (float)numBsdfSamples * BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi) * dwdA;
+        const float m_l = denom > 0 ? 1.0f / denom : 0;
+        const float w_l = m_l * Math::Luminance(target);
+        if (r.Update(w_l, le, emissiveIdx, lightSample.bary, rng))
+        {
+            r.target = target; r.lightID = lightID; r.lightNormal = lightSample.normal; r.lightPos = lightSample.pos; r.doubleSided = doubleSided;
+        }
+    }
+    float targetLum = Math::Luminance(r.target);
+    r.W = targetLum > 0.0f ? r.w_sum / targetLum : 0.0f;
+    return r;
+}
+
+ZR_D bool PlaneHeuristicDI(float3 samplePos, float3 currNormal, float3 currPos, float linearDepth, float tolerance = 1e-1f)
+{
+    float planeDist = dot(currNormal, samplePos - currPos);
+    return fabsf(planeDist) <= tolerance * linearDepth;
+}
+
+struct TemporalCandidate { BSDF::ShadingData surface; float3 pos, normal; int px, py; bool valid; };
+
+ZR_D TemporalCandidate FindTemporalCandidate(const FrameView& f, const SceneDev& sc, float3 pos, float3 normal, float roughness, const BSDF::ShadingData& surface, float2 prevUV)
+{
+    TemporalCandidate c; c.valid = false; c.px = c.py = 0; c.pos = c.normal = f3(0);
+    if (prevUV.x < 0.0f || prevUV.y < 0.0f || prevUV.x > 1.0f || prevUV.y > 1.0f) return c;
+    const float2 renderDim = f2((float)f.W, (float)f.H);
+    float2 pp = prevUV * renderDim;
+    int ppx = (int)pp.x, ppy = (int)pp.y;
+    float prevRoughness;
+    GFlags prevFlags = FlagsAt(f.pcore, f.W, ppx, ppy, &prevRoughness);
+    if (prevFlags.invalid || prevFlags.emissive || (fabsf(prevRoughness - roughness) > 0.15f) ||
+        (prevFlags.metallic != surface.metallic) || (prevFlags.transmissive != surface.specTr))
+        return c;
+    Pixel p = LoadPixel(f, sc, f.pcore, f.pcoat, ppx, ppy, true, ppx, ppy);
+    // note: the depth passed to the plane test is the PREVIOUS pixel's (Resampling.hlsli:77)
+    if (!PlaneHeuristicDI(p.pos, normal, pos, p.z))
+        return c;
+    c.surface = p.surface; c.px = ppx; c.py = ppy; c.pos = p.pos; c.normal = p.normal; c.valid = true;
+    return c;
+}
+
+ZR_D float OffsetPathTarget_CtT(const SceneDev& sc, const Reservoir& r_curr, TemporalCandidate candidate)
+{
+    float3 wi_offset = r_curr.lightPos - candidate.pos;
+    const bool isZero = dot(wi_offset, wi_offset) == 0;
+    float t_offset = isZero ? 0 : length(wi_offset);
+    wi_offset = isZero ? wi_offset : wi_offset / t_offset;
+    candidate.surface.SetWi(wi_offset, candidate.normal);
+    float3 lightNormal = r_curr.lightNormal;
+    if (r_curr.doubleSided && dot(-wi_offset, lightNormal) < 0)
+        lightNormal = -lightNormal;
+    float cosThetaPrime = saturate(dot(lightNormal, -wi_offset));
+    const float dwdA = isZero ? 0 : cosThetaPrime / (t_offset * t_offset);
+    float3 target_offset = r_curr.le * dwdA;
+    target_offset *= BSDF::Unified(candidate.surface).f;
+    float targetLum_offset = Math::Luminance(target_offset);
+    if (targetLum_offset > 0)
+        targetLum_offset *= Visibility_Segment(sc, candidate.pos, wi_offset, t_offset, candidate.normal, r_curr.lightID,
+            candidate.surface.Transmissive()) ? 1.0f : 0.0f;
+    return targetLum_offset;
+}
+
+ZR_D float3 OffsetPathTarget_TtC(const SceneDev& sc, const Reservoir& r_prev, float3 pos, float3 normal, BSDF::ShadingData surface)
+{
+    EmissiveData prevEmissive = EmissiveData::Init(sc, r_prev.lightIdx, r_prev.bary);
+    prevEmissive.SetSurfacePos(pos);
+    float dwdA = prevEmissive.dWdA();
+    surface.SetWi(prevEmissive.wi, normal);
+    float3 target_offset = r_prev.le * dwdA;
+    target_offset *= BSDF::Unified(surface).f;
+    if (dot(target_offset, target_offset) > 0)
+        target_offset *= Visibility_Segment(sc, pos, prevEmissive.wi, prevEmissive.t, normal, prevEmissive.ID, surface.Transmissive()) ? 1.0f : 0.0f;
+    return target_offset;
+}
+
+ZR_D void TemporalResample1(const SceneDev& sc, float3 pos, float3 normal, const BSDF::ShadingData& surface, const TemporalCandidate& candidate,
+    const zr_rdi_reservoir* prevRes, uint32_t W, Reservoir& r_curr, RNG& rng)
+{
+    Reservoir r_prev = Reservoir::Load(prevRes[(size_t)candidate.py * W + candidate.px]);
+    const uint32_t newM = r_curr.M + r_prev.M;
+    if (r_curr.w_sum != 0)
+    {
+        float targetLum_prev = OffsetPathTarget_CtT(sc, r_curr, candidate);
+        const float numerator = (float)r_curr.M * Math::Luminance(r_curr.target);
+        const float denom = numerator + (float)r_prev.M * targetLum_prev * 1.0f;
+        const float m_curr = denom > 0 ? numerator / denom : 0;
+        r_curr.w_sum *= m_curr;
+    }
+    if (r_prev.lightIdx != UINT32_MAX_)
+    {
+        const float3 target_curr = OffsetPathTarget_TtC(sc, r_prev, pos, normal, surface);
+        const float targetLum_curr = Math::Luminance(target_curr);
+        if (targetLum_curr > 0)
+        {
+            const float targetLum_prev = r_prev.W > 0 ? r_prev.w_sum / r_prev.W : 0;
+            const float numerator = (float)r_prev.M * targetLum_prev;
+            const float denom = numerator / 1.0f + (float)r_curr.M * targetLum_curr;
+            const float m_prev = denom > 0 ? numerator / denom : 0;
+            const float w_prev = m_prev * targetLum_curr * r_prev.W;
+            if (r_curr.Update(w_prev, r_prev.le, r_prev.lightIdx, r_prev.bary, rng))
+                r_curr.target = target_curr;
+        }
+    }
+    float targetLum = Math::Luminance(r_curr.target);
+    r_curr.W = targetLum > 0.0f ? r_curr.w_sum / targetLum : 0.0f;
+    r_curr.M = newM;
+}
+
+// ---- PairwiseMIS.hlsli ----
+struct PairwiseMIS
+{
+    Reservoir r_s; float m_c; float M_s; uint32_t k;
+    static ZR_D PairwiseMIS Init(uint32_t numStrategies, const Reservoir& r_c)
+    {
+        PairwiseMIS ret;
+        ret.r_s = Reservoir::Init(); ret.m_c = 1.0f; ret.M_s = to_half((float)r_c.M); ret.k = numStrategies;
+        return ret;
+    }
+    ZR_D float Compute_m_i(const Reservoir& r_c, const Reservoir& r_i, float targetLum, float jacobian) const
+    {
+        const float p_i_y_i = r_i.W > 0 ? r_i.w_sum / r_i.W : 0;
+        const float p_c_y_i = targetLum;
+        float numerator = (float)r_i.M * p_i_y_i;
+        float denom = (numerator / jacobian) + ((float)r_c.M / (float)k) * p_c_y_i;
+        return denom > 0 ? numerator / denom : 0;
+    }
+    ZR_D void Update_m_c(const Reservoir& r_c, const Reservoir& r_i, float targetLum, float jacobian)
+    {
+        const float p_i_y_c = targetLum;
+        const float p_c_y_c = Math::Luminance(r_c.target);
+        const float numerator = (float)r_i.M * p_i_y_c * jacobian;
+        const float denom = numerator + ((float)r_c.M / (float)k) * p_c_y_c;
+        m_c += 1 - (numerator / denom);
+    }
+    ZR_D void Stream(const SceneDev& sc, const Reservoir& r_c, float3 pos_c, float3 normal_c, BSDF::ShadingData surface_c, const Reservoir& r_i,
+        float3 pos_i, float3 normal_i, BSDF::ShadingData surface_i, RNG& rng)
+    {
+        float3 target_c_y_i = f3(0), target_i_y_c = f3(0.0f);
+        float m_i = 0;
+        if (r_i.lightIdx != UINT32_MAX_)
+        {
+            float jacobian_i_to_c = 1;      // IsShiftInvertible == true, halfVectorCopyShift == false
+            EmissiveData emissive_i = EmissiveData::Init(sc, r_i.lightIdx, r_i.bary);
+            emissive_i.SetSurfacePos(pos_c);
+            float dwdA = emissive_i.dWdA();
+            surface_c.SetWi(emissive_i.wi, normal_c);
+            target_c_y_i = r_i.le * dwdA;
+            if (dot(target_c_y_i, target_c_y_i) > 0)
+                target_c_y_i *= Visibility_Segment(sc, pos_c, emissive_i.wi, emissive_i.t, normal_c, emissive_i.ID, surface_c.Transmissive()) ? 1.0f : 0.0f;
+            target_c_y_i *= BSDF::Unified(surface_c).f;
+            const float targetLum = Math::Luminance(target_c_y_i);
+            m_i = Compute_m_i(r_c, r_i, targetLum, jacobian_i_to_c);
+        }
+        float jacobian_c_to_i = 0;
+        if (r_c.lightIdx != UINT32_MAX_)
+        {
+            jacobian_c_to_i = 1;
+            float3 wi_i = r_c.lightPos - pos_i;
+            const bool isZero = dot(wi_i, wi_i) == 0;
+            float t_i = isZero ? 0 : length(wi_i);
+            wi_i = isZero ? f3(0) : wi_i / t_i;
+            surface_i.SetWi(wi_i, normal_i);
+            const float3 lightNormal = dot(r_c.lightNormal, -wi_i) < 0 && r_c.doubleSided ? -r_c.lightNormal : r_c.lightNormal;
+            const float cosThetaPrime = saturate(dot(lightNormal, -wi_i));
+            const float dwdA = isZero ? 0 : cosThetaPrime / (t_i * t_i);
+            target_i_y_c = r_c.le * dwdA;
+            if (dot(target_i_y_c, target_i_y_c) > 0)
+                target_i_y_c *= Visibility_Segment(sc, pos_i, wi_i, t_i, normal_i, r_c.lightID, surface_i.Transmissive()) ? 1.0f : 0.0f;
+            target_i_y_c *= BSDF::Unified(surface_i).f;
+        }
+        const float targetLum = Math::Luminance(target_i_y_c);
+        Update_m_c(r_c, r_i, targetLum, jacobian_c_to_i);
+        if (r_i.lightIdx != UINT32_MAX_)
+        {
+            const float w_i = m_i * Math::Luminance(target_c_y_i) * r_i.W;
+            if (r_s.Update(w_i, r_i.le, r_i.lightIdx, r_i.bary, rng))
+                r_s.target = target_c_y_i;
+        }
+        M_s = to_half(M_s + (float)r_i.M);
+    }
+    ZR_D void End(const Reservoir& r_c, RNG& rng)
+    {
+        const float w_c = m_c * r_c.w_sum;
+        if (r_s.Update(w_c, r_c.le, r_c.lightIdx, r_c.bary, rng))
+            r_s.target = r_c.target;
+        r_s.M = (uint32_t)M_s;
+        const float targetLum = Math::Luminance(r_s.target);
+        r_s.W = targetLum > 0 ? r_s.w_sum / (targetLum * (1 + (float)k)) : 0;
+    }
+};
+
+
+    ZR_D void LoadRdi(const zr_rdi_reservoir* __restrict__ p, zr_rdi_reservoir& r)
+    {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 v[2] = { q[0], q[1] };
+        memcpy(&r, v, 32);
+    }
+    ZR_D void StoreRdi(zr_rdi_reservoir* __restrict__ p, const zr_rdi_reservoir& r)
+    {
+        uint4 v[2];
+        memcpy(v, &r, 32);
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = v[0]; q[1] = v[1];
+    }
+
+    ZR_D void WriteFinal(const zr_frame_constants& fc, float4* __restrict__ finalImg, size_t idx, float3 li)
+    {
+        li = isnan3(li) ? f3(0) : li;
+        if (fc.Accumulate && fc.CameraStatic && fc.NumFramesCameraStatic > 1)
+        {
+            const float4 prev = finalImg[idx];
+            finalImg[idx] = f4(prev.x + li.x, prev.y + li.y, prev.z + li.z, prev.w);
+        }
+        else
+            finalImg[idx] = f4(li.x, li.y, li.z, 0.0f);
+    }
+
+    ZR_D void WriteEmissive(const zr_frame_constants& fc, const FrameView& f, float4* __restrict__ finalImg, size_t idx)
+    {
+        const float3 le = unpack_r11g11b10(__ldg(&f.me[idx].y));
+        if (fc.Accumulate && fc.CameraStatic)
+        {
+            const float4 prev = finalImg[idx];
+            finalImg[idx] = f4(prev.x + le.x, prev.y + le.y, prev.z + le.z, prev.w);
+        }
+        else
+            finalImg[idx] = f4(le.x, le.y, le.z, 0.0f);
+    }
+
+    // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting
+    __global__ void __launch_bounds__(64) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
+        const zr_rdi_reservoir* __restrict__ resPrev, uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
+    {
+        const zr_frame_constants& fc = f.fc;
+        uint2 sg;
+        const uint2 px = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 7, threadIdx.x >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
+        if (px.x >= f.W || px.y >= f.H) return;
+        const uint32_t x = px.x, y = px.y;
+        const size_t idx = (size_t)y * f.W + x;
+        const GFlags flags = FlagsAt(f.core, f.W, x, y);
+        if (flags.invalid)
+        {
+            // the sky / sun-disk background belongs to the sun-sky path (not in this build)
+            finalImg[idx] = f4(0, 0, 0, 0);
+            return;
+        }
+        if (flags.emissive && !prm.spatial)
+        {
+            WriteEmissive(fc, f, finalImg, idx);
+            return;
+        }
+        const Pixel p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
+        RNG rng_thread = RNG::Init(x, y, fc.FrameNum);
+        const int numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
+        Reservoir r = RIS_InitialCandidates(sc, p.pos, p.normal, p.roughness, p.surface, numBsdfSamples, rng_thread);
+        if (prm.temporal)
+        {
+            const float2 motionVec = unpack_snorm16x2(__ldg(&f.me[idx].x));
+            const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / f2((float)f.W, (float)f.H);
+            const float2 prevUV = currUV - motionVec;
+            const TemporalCandidate tc = FindTemporalCandidate(f, sc, p.pos, p.normal, p.roughness, p.surface, prevUV);
+            if (tc.valid)
+                TemporalResample1(sc, p.pos, p.normal, p.surface, tc, resPrev, f.W, r, rng_thread);
+            if (prm.spatial)
+            {
+                const bool disoccluded = !tc.valid && (dot(motionVec, motionVec) > 0);
+                r.target = disoccluded ? -r.target : r.target;
+                WriteTarget(target, idx, r.target);
+                r.target = Math::Sanitize(r.target);
+            }
+        }
+        if (prm.temporal || prm.reset)
+        {
+            zr_rdi_reservoir rec;
+            r.Write(rec, prm.M_max);
+            StoreRdi(&resCurr[idx], rec);
+        }
+        if (!prm.spatial || !prm.temporal)
+            WriteFinal(fc, finalImg, idx, r.target * r.W);
+    }
+
+    // ReSTIR_DI_Spatial.hlsl main + SpatialResample
+    __global__ void __launch_bounds__(64) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
+        const uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
+    {
+        const zr_frame_constants& fc = f.fc;
+        uint2 sg;
+        const uint2 px = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 7, threadIdx.x >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
+        bool active = px.x < f.W && px.y < f.H;
+        const int x = (int)px.x, y = (int)px.y;
+        const size_t idx = (size_t)y * f.W + x;
+        if (active)
+        {
+            const GFlags flags = FlagsAt(f.core, f.W, x, y);
+            if (flags.invalid) active = false;
+            else if (flags.emissive)
+            {
+                WriteEmissive(fc, f, finalImg, idx);
+                active = false;
+            }
+        }
+        Pixel p;
+        Reservoir r = Reservoir::Init();
+        bool disoccluded = false;
+        if (active)
+        {
+            p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
+            zr_rdi_reservoir rec;
+            LoadRdi(&resCurr[idx], rec);
+            r = Reservoir::Load(rec);
+            if (r.lightIdx != UINT32_MAX_)
+            {
+                const zr_emissive_tri& tri = sc.emissives[r.lightIdx];
+                r.lightID = tri.ID;
+                const float3 vtx0 = Light::Vtx0(tri);
+                const float3 vtx1 = Light::DecodeEmissiveTriV1(tri);
+                const float3 vtx2 = Light::DecodeEmissiveTriV2(tri);
+                r.lightPos = (1.0f - r.bary.x - r.bary.y) * vtx0 + r.bary.x * vtx1 + r.bary.y * vtx2;
+                r.lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
+                r.lightNormal = dot(r.lightNormal, r.lightNormal) == 0 ? r.lightNormal : normalize(r.lightNormal);
+                r.doubleSided = Light::IsDoubleSided(tri);
+                r.target = LoadTarget(target, idx);
+                disoccluded = r.target.x < 0 || r.target.y < 0 || r.target.z < 0;
+                r.target = abs3(r.target);
+            }
+        }
+        const uint32_t waveDisoccluded = __popc(__ballot_sync(0xffffffffu, active && disoccluded));
+        if (!active) return;
+        RNG rng_group = RNG::Init(blockIdx.x, blockIdx.y, fc.FrameNum);
+        rng_group.Uniform();    // sample-set index (unused without presampled sets)
+        const bool extra = !prm.stochasticSpatial || (rng_group.Uniform() < 0.6f);
+        if (prm.extraDisocclusion)
+            disoccluded = disoccluded && (waveDisoccluded > 3);
+        int numSamples = extra ? 2 : 1;
+        numSamples = !disoccluded ? numSamples : 4;
+        RNG rng = RNG::Init((uint32_t)x, (uint32_t)y, fc.FrameNum);
+        const float u0 = rng.Uniform();
+        const int offset = (int)rng.UniformUintBounded_Faster(8);
+        const float theta = u0 * TWO_PI;
+        float sinTheta, cosTheta;
+        zr_sincosf(theta, &sinTheta, &cosTheta);
+        PairwiseMIS pairwiseMIS = PairwiseMIS::Init((uint32_t)numSamples, r);
+        float3 samplePos[4]; int spx[4], spy[4]; uint32_t k = 0;
+        for (int i = 0; i < numSamples; i++)
+        {
+            const float2 sampleUV = f2(c_disk32[((offset + i) & 31) * 2], c_disk32[((offset + i) & 31) * 2 + 1]);
+            float2 rotated;
+            rotated.x = dot(sampleUV, f2(cosTheta, -sinTheta));
+            rotated.y = dot(sampleUV, f2(sinTheta, cosTheta));
+            rotated = rotated * 16.0f;
+            const float fx = fmaxf(rintf((float)x + rotated.x), 0.0f), fy = fmaxf(rintf((float)y + rotated.y), 0.0f);
+            if (fx >= (float)f.W || fy >= (float)f.H) continue;
+            const int qx = (int)fx, qy = (int)fy;
+            float rough_i;
+            const GFlags flags_i = FlagsAt(f.core, f.W, qx, qy, &rough_i);
+            if (flags_i.invalid || flags_i.emissive) continue;
+            const Pixel pi = LoadPixel(f, sc, f.core, f.coat, qx, qy, false, qx, qy);
+            bool valid = PlaneHeuristicDI(pi.pos, p.normal, p.pos, p.z);
+            valid = valid && (fabsf(rough_i - p.roughness) < 0.15f);
+            if (!valid) continue;
+            samplePos[k] = pi.pos; spx[k] = qx; spy[k] = qy;
+            k++;
+        }
+        pairwiseMIS.k = k;
+        for (uint32_t i = 0; i < k; i++)
+        {
+            const Pixel pi = LoadPixel(f, sc, f.core, f.coat, spx[i], spy[i], false, spx[i], spy[i]);
+            // the neighbour surface is rebuilt with transmission depth = 0 (Resampling.hlsli:507-510)
+            const uint4 c = ld128(&f.core[(size_t)spy[i] * f.W + spx[i]]);
+            const float3 bc = f3((float)(c.z & 0xff) / 255.0f, (float)((c.z >> 8) & 0xff) / 255.0f, (float)((c.z >> 16) & 0xff) / 255.0f);
+            const float bw = pi.flags.subsurface ? (float)(c.z >> 24) / 255.0f : 0.0f;
+            const float3 wo_i = normalize(pi.origin - samplePos[i]);
+            const BSDF::ShadingData surface_i = BSDF::ShadingData::Init(pi.normal, wo_i, pi.flags.metallic, pi.roughness, bc, BSDF::ETA_AIR,
+                pi.eta_next, pi.flags.transmissive, 0.0f, to_half(bw), pi.surface.coat_weight, pi.surface.coat_color,
+                pi.coatRoughness, pi.coatIor, sc.rho);
+            zr_rdi_reservoir recN;
+            LoadRdi(&resCurr[(size_t)spy[i] * f.W + spx[i]], recN);
+            const Reservoir r_spatial = Reservoir::Load(recN);
+            pairwiseMIS.Stream(sc, r, p.pos, p.normal, p.surface, r_spatial, samplePos[i], pi.normal, surface_i, rng);
+        }
+        pairwiseMIS.End(r, rng);
+        const Reservoir rs = pairwiseMIS.r_s;
+        WriteFinal(fc, finalImg, idx, rs.target * rs.W);
+    }
+}
+} // namespace zr
+
+// ------------------------------------------------------------------------------------------------
+// DirectLighting pass object (DirectLighting/Emissive/DirectLighting.h:36-57)
+// ------------------------------------------------------------------------------------------------
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+struct zr_direct_pass
+{
+    uint32_t width = 0, height = 0;
+    zr_rdi_reservoir* d_res[2] = { nullptr, nullptr };
+    uint2* d_target = nullptr;      // RGBA16F
+    float4* d_final = nullptr;
+    int currTemporalIdx = 0;
+    bool isTemporalReservoirValid = false;
+    bool resetTemporalTextures = true;
+    bool patternLoaded = false;
+    zr_direct_params params{};
+
+    static void Defaults(zr_direct_params* p)
+    {
+        // DirectLighting.cpp:99-107, DirectLighting.h:93-98
+        p->temporal_resample = 1; p->spatial_resample = 1; p->stochastic_spatial = 1; p->extra_disocclusion_sampling = 1;
+        p->M_max = 20; p->alpha_min = 0.05f * 0.05f;
+    }
+    void Release()
+    {
+        for (int i = 0; i < 2; i++) { if (d_res[i]) cudaFree(d_res[i]); d_res[i] = nullptr; }
+        if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final);
+        d_target = nullptr; d_final = nullptr;
+    }
+    zr_status OnWindowResized(uint32_t w, uint32_t h)
+    {
+        Release();
+        width = w; height = h;
+        const size_t n = (size_t)w * h;
+        for (int i = 0; i < 2; i++) ZR_CUDA(cudaMalloc(&d_res[i], n * sizeof(zr_rdi_reservoir)));
+        ZR_CUDA(cudaMalloc(&d_target, n * 8));
+        ZR_CUDA(cudaMalloc(&d_final, n * 16));
+        return ResetTemporal();
+    }
+    zr_status ResetTemporal()
+    {
+        const size_t n = (size_t)width * height;
+        for (int i = 0; i < 2; i++) ZR_CUDA(cudaMemset(d_res[i], 0, n * sizeof(zr_rdi_reservoir)));
+        ZR_CUDA(cudaMemset(d_target, 0, n * 8));
+        ZR_CUDA(cudaMemset(d_final, 0, n * 16));
+        currTemporalIdx = 0; isTemporalReservoirValid = false; resetTemporalTextures = true;
+        return ZR_OK;
+    }
+    zr_status LoadPattern()
+    {
+        if (patternLoaded) return ZR_OK;
+        Dl_info info;
+        std::string dir = ".";
+        if (dladdr((void*)&zr_direct_pass::Defaults, &info) && info.dli_fname)
+        {
+            std::string p = info.dli_fname;
+            size_t s = p.find_last_of('/');
+            if (s != std::string::npos) dir = p.substr(0, s);
+        }
+        const std::string path = dir + "/assets/disk32.bin";
+        float pat[64];
+        FILE* fp = fopen(path.c_str(), "rb");
+        if (!fp || fread(pat, 4, 64, fp) != 64)
+        {
+            if (fp) fclose(fp);
+            zr::set_error("zr_direct_pass: cannot read %s (run tools/gen_sample_patterns.py)", path.c_str());
+            return ZR_ERR_NOT_INITIALIZED;
+        }
+        fclose(fp);
+        ZR_CUDA(cudaMemcpyToSymbol(zr::c_disk32, pat, 256));
+        patternLoaded = true;
+        return ZR_OK;
+    }
+    zr_status Render(const zr_frame_inputs* in, cudaStream_t stream)
+    {
+        using namespace zr;
+        if (!in || !in->scene || !in->curr.d_core || !in->curr.d_motion_emissive || !in->curr.d_coat)
+        {
+            set_error("zr_direct_pass_render: missing scene or G-buffer");
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (in->frame.RenderWidth != width || in->frame.RenderHeight != height)
+        {
+            set_error("zr_direct_pass_render: frame/pass size mismatch");
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (in->scene->dev.numEmissives == 0 || !in->scene->aliasBuilt)
+        {
+            // PathTracer.cpp:274-284: ReSTIR DI (emissive) only runs when the scene has emissive triangles
+            set_error("zr_direct_pass_render: needs emissive triangles and zr_prelighting_render first (SkyDI is not part of this build)");
+            return ZR_ERR_UNSUPPORTED;
+        }
+        zr_status st = LoadPattern();
+        if (st != ZR_OK) return st;
+        const bool doTemporal = isTemporalReservoirValid && params.temporal_resample;
+        const bool doSpatial = doTemporal && params.spatial_resample;
+        if (doTemporal && (!in->prev.d_core || !in->prev.d_coat))
+        {
+            set_error("zr_direct_pass_render: temporal reuse needs the previous G-buffer");
+            return ZR_ERR_INVALID_ARG;
+        }
+        FrameView f;
+        f.fc = in->frame;
+        f.core = (const uint4*)in->curr.d_core; f.depth = (const float*)in->curr.d_depth;
+        f.me = (const uint2*)in->curr.d_motion_emissive; f.coat = (const uint2*)in->curr.d_coat;
+        f.pcore = (const uint4*)in->prev.d_core; f.pcoat = (const uint2*)in->prev.d_coat;
+        f.W = width; f.H = height;
+        DIParams prm{ doTemporal, doSpatial, params.stochastic_spatial, params.extra_disocclusion_sampling, params.M_max,
+            params.alpha_min, resetTemporalTextures };
+        const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
+        const int cur = currTemporalIdx;
+        k_di_temporal<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
+        ZR_LAUNCH_CHECK();
+        if (doSpatial)
+        {
+            k_di_spatial<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
+            ZR_LAUNCH_CHECK();
+        }
+        isTemporalReservoirValid = true;
+        currTemporalIdx = 1 - cur;
+        resetTemporalTextures = false;
+        return ZR_OK;
+    }
+};
+
+extern "C"
+{
+    zr_status zr_direct_pass_create(uint32_t width, uint32_t height, zr_direct_pass** out)
+    {
+        if (!out || !width || !height) { zr::set_error("zr_direct_pass_create: bad args"); return ZR_ERR_INVALID_ARG; }
+        zr_direct_pass* p = new zr_direct_pass();
+        zr_direct_pass::Defaults(&p->params);
+        zr_status s = p->OnWindowResized(width, height);
+        if (s != ZR_OK) { p->Release(); delete p; return s; }
+        *out = p;
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_resize(zr_direct_pass* p, uint32_t width, uint32_t height)
+    {
+        if (!p || !width || !height) return ZR_ERR_INVALID_ARG;
+        return p->OnWindowResized(width, height);
+    }
+    zr_status zr_direct_pass_reset_temporal(zr_direct_pass* p) { return p ? p->ResetTemporal() : ZR_ERR_INVALID_ARG; }
+    zr_status zr_direct_pass_default_params(zr_direct_params* out)
+    {
+        if (!out) return ZR_ERR_INVALID_ARG;
+        zr_direct_pass::Defaults(out);
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_set_params(zr_direct_pass* p, const zr_direct_params* params)
+    {
+        if (!p || !params) return ZR_ERR_INVALID_ARG;
+        if (params->M_max == 0 || params->M_max > 31) { zr::set_error("zr_direct_pass_set_params: M_max must be in 1..31 (5-bit field)"); return ZR_ERR_INVALID_ARG; }
+        p->params = *params;
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_render(zr_direct_pass* p, const zr_frame_inputs* in, void* stream)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        return p->Render(in, (cudaStream_t)stream);
+    }
+    zr_status zr_direct_pass_get_output(zr_direct_pass* p, zr_direct_output id, zr_image2d* out)
+    {
+        if (!p || !out) return ZR_ERR_INVALID_ARG;
+        const uint32_t w = p->width, h = p->height;
+        switch (id)
+        {
+        case ZR_DIRECT_FINAL: *out = zr_image2d{ p->d_final, w, h, w * 16u, 16u }; break;
+        case ZR_DIRECT_RESERVOIR_CURR: *out = zr_image2d{ p->d_res[1 - p->currTemporalIdx], w, h, w * 32u, 32u }; break;
+        case ZR_DIRECT_TARGET: *out = zr_image2d{ p->d_target, w, h, w * 8u, 8u }; break;
+        default: zr::set_error("zr_direct_pass_get_output: unknown output id"); return ZR_ERR_INVALID_ARG;
+        }
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_describe_io(zr_direct_pass* p, zr_resource_use* uses, int* n)
+    {
+        if (!p || !uses || !n) return ZR_ERR_INVALID_ARG;
+        uses[0] = zr_resource_use{ ZR_RES_GBUFFER_CURR, 0 };
+        uses[1] = zr_resource_use{ ZR_RES_GBUFFER_PREV, 0 };
+        uses[2] = zr_resource_use{ ZR_RES_SCENE_BVH, 0 };
+        uses[3] = zr_resource_use{ ZR_RES_ALIAS_TABLE, 0 };
+        uses[4] = zr_resource_use{ ZR_RES_DI_FINAL, 1 };
+        *n = 5;
+        return ZR_OK;
+    }
+    void zr_direct_pass_destroy(zr_direct_pass* p) { if (p) { p->Release(); delete p; } }
+}

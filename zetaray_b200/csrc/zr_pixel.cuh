@@ -36,6 +36,7 @@ struct Pixel
 {
     GFlags flags; float roughness; float z; float3 pos, normal, origin; float2 lensSample;
     BSDF::ShadingData surface; float eta_next;
+    float coatRoughness, coatIor;   // raw coat parameters (ShadingData keeps alpha / relative eta)
 };
 
 ZR_D float3 row3(const float m[3][4], int r) { return f3(m[r][0], m[r][1], m[r][2]); }
@@ -89,6 +90,7 @@ ZR_D Pixel LoadPixel(const FrameView& f, const SceneDev& sc, const uint4* __rest
         coat_color = Math::UnpackRGB8(px_ | ((py_ & 0xff) << 16));
         coat_ior = DecodeIOR(Math::UNorm8ToFloat(pz_ >> 8));
     }
+    p.coatRoughness = coat_roughness; p.coatIor = coat_ior;
     const float3 wo = normalize(p.origin - p.pos);
     p.surface = BSDF::ShadingData::Init(p.normal, wo, p.flags.metallic, p.roughness, baseColor, BSDF::ETA_AIR, p.eta_next,
         p.flags.transmissive, p.flags.trDepthGt0 ? 1.0f : 0.0f, to_half(baseW), coat_weight, coat_color, coat_roughness,
