@@ -1,0 +1,298 @@
+"""bench.py -- Mpaths/s of the ReSTIR PT frame (1 spp, 1920x1080, Cornell Box) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one frame of the reference's frame graph for the emissive Cornell Box, steady state (temporal and
+spatial reuse active): G-buffer -> ReSTIR DI (temporal + pairwise-MIS spatial) -> ReSTIR PT (path generation,
+temporal + spatial path reuse) -> compositing + firefly filter -> TAA. Nothing is skipped or cached.
+
+  value   frames timed with CUDA events on the launching stream, per-frame inputs already on the device
+  e2e     the same frames through the C-ABI with HOST buffers in the timed region: the frame constants come from
+          pinned host memory every frame and the anti-aliased RGBA16F image is read back to pinned host memory
+  roofline        the kernel with the largest share of the frame: algorithmic bytes / event-timed duration
+  cpu_baseline    the CPU oracle (a port: the reference ships no CPU renderer) on a bounded sample of the workload
+  --impl reference   the same CPU path with every host core (the only CPU arm the reference's math has)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+METRIC = "Mpaths/s (1spp ReSTIR PT, 1080p)"
+WORKLOAD = "Cornell Box 1080p ReSTIR PT 3-bounce + ReSTIR DI + firefly/TAA (cornell_emissive.gltf, static camera, 8-phase Halton jitter)"
+
+# algorithmic bytes per pixel of each kernel (DESIGN.md "kernels"; SURVEY 8d for the reference's layout)
+ALG_BYTES = {
+    "k_gbuffer": 28.0,          # writes: core 16 + depth 4 + motion/emissive 8 (coat only when coated)
+    "k_di_temporal": 16 + 8 + 16 + 32 + 32 + 8 + 16.0,   # core, motion, prev core, prev reservoir -> reservoir, target, final
+    "k_di_spatial": 16 + 32 + 8 + 1.5 * (16 + 32) + 16.0,  # self + 1-2 neighbours -> final
+    "k_pathtrace": 16 + 64 + 16.0 + 3 * 192,   # core -> reservoir + target, plus ~192 B of scene gathers per bounce
+    "k_temporal": 16 + 8 + 64 + 16 + 16 + 64 + 64 + 16.0,   # fused CtT+TtC (SURVEY 8d 'temporal resample': 308 with 62 B planes)
+    "k_spatial_search": 16 + 16 + 2.0,
+    "k_sort": 16 + 2 + 4 + 2.0,
+    "k_spatial": 16 + 64 + 16 + 2 + 2 + 16 + 64 + 64 + 16.0,  # fused CtS+StC (SURVEY 8d B_spatial = 294 with 62 B planes)
+    "k_firefly": 16 + 16 + 4 + 16 + 16.0,   # fused compositing + firefly: direct, indirect, depth, core(flags) -> composited
+    "k_taa": 16 + 4 + 8 + 8 + 8.0,
+}
+
+
+def _clock_sampler(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    dev = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", dev, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            parts = [p.strip() for p in r.stdout.strip().split(",")]
+            if len(parts) >= 6:
+                out.append(parts)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _clock_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in samples)
+    reasons = []
+    for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+        if any(s[2 + i].lower().startswith("active") for s in samples):
+            reasons.append(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "reasons": reasons}
+
+
+def cpu_frames(w, h, nframes, nthreads, warm=3):
+    """Times the CPU oracle on `nframes` steady-state frames of w x h (after `warm` untimed frames)."""
+    from tests import scene_util, rpt_util
+    import numpy as np
+    R = rpt_util.OracleRenderer(scene_util.cornell(), w, h, nthreads=nthreads)
+    seq = rpt_util.FrameSequence(w, h)
+    taa_prev = np.zeros((w * h, 2), dtype=np.uint32)
+
+    def frame(i):
+        nonlocal taa_prev
+        fc = seq.next()
+        R.gbuffer(fc); R.rdi(fc); R.rpt(fc)
+        _, taa_prev = R.post(fc, taa_prev, i > 0)
+    for i in range(warm):
+        frame(i)
+    t0 = time.perf_counter()
+    for i in range(nframes):
+        frame(warm + i)
+    dt = time.perf_counter() - t0
+    return w * h * nframes / dt / 1e6, dt / nframes
+
+
+def run_reference(args):
+    """`--impl reference`: the reference has no CPU implementation of this path and cannot be built here (HLSL/DXR/D3D12);
+    the arm is the oracle port of its math, all host cores, on a bounded sample (reduced resolution) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sw, sh = 960, 540
+    per = []
+    for _ in range(max(1, args.steps)):
+        mp, spf = cpu_frames(sw, sh, 1, cores, warm=3 if not per else 0)
+        per.append((mp, spf))
+        if sum(p[1] for p in per) > 90:
+            break
+    mp = sum(p[0] for p in per) / len(per)
+    sample = "%d steady-state frame(s) at %dx%d (1/4 of the 1080p pixels), %d threads" % (len(per), sw, sh, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mp, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": len(per),
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(p[1] for p in per) / len(per), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU port of the reference's shader math (the reference ships no CPU renderer)"},
+        "cpu_baseline": {"value": mp, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mp, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from zetaray_b200 import lib, check, _lib
+    from zetaray_b200.passes import Scene, GBuffers, GBufferRT, DirectLighting, IndirectLighting, Compositing, TAA
+    from tests import scene_util, rpt_util     # scene fixture + frame-constant generator (no oracle code on this path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    st = C.c_void_p(stream.cuda_stream)
+
+    # Multi-GPU: pixels are independent except for neighbour reads. This round runs weak scaling with one
+    # full 1080p frame per GPU and no data-path collective ("replicas", DESIGN.md multi-GPU); value = all frames / time.
+    flat = scene_util.cornell()
+    scene = Scene(flat)
+    scene.prelighting(st)
+    gb = GBuffers(W, H)
+    gpass, di, ind, comp, taa = GBufferRT(), DirectLighting(W, H), IndirectLighting(W, H), Compositing(W, H), TAA(W, H)
+    seq = rpt_util.FrameSequence(W, H)
+    fi = _lib.FrameInputs()
+    fi.scene = scene.handle
+
+    def frame(fc):
+        gb.flip()
+        fi.frame = fc
+        gb.fill_inputs(fi)
+        gpass.Render(fi, st)
+        di.Render(fi, st)
+        ind.Render(fi, st)
+        comp.Render(fi, di.GetOutput(0).d_ptr, ind.GetOutput(0).d_ptr, st)
+        taa.Render(fi, comp.GetOutput().d_ptr, st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also brings temporal + spatial reuse to steady state: frame >= 3) ----
+    for _ in range(args.warmup):
+        frame(seq.next())
+    # per-frame working set: G-buffers 2 x 36 B/px, PT reservoirs 2 x 64, DI 2 x 32, targets/finals ~ 90 B/px => ~0.8 GB
+    # at 1080p, larger than the 126 MB L2, so no explicit flush between frames is needed.
+
+    # ---- value: device-resident ----
+    launches0 = lib.zr_kernel_launch_count()
+    clocks, stop = [], threading.Event()
+    th = threading.Thread(target=_clock_sampler, args=(stop, clocks), daemon=True)
+    th.start()
+    fcs = [seq.next() for _ in range(args.steps)]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for fc in fcs:
+        frame(fc)
+    e1.record(stream)
+    barrier()
+    stop.set()
+    ms = e0.elapsed_time(e1)
+    launches = lib.zr_kernel_launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * W * H * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- e2e: host buffers in, host image out, every frame ----
+    n_e2e = max(3, min(args.steps, 20))
+    fc_host = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8).pin_memory()
+    fc_dev = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8, device="cuda")
+    out_host = torch.empty(W * H * 8, dtype=torch.uint8).pin_memory()
+    fcs2 = [seq.next() for _ in range(n_e2e)]
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for fc in fcs2:
+        C.memmove(fc_host.data_ptr(), C.addressof(fc), C.sizeof(fc))
+        fc_dev.copy_(fc_host, non_blocking=True)            # H2D of the per-frame inputs
+        frame(fc)
+        img = taa.GetOutput()
+        check(lib.zr_memcpy_d2h(C.c_void_p(out_host.data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st))
+        stream.synchronize()                                 # the caller consumes the image before the next frame
+    e3.record(stream)
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * W * H * n_e2e / (float(t2.item()) * 1e-3) / 1e6
+
+    # ---- per-kernel timing (CUDA events on the launching stream around every launch) ----
+    kern = {}
+    if rank == 0:
+        check(lib.zr_profile_enable(1))
+        nprof = 5
+        for _ in range(nprof):
+            frame(seq.next())
+        buf = C.create_string_buffer(8192)
+        check(lib.zr_profile_collect(buf, 8192))
+        check(lib.zr_profile_enable(0))
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, calls, total = item.split(":")
+                kern[name] = float(total) / nprof      # ms per frame (all launches of that kernel)
+    roofline, kernels = None, []
+    if rank == 0 and kern:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        tot = sum(kern.values())
+        for name, msf in sorted(kern.items(), key=lambda kv: -kv[1]):
+            ab = ALG_BYTES.get(name)
+            gbs = (ab * W * H / (msf * 1e-3) / 1e9) if ab else None
+            kernels.append({"kernel": name, "ms_per_frame": round(msf, 4), "share": round(msf / tot, 4),
+                            "alg_bytes_per_px": ab, "achieved_gbs": None if gbs is None else round(gbs, 1),
+                            "frac": None if gbs is None else round(gbs / peak, 4)})
+        top = kernels[0]
+        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                    "note": "algorithmic bytes/px x pixels / CUDA-event duration; traversal-bound kernels are listed for share, "
+                            "their HBM fraction is informational (SURVEY 8d)"}
+
+    # ---- CPU baseline (rank 0, N == 1): bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        mp, spf = cpu_frames(480, 270, 2, cores)
+        cpu = {"value": round(mp, 4), "unit": "Mpaths/s", "cores": cores, "kind": "port",
+               "sample": "2 steady-state frames at 480x270 (1/16 of the 1080p pixels, same scene/params), %d threads, %.2f s/frame" % (cores, spf)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "resolution": [W, H], "spp": 1, "bounces": 3, "restir_pt": "temporal + 1 spatial pass",
+                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "replicas x%d" % world,
+                       "l2": "per-frame working set ~0.8 GB >> 126 MB L2 (no flush needed)"},
+            "e2e": {"value": round(e2e_value, 3), "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(_lib.FrameConstants),
+                    "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},
+            "gpu_launches": int(launches),
+            "clocks": _clock_summary(clocks),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

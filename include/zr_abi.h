@@ -445,6 +445,10 @@ ZR_API zr_status zr_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, voi
 ZR_API zr_status zr_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 ZR_API zr_status zr_memset_d(void* d_dst, int value, size_t bytes, void* stream);
 ZR_API zr_status zr_stream_synchronize(void* stream);
+/* per-kernel device timing for the roofline report: while enabled every launch is bracketed by CUDA events on
+ * its stream; collect() synchronises and returns "name:calls:total_ms;..." */
+ZR_API zr_status zr_profile_enable(int on);
+ZR_API zr_status zr_profile_collect(char* buf, size_t buf_size);
 /* number of kernels this library launched since load (for bench.py's gpu_launches) */
 ZR_API uint64_t zr_kernel_launch_count(void);
 

@@ -303,14 +303,19 @@ zr_status alias_table_build(float* d_weights, uint32_t n, zr_alias_entry* d_tabl
     float* d_sums = d_small;
     uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_small + 4);
 
+    ZR_PROF("k_kahan_sum", stream);
     k_kahan_sum<<<1, SUM_THREADS, 0, stream>>>(d_weights, n, d_sums);
     ZR_LAUNCH_CHECK();
+    ZR_PROF("k_normalize", stream);
     k_normalize<<<(n + 255) / 256, 256, 0, stream>>>(d_weights, n, d_sums, d_table);
     ZR_LAUNCH_CHECK();
+    ZR_PROF("k_partition", stream);
     k_partition<<<1, PART_THREADS, 0, stream>>>(d_weights, n, d_scratch, d_scratch + n, d_counts);
     ZR_LAUNCH_CHECK();
+    ZR_PROF("k_vose", stream);
     k_vose<<<1, 32, 0, stream>>>(d_weights, d_scratch, d_scratch + n, d_counts, d_table);
     ZR_LAUNCH_CHECK();
+    ZR_PROF("k_cache_alias_p", stream);
     k_cache_alias_p<<<(n + 255) / 256, 256, 0, stream>>>(d_table, n);
     ZR_LAUNCH_CHECK();
     return ZR_OK;
@@ -324,6 +329,7 @@ zr_status alias_table_sample(const zr_alias_entry* d_table, uint32_t n, uint32_t
         set_error("zr_alias_table_sample: null pointer or n == 0");
         return ZR_ERR_INVALID_ARG;
     }
+    ZR_PROF("k_sample", stream);
     k_sample<<<1, 32, 0, stream>>>(d_table, n, seed, num_draws, d_out_idx, d_out_pdf);
     ZR_LAUNCH_CHECK();
     return ZR_OK;

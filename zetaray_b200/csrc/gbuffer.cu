@@ -210,6 +210,7 @@ struct zr_gbuffer_pass
         const uint32_t W = in->frame.RenderWidth, H = in->frame.RenderHeight;
         if (!W || !H) { set_error("zr_gbuffer_pass_render: zero render size"); return ZR_ERR_INVALID_ARG; }
         dim3 grid((W + 7) / 8, (H + 7) / 8);
+        ZR_PROF("k_gbuffer", stream);
         k_gbuffer<<<grid, 64, 0, stream>>>(in->scene->dev, in->frame, (uint4*)in->curr.d_core, (float*)in->curr.d_depth,
             (uint2*)in->curr.d_motion_emissive, (uint2*)in->curr.d_coat, (uint2*)in->curr.d_tridiff);
         ZR_LAUNCH_CHECK();
@@ -268,6 +269,7 @@ extern "C"
         if (!scene || !d_power) { zr::set_error("zr_estimate_emissive_power: null argument"); return ZR_ERR_INVALID_ARG; }
         const uint32_t n = scene->dev.numEmissives;
         if (n == 0) return ZR_OK;
+        ZR_PROF("k_emissive_power", (cudaStream_t)stream);
         zr::k_emissive_power<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scene->dev, d_power);
         ZR_LAUNCH_CHECK();
         return ZR_OK;

@@ -313,12 +313,14 @@ struct zr_compositing_pass
         dim3 grid((width + 31) / 32, (height + 7) / 8);
         if (params.firefly_filter)
         {
+            ZR_PROF("k_firefly", stream);
             k_firefly<true><<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
                 direct, indirect, d_composited, p);
             ZR_LAUNCH_CHECK();
         }
         else
         {
+            ZR_PROF("k_compositing", stream);
             k_compositing<<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, direct, indirect, d_composited, p);
             ZR_LAUNCH_CHECK();
         }
@@ -330,9 +332,11 @@ struct zr_compositing_pass
         using namespace zr;
         PostParams p = make_params(in->frame);
         dim3 grid((width + 31) / 32, (height + 7) / 8);
+        ZR_PROF("k_compositing", stream);
         k_compositing<<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float4*)d_direct,
             (const float4*)d_indirect, d_scratch, p);
         ZR_LAUNCH_CHECK();
+        ZR_PROF("k_firefly", stream);
         k_firefly<false><<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
             d_scratch, nullptr, d_composited, p);
         ZR_LAUNCH_CHECK();
@@ -383,6 +387,7 @@ struct zr_taa_pass
         p.temporalIsValid = isTemporalTexValid ? 1u : 0u;
         dim3 grid((width + 31) / 32, (height + 7) / 8);
         outIdx ^= 1;
+        ZR_PROF("k_taa", stream);
         k_taa<<<grid, 256, 0, stream>>>((const float*)in->curr.d_depth, (const uint2*)in->curr.d_motion_emissive,
             (const float4*)d_signal, d_tex[outIdx ^ 1], d_tex[outIdx], p);
         ZR_LAUNCH_CHECK();

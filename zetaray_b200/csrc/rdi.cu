@@ -715,10 +715,12 @@ struct zr_direct_pass
             params.alpha_min, resetTemporalTextures };
         const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
         const int cur = currTemporalIdx;
+        ZR_PROF("k_di_temporal", stream);
         k_di_temporal<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
         ZR_LAUNCH_CHECK();
         if (doSpatial)
         {
+            ZR_PROF("k_di_spatial", stream);
             k_di_spatial<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
             ZR_LAUNCH_CHECK();
         }

@@ -999,11 +999,13 @@ struct zr_indirect_pass
         int cur = currTemporalIdx;
         {
             const uint32_t dispX = (width + 15) / 16, dispY = (height + 7) / 8;
+            ZR_PROF("k_pathtrace", stream);
             k_pathtrace<<<dim3(dispX, dispY), 128, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
             ZR_LAUNCH_CHECK();
         }
         if (doTemporal && lastStage != ZR_RPT_STAGE_PATHTRACE)
         {
+            ZR_PROF("k_temporal", stream);
             k_temporal<<<dim3((width + 15) / 16, (rows + 7) / 8), 128, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
                 d_target, d_final);
             ZR_LAUNCH_CHECK();
@@ -1012,6 +1014,7 @@ struct zr_indirect_pass
         {
             for (uint32_t pass = 0; pass < params.num_spatial_passes; pass++)
             {
+                ZR_PROF("k_spatial_search", stream);
                 k_spatial_search<<<dim3((width + 31) / 32, (rows + 7) / 8), 256, 0, stream>>>(f, prm, d_neighbor);
                 ZR_LAUNCH_CHECK();
                 zr_rpt_reservoir* rin = d_res[cur];
@@ -1020,10 +1023,12 @@ struct zr_indirect_pass
                 if (params.sort_spatial)
                 {
                     const uint32_t sx = (width + 31) / 32, sy = (height + 31) / 32;
+                    ZR_PROF("k_sort", stream);
                     k_sort<<<dim3(sx, sy), 256, 0, stream>>>(f, 3, 1u, rin, nullptr, d_neighbor, d_threadMap[1], sx, sy);
                     ZR_LAUNCH_CHECK();
                 }
                 const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
+                ZR_PROF("k_spatial", stream);
                 k_spatial<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
                     d_threadMap[1], dispX, dispY);
                 ZR_LAUNCH_CHECK();

@@ -414,6 +414,7 @@ extern "C"
     {
         if (!sc || !d_rays || !d_hits) { zr::set_error("zr_scene_trace_closest: null argument"); return ZR_ERR_INVALID_ARG; }
         if (n == 0) return ZR_OK;
+        ZR_PROF("k_trace_closest", (cudaStream_t)stream);
         zr::k_trace_closest<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sc->dev, d_rays, n, d_hits);
         ZR_LAUNCH_CHECK();
         return ZR_OK;
@@ -422,6 +423,7 @@ extern "C"
     {
         if (!sc || !d_rays || !d_flags) { zr::set_error("zr_scene_trace_any: null argument"); return ZR_ERR_INVALID_ARG; }
         if (n == 0) return ZR_OK;
+        ZR_PROF("k_trace_any", (cudaStream_t)stream);
         zr::k_trace_any<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sc->dev, d_rays, n, d_flags);
         ZR_LAUNCH_CHECK();
         return ZR_OK;

@@ -30,7 +30,10 @@ void set_error(const char* fmt, ...);
 zr_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(uint64_t n = 1);
 #define ZR_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return zr::cuda_fail(e__, #expr); } while (0)
-#define ZR_LAUNCH_CHECK() do { zr::count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return zr::cuda_fail(e__, "kernel launch"); } while (0)
+void prof_before(const char* name, cudaStream_t stream);
+void prof_after();
+#define ZR_PROF(name, stream) zr::prof_before(name, (cudaStream_t)(stream))
+#define ZR_LAUNCH_CHECK() do { zr::count_launch(); zr::prof_after(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return zr::cuda_fail(e__, "kernel launch"); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // vectors
