@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libzetaray_b200.so")
+SO_PATH = os.environ.get("ZETARAY_B200_LIB") or os.path.join(HERE, "libzetaray_b200.so")
 
 
 class ZRError(RuntimeError):

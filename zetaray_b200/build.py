@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-SO = os.path.join(HERE, "libzetaray_b200.so")
+# ZR_VARIANT=<name> ZR_EXTRA_FLAGS="-D..." builds an experimental libzetaray_b200_<name>.so beside the default one
+# (selected at run time with ZETARAY_B200_LIB); used for A/B measurements on the GPU box.
+VARIANT = os.environ.get("ZR_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+SO = os.path.join(HERE, "libzetaray_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 # -fmad=false / -ffp-contract=off: the numeric contract -- fused multiply-adds appear only
@@ -37,7 +40,7 @@ def _compile(src, force):
     deps = [src] + _deps() + [__file__]
     if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
         return obj, False
-    cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    cmd = [NVCC] + NVCC_FLAGS + os.environ.get("ZR_EXTRA_FLAGS", "").split() + ["-c", src, "-o", obj]
     if os.environ.get("ZR_PTXAS_V"):
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

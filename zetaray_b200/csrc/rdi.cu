@@ -444,7 +444,7 @@ struct PairwiseMIS
     }
 
     // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting
-    __global__ void __launch_bounds__(64) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
+    __global__ void ZR_LB(64) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
         const zr_rdi_reservoir* __restrict__ resPrev, uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
@@ -496,7 +496,7 @@ struct PairwiseMIS
     }
 
     // ReSTIR_DI_Spatial.hlsl main + SpatialResample
-    __global__ void __launch_bounds__(64) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
+    __global__ void ZR_LB(64) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
         const uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;

@@ -76,12 +76,21 @@ namespace
         }
     }
 
-    __global__ void __launch_bounds__(128) k_pathtrace(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ res,
+#ifndef ZR_PT_THREADS
+#define ZR_PT_THREADS 1024
+#endif
+    // A block is ZR_PT_THREADS/128 consecutive 16x8 groups of the reference's swizzled dispatch; each warp is one
+    // reference wave. The warps of a block walk the bounce phases together (zr_rpt.cuh "block-synchronous phases").
+    __global__ void ZR_LB(ZR_PT_THREADS) k_pathtrace(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ res,
         float4* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
-        uint2 sg;
-        const uint2 px = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 15, threadIdx.x >> 4, 16, 8, dispX, 16, 4, 16 * dispY, sg);
+        uint2 sg = make_uint2(0, 0);
+        const uint32_t groupFlat = blockIdx.x * (ZR_PT_THREADS / 128) + (threadIdx.x >> 7);
+        const uint32_t tInGroup = threadIdx.x & 127;
+        uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
+        if (groupFlat < dispX * dispY)
+            px = SwizzleThreadGroup(groupFlat, 0, tInGroup & 15, tInGroup >> 4, 16, 8, dispX, 16, 4, 16 * dispY, sg);
         bool inBounds = px.x < f.W && px.y < f.H && px.y >= prm.rowBegin && px.y < prm.rowEnd;
         const size_t idx = (size_t)px.y * f.W + px.x;
         bool alive = false;
@@ -131,26 +140,31 @@ namespace
                 prevHit.lobe = bsdfSample.lobe; prevHit.wi = bsdfSample.wi; prevHit.pdf = bsdfSample.pdf;
                 eta_curr = dot(p.normal, bsdfSample.wi) < 0 ? p.eta_next : BSDF::ETA_AIR;
                 inTranslucentMedium = eta_curr != BSDF::ETA_AIR;
-                nextHit = FindClosestEmissive(sc, pos, normal, bsdfSample.wi, surface.Transmissive());
                 alive = true;
             }
         }
+        ZR_PHASE();
+        if (alive)
+            nextHit = FindClosestEmissive(sc, pos, normal, bsdfSample.wi, surface.Transmissive());
 
-        // lock-step bounce loop (ReSTIR_PT_PathTrace.hlsl:227-355)
-        while (__any_sync(0xffffffffu, alive))
+        // lock-step bounce loop (ReSTIR_PT_PathTrace.hlsli:227-355) as block-synchronous phases (zr_rpt.cuh)
+        while (__syncthreads_or(alive))
         {
             bool atRR = false;
             Hit hitInfo;
             float prevBsdfSamplePdf = 0; BSDF::LOBE prevBsdfSampleLobe = BSDF::DIFFUSE_R;
-            int pathVertex = bounce + 2;
+            const int pathVertex = bounce + 2;
+            // phase: attributes + material of the vertex the previous sample hit
+            if (alive && !nextHit.hit)
+                alive = false;
             if (alive)
             {
-                do
+                hitInfo = HitAttributes(sc, nextHit.geoIdx, nextHit.primIdx, nextHit.bary, nextHit.t);
+                const float3 newPos = mad(hitInfo.t, bsdfSample.wi, pos);
+                if (!GetMaterialData(sc, -bsdfSample.wi, eta_curr, hitInfo, surface, eta_next))
+                    alive = false;
+                else
                 {
-                    if (!nextHit.hit) { alive = false; break; }
-                    hitInfo = HitAttributes(sc, nextHit.geoIdx, nextHit.primIdx, nextHit.bary, nextHit.t);
-                    const float3 newPos = mad(hitInfo.t, bsdfSample.wi, pos);
-                    if (!GetMaterialData(sc, -bsdfSample.wi, eta_curr, hitInfo, surface, eta_next)) { alive = false; break; }
                     pos = newPos;
                     normal = hitInfo.normal;
                     prevBsdfSamplePdf = bsdfSample.pdf;
@@ -163,42 +177,94 @@ namespace
                         tr = f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
                         throughput *= tr;
                     }
-                    // EstimateDirectAndUpdateRC<Emissive>
-                    {
-                        BSDF::BSDFSample nextBsdfSample = bsdfSample;
-                        const int nextBounce = pathVertex - 1;
-                        const DirectLightingEstimate ls_b = NEE_Bsdf(sc, pos, hitInfo.normal, surface, nextBounce, maxNumBounces,
-                            nextBsdfSample, nextHit, rngReplay);
-                        if (nextHit.HitWasEmissive())
-                        {
-                            const float3 fOverPdf = throughput * ls_b.ld;
-                            li += fOverPdf;
-                            rc.L = Reconnection::half3(ls_b.ld * throughput_k);
-                            MaybeSetCase2OrCase3(pathVertex, pos, hitInfo.normal, hitInfo.t, hitInfo.ID, hitInfo.meshIdx, surface,
-                                prevHit, ls_b, 0, rc, prm.alpha_min);
-                            r.Update(Math::Luminance(fOverPdf), fOverPdf, rc, rngThread);
-                        }
-                        if (!IsSpecularSurface(surface))
-                        {
-                            const uint32_t seed_nee = rngThread.State;
-                            const DirectLightingEstimate ls = NEE_Emissive(sc, pos, hitInfo.normal, surface, rngThread);
-                            const float3 fOverPdf = throughput * ls.ld;
-                            li += fOverPdf;
-                            if (rc.IsCase2() || rc.IsCase3())
-                                rc.Clear();
-                            rc.L = Reconnection::half3(ls.ld * throughput_k);
-                            MaybeSetCase2OrCase3(pathVertex, pos, hitInfo.normal, hitInfo.t, hitInfo.ID, hitInfo.meshIdx, surface,
-                                prevHit, ls, seed_nee, rc, prm.alpha_min);
-                            r.Update(Math::Luminance(fOverPdf), fOverPdf, rc, rngThread);
-                        }
-                        bsdfSample = nextBsdfSample;
-                    }
-                    if (bounce >= (maxNumBounces - 1)) { alive = false; break; }
+                }
+            }
+            ZR_PHASE();
+            // EstimateDirectAndUpdateRC<Emissive>. phase: draw the next direction (NEE_Bsdf, ReSTIR_PT_NEE.hlsli:145-222)
+            BSDF::BSDFSample nextBsdfSample = bsdfSample;
+            const int nextBounce = pathVertex - 1;
+            if (alive && nextBounce <= maxNumBounces)
+                nextBsdfSample = BSDF::SampleBSDF(hitInfo.normal, surface, rngReplay);
+            ZR_PHASE();
+            // phase: closest hit along it
+            RaySetup rs; rs.go = false;
+            RayHit rh; rh.hit = false;
+            if (alive)
+            {
+                rs = SetupClosestEmissive(pos, hitInfo.normal, nextBsdfSample.wi, surface.Transmissive());
+                if (rs.go)
+                    rh = TraceClosest(sc, rs.o, nextBsdfSample.wi, rs.tmin, FLT_MAX_);
+            }
+            ZR_PHASE();
+            // phase: BSDF-sampled light hit, then light sample + BSDF value (NEE_Emissive, ReSTIR_PT_NEE.hlsli:224-302)
+            NeeLightState nee;
+            nee.facing = false; nee.ld = f3(0);
+            BSDF::ShadingData surfNee;
+            bool lightSample = false;
+            uint32_t seed_nee = 0;
+            RaySetup seg; seg.go = false;
+            if (alive)
+            {
+                nextHit = FinishClosestEmissive(sc, rs, rh, nextBsdfSample.wi);
+                const DirectLightingEstimate ls_b = NEE_Bsdf_Finish(sc, pos, surface, nextBounce, maxNumBounces, nextBsdfSample, nextHit);
+                if (nextHit.HitWasEmissive())
+                {
+                    const float3 fOverPdf = throughput * ls_b.ld;
+                    li += fOverPdf;
+                    rc.L = Reconnection::half3(ls_b.ld * throughput_k);
+                    MaybeSetCase2OrCase3(pathVertex, pos, hitInfo.normal, hitInfo.t, hitInfo.ID, hitInfo.meshIdx, surface,
+                        prevHit, ls_b, 0, rc, prm.alpha_min);
+                    r.Update(Math::Luminance(fOverPdf), fOverPdf, rc, rngThread);
+                }
+                lightSample = !IsSpecularSurface(surface);
+                if (lightSample)
+                {
+                    seed_nee = rngThread.State;
+                    surfNee = surface;
+                    nee = NEE_Emissive_Begin(sc, pos, hitInfo.normal, surfNee, rngThread);
+                    if (nee.facing && dot(nee.ld, nee.ld) > 0)
+                        seg = SetupSegment(pos, nee.ret.wi, nee.t, hitInfo.normal, nee.ret.ID, surfNee.Transmissive());
+                }
+            }
+            ZR_PHASE();
+            // phase: shadow segment
+            if (lightSample && nee.facing && dot(nee.ld, nee.ld) > 0)
+            {
+                const bool visible = seg.go ? !TraceAnyExcept(sc, seg.o, nee.ret.wi, seg.tmin, seg.tmax, nee.ret.ID) : false;
+                nee.ld *= visible ? 1.0f : 0.0f;
+            }
+            ZR_PHASE();
+            // phase: sampler pdf of the light direction, MIS, reservoir update
+            if (lightSample)
+            {
+                float bsdfPdf = 0;
+                if (nee.facing && dot(nee.ld, nee.ld) > 0)
+                {
+                    bsdfPdf = BSDF::BSDFSamplerPdf(hitInfo.normal, surfNee, nee.ret.wi, rngThread);
+                    bsdfPdf *= nee.dwdA;
+                }
+                const DirectLightingEstimate ls = NEE_Emissive_Finish(nee, bsdfPdf);
+                const float3 fOverPdf = throughput * ls.ld;
+                li += fOverPdf;
+                if (rc.IsCase2() || rc.IsCase3())
+                    rc.Clear();
+                rc.L = Reconnection::half3(ls.ld * throughput_k);
+                MaybeSetCase2OrCase3(pathVertex, pos, hitInfo.normal, hitInfo.t, hitInfo.ID, hitInfo.meshIdx, surface,
+                    prevHit, ls, seed_nee, rc, prm.alpha_min);
+                r.Update(Math::Luminance(fOverPdf), fOverPdf, rc, rngThread);
+            }
+            if (alive)
+            {
+                bsdfSample = nextBsdfSample;
+                if (bounce >= (maxNumBounces - 1))
+                    alive = false;
+                else
+                {
                     if (rc.IsCase2() || rc.IsCase3())
                         rc.Clear();
                     bounce++;
                     atRR = true;
-                } while (false);
+                }
             }
             // Russian roulette against the wave's maximum throughput
             const uint32_t rrMask = __ballot_sync(0xffffffffu, atRR);
@@ -319,37 +385,49 @@ namespace
     }
 
     // -------------------------------------------------------------------------------------------
-    // Temporal reuse: Reconnect_CtT then Reconnect_TtC for the same pixel (replay inline)
+    // Temporal reuse: Reconnect_CtT then Reconnect_TtC for the same pixel (replay inline).
+    // A block is 32 x ZR_RPT_THREADS/32 pixels, one warp per 8x4 tile; block-synchronous phases throughout,
+    // so no thread leaves before the last barrier.
     // -------------------------------------------------------------------------------------------
-    __global__ void __launch_bounds__(128) k_temporal(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ resCurr,
+#ifndef ZR_RPT_THREADS
+#define ZR_RPT_THREADS 1024
+#endif
+    __global__ void ZR_LB(ZR_RPT_THREADS) k_temporal(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ resCurr,
         const zr_rpt_reservoir* __restrict__ resPrev, float4* __restrict__ target, float4* __restrict__ finalImg)
     {
         const zr_frame_constants& fc = f.fc;
-        const int x = blockIdx.x * 16 + (threadIdx.x & 15);
-        const int y = (int)prm.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 4);
-        if (x >= (int)f.W || y >= (int)f.H || y >= (int)prm.rowEnd) return;
-        const size_t idx = (size_t)y * f.W + x;
-        const uint4 coreC = ld128(&f.core[idx]);
-        const GFlags flags = DecodeFlags(coreC.w & 0xff);
-        if (flags.invalid || flags.emissive) return;
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int x = (int)(blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7));
+        const int y = (int)(prm.rowBegin + blockIdx.y * (ZR_RPT_THREADS / 32) + (warp >> 2) * 4 + (lane >> 3));
+        bool act = !(x >= (int)f.W || y >= (int)f.H || y >= (int)prm.rowEnd);
+        const size_t idx = act ? (size_t)y * f.W + x : 0;
+        if (act)
+        {
+            const GFlags flags = DecodeFlags(ld128(&f.core[idx]).w & 0xff);
+            if (flags.invalid || flags.emissive) act = false;
+        }
 
         zr_rpt_reservoir rec;
-        LoadRecord(&resCurr[idx], rec);
-        Reservoir r_curr = Reservoir::Load_NonReconnection(rec);
-        const float4 tg = target[idx];
-        r_curr.target = f3(tg.x, tg.y, tg.z);
-
-        // temporal validity (identical tests in CtT, TtC and both replays; the replays use the tighter plane test)
-        int ppx, ppy;
-        bool ok = PrevPixel(f, x, y, ppx, ppy);
-        float prevViewDepth = FLT_MAX_;
-        if (ok)
-        {
-            prevViewDepth = asfloat(__ldg(&f.pcore[(size_t)ppy * f.W + ppx].x));
-            ok = prevViewDepth != FLT_MAX_;
-        }
+        Reservoir r_curr = Reservoir::Init();
+        int ppx = 0, ppy = 0;
+        bool ok = false, okReplay = false;
         Pixel cur, prev;
-        bool okReplay = false;
+        if (act)
+        {
+            LoadRecord(&resCurr[idx], rec);
+            r_curr = Reservoir::Load_NonReconnection(rec);
+            const float4 tg = target[idx];
+            r_curr.target = f3(tg.x, tg.y, tg.z);
+            // temporal validity (identical tests in CtT, TtC and both replays; the replays use the tighter plane test)
+            ok = PrevPixel(f, x, y, ppx, ppy);
+            float prevViewDepth = FLT_MAX_;
+            if (ok)
+            {
+                prevViewDepth = asfloat(__ldg(&f.pcore[(size_t)ppy * f.W + ppx].x));
+                ok = prevViewDepth != FLT_MAX_;
+            }
+        }
+        ZR_PHASE();
         if (ok)
         {
             cur = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
@@ -361,50 +439,58 @@ namespace
             ok = ok && matOk;
             okReplay = okReplay && matOk;
         }
-        if (!ok)
+        if (act && !ok)
         {
             if (!prm.spatialFlag)
                 WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
-            return;
+            act = false;
         }
-        const size_t pidx = (size_t)ppy * f.W + ppx;
+        const size_t pidx = ok ? (size_t)ppy * f.W + ppx : 0;
         zr_rpt_reservoir recPrev;
-        LoadRecord(&resPrev[pidx], recPrev);
-        Reservoir r_prev = Reservoir::Load_NonReconnection(recPrev);
+        Reservoir r_prev = Reservoir::Init();
+        if (ok)
+        {
+            LoadRecord(&resPrev[pidx], recPrev);
+            r_prev = Reservoir::Load_NonReconnection(recPrev);
+        }
 
         // ---- Reconnect_CtT: scale w_sum by the MIS weight of the current sample in the temporal domain ----
-        if (r_curr.w_sum != 0 && r_prev.M > 0 && !r_curr.rc.Empty())
         {
-            Reservoir rc_full = r_curr;
-            rc_full.Load_Reconnection(rec);
-            const Reconnection rcOrig = rc_full.rc;
-            if (rc_full.rc.IsCase1() || rc_full.rc.IsCase2())
-                XkToPrev(sc, rc_full.rc);
-            OffsetPathContext ctx;
-            const OffsetPathContext* pctx = nullptr;
-            if (rc_full.rc.k > 2)
+            const bool doCtT = ok && r_curr.w_sum != 0 && r_prev.M > 0 && !r_curr.rc.Empty();
+            Reservoir rc_full = Reservoir::Init();
+            Reconnection rcOrig = Reconnection::Init();
+            if (doCtT)
             {
-                ctx = OffsetPathContext::Init();
-                if (okReplay)
-                    ctx = Replay_kGt2(sc, prev.pos, prev.normal, prev.eta_next, prev.surface, rcOrig, prm.alpha_min).Quantize();
-                pctx = &ctx;
+                rc_full = r_curr;
+                rc_full.Load_Reconnection(rec);
+                rcOrig = rc_full.rc;
+                if (rc_full.rc.IsCase1() || rc_full.rc.IsCase2())
+                    XkToPrev(sc, rc_full.rc);
             }
-            const OffsetPath shift = Shift2(sc, prev.pos, prev.normal, prev.eta_next, prev.surface, rc_full.rc, pctx, prm.alpha_min);
-            const float target_prev = Math::Luminance(shift.target);
-            if (target_prev > 0)
+            const bool needCtx = doCtT && rc_full.rc.k > 2;
+            ZR_PHASE();
+            OffsetPathContext ctx = Replay_kGt2_Sync(needCtx && okReplay, sc, prev.pos, prev.normal, prev.eta_next, prev.surface, rcOrig, prm.alpha_min);
+            if (needCtx && okReplay)
+                ctx = ctx.Quantize();
+            const OffsetPath shift = Shift2_Sync(doCtT, sc, prev.pos, prev.normal, prev.eta_next, prev.surface, rc_full.rc, &ctx, prm.alpha_min);
+            if (doCtT)
             {
-                const float targetLum_curr = r_curr.W > 0 ? r_curr.w_sum / r_curr.W : 0;
-                const float jacobian = rc_full.rc.partialJacobian > 0 ? shift.partialJacobian / rc_full.rc.partialJacobian : 0;
-                const float m_curr = targetLum_curr / (targetLum_curr + (float)r_prev.M * target_prev * jacobian);
-                r_curr.w_sum *= m_curr;
-                rec.w_sum = r_curr.w_sum;
+                const float target_prev = Math::Luminance(shift.target);
+                if (target_prev > 0)
+                {
+                    const float targetLum_curr = r_curr.W > 0 ? r_curr.w_sum / r_curr.W : 0;
+                    const float jacobian = rc_full.rc.partialJacobian > 0 ? shift.partialJacobian / rc_full.rc.partialJacobian : 0;
+                    const float m_curr = targetLum_curr / (targetLum_curr + (float)r_prev.M * target_prev * jacobian);
+                    r_curr.w_sum *= m_curr;
+                    rec.w_sum = r_curr.w_sum;
+                }
             }
         }
 
         // ---- Reconnect_TtC ----
         const uint32_t M_new = r_curr.M + r_prev.M;
         const uint32_t M_max = prm.M_max_temporal;
-        if (r_prev.rc.Empty())
+        if (ok && r_prev.rc.Empty())
         {
             const float targetLum = Math::Luminance(r_curr.target);
             r_curr.W = targetLum > 0 ? r_curr.w_sum / targetLum : 0;
@@ -416,22 +502,24 @@ namespace
             st128(&resCurr[idx], make_uint4(rec.meta, asuint(rec.w_sum), asuint(rec.W), rec.L_b));
             if (!prm.spatialFlag)
                 WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
-            return;
+            ok = false;
         }
-        r_prev.Load_Reconnection(recPrev);
-        const Reconnection rcReplay = r_prev.rc;
-        if (r_prev.rc.IsCase1() || r_prev.rc.IsCase2())
-            XkToCurr(sc, r_prev.rc);
-        OffsetPathContext ctx;
-        const OffsetPathContext* pctx = nullptr;
-        if (r_prev.rc.k > 2)
+        Reconnection rcReplay = Reconnection::Init();
+        if (ok)
         {
-            ctx = OffsetPathContext::Init();
-            if (okReplay)
-                ctx = Replay_kGt2(sc, cur.pos, cur.normal, cur.eta_next, cur.surface, rcReplay, prm.alpha_min).Quantize();
-            pctx = &ctx;
+            r_prev.Load_Reconnection(recPrev);
+            rcReplay = r_prev.rc;
+            if (r_prev.rc.IsCase1() || r_prev.rc.IsCase2())
+                XkToCurr(sc, r_prev.rc);
         }
-        const OffsetPath shift = Shift2(sc, cur.pos, cur.normal, cur.eta_next, cur.surface, r_prev.rc, pctx, prm.alpha_min);
+        const bool needCtx = ok && r_prev.rc.k > 2;
+        ZR_PHASE();
+        OffsetPathContext ctx = Replay_kGt2_Sync(needCtx && okReplay, sc, cur.pos, cur.normal, cur.eta_next, cur.surface, rcReplay, prm.alpha_min);
+        if (needCtx && okReplay)
+            ctx = ctx.Quantize();
+        const OffsetPath shift = Shift2_Sync(ok, sc, cur.pos, cur.normal, cur.eta_next, cur.surface, r_prev.rc, &ctx, prm.alpha_min);
+        if (!ok)
+            return;         // past the last barrier
         const float targetLum_curr = Math::Luminance(shift.target);
         const float jacobian = r_prev.rc.partialJacobian > 0 ? shift.partialJacobian / r_prev.rc.partialJacobian : 0;
         bool changed = false;
@@ -698,13 +786,18 @@ namespace
         }
     }
 
-    __global__ void __launch_bounds__(64) k_spatial(SceneDev sc, FrameView f, RptParams prm, const zr_rpt_reservoir* __restrict__ resIn,
+    // A block is ZR_RPT_THREADS/64 consecutive 8x8 groups of the reference's swizzled dispatch (two waves each).
+    __global__ void ZR_LB(ZR_RPT_THREADS) k_spatial(SceneDev sc, FrameView f, RptParams prm, const zr_rpt_reservoir* __restrict__ resIn,
         zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target, float4* __restrict__ finalImg,
         const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
-        uint2 sg;
-        const uint2 sp = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 7, threadIdx.x >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
+        uint2 sg = make_uint2(0, 0);
+        const uint32_t groupFlat = blockIdx.x * (ZR_RPT_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t tInGroup = threadIdx.x & 63;
+        uint2 sp = make_uint2(0xffffffffu, 0xffffffffu);
+        if (groupFlat < dispX * dispY)
+            sp = SwizzleThreadGroup(groupFlat, 0, tInGroup & 7, tInGroup >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
         bool active = sp.x < f.W && sp.y < f.H;
         int x = (int)sp.x, y = (int)sp.y;
         if (active && prm.sortSpatial)
@@ -753,25 +846,34 @@ namespace
         zr_rpt_reservoir recN;
         Reservoir r_spatial = Reservoir::Init();
         uint32_t M_new = 0;
-        if (active)
         {
-            LoadRecord(&resIn[(size_t)ny * f.W + nx], recN);
-            r_spatial = Reservoir::Load_NonReconnection(recN);
             // ---- Reconnect_CtS (its result only matters under the StC LoadWSum condition) ----
-            if ((r_curr.w_sum != 0) && !r_curr.rc.Empty() && (r_spatial.M > 0))
+            bool doCtS = false;
+            Reservoir rc_full = Reservoir::Init();
+            Pixel pn, pr;
+            if (active)
             {
-                Reservoir rc_full = r_curr;
+                LoadRecord(&resIn[(size_t)ny * f.W + nx], recN);
+                r_spatial = Reservoir::Load_NonReconnection(recN);
+                doCtS = (r_curr.w_sum != 0) && !r_curr.rc.Empty() && (r_spatial.M > 0);
+            }
+            ZR_PHASE();
+            if (doCtS)
+            {
+                rc_full = r_curr;
                 rc_full.Load_Reconnection(rec);
-                const Pixel pn = LoadPixel(f, sc, f.core, f.coat, nx, ny, false, x, y);
-                OffsetPathContext ctx;
-                const OffsetPathContext* pctx = nullptr;
-                if (rc_full.rc.k > 2)
-                {
-                    const Pixel pr = LoadPixel(f, sc, f.core, f.coat, nx, ny, false, nx, ny);
-                    ctx = Replay_kGt2(sc, pr.pos, pr.normal, pr.eta_next, pr.surface, rc_full.rc, prm.alpha_min).Quantize();
-                    pctx = &ctx;
-                }
-                const OffsetPath shift = Shift2(sc, pn.pos, pn.normal, pn.eta_next, pn.surface, rc_full.rc, pctx, prm.alpha_min);
+                pn = LoadPixel(f, sc, f.core, f.coat, nx, ny, false, x, y);
+            }
+            const bool needCtx = doCtS && rc_full.rc.k > 2;
+            if (needCtx)
+                pr = LoadPixel(f, sc, f.core, f.coat, nx, ny, false, nx, ny);
+            ZR_PHASE();
+            OffsetPathContext ctx = Replay_kGt2_Sync(needCtx, sc, pr.pos, pr.normal, pr.eta_next, pr.surface, rc_full.rc, prm.alpha_min);
+            if (needCtx)
+                ctx = ctx.Quantize();
+            const OffsetPath shift = Shift2_Sync(doCtS, sc, pn.pos, pn.normal, pn.eta_next, pn.surface, rc_full.rc, &ctx, prm.alpha_min);
+            if (doCtS)
+            {
                 const float target_spatial = Math::Luminance(shift.target);
                 if (target_spatial > 0)
                 {
@@ -783,7 +885,8 @@ namespace
                     r_curr.w_sum *= m_curr;
                 }
             }
-            M_new = r_curr.M + r_spatial.M;
+            if (active)
+                M_new = r_curr.M + r_spatial.M;
         }
         waveAcc += WaveSum32(active && r_spatial.rc.Empty() ? r_curr.w_sum : 0.0f);
         if (active && r_spatial.rc.Empty())
@@ -797,21 +900,20 @@ namespace
             active = false;
         }
         bool changed = false;
-        OffsetPath shift;
-        shift.target = f3(0); shift.partialJacobian = 0; shift.surfKMin1Tramsmissive = false;
         if (active)
         {
             M_max = r_spatial.rc.x_k_in_motion ? (M_max < 4 ? M_max : 4) : M_max;
             r_spatial.rc.x_k_in_motion = false;
             r_spatial.Load_Reconnection(recN);
-            OffsetPathContext ctx;
-            const OffsetPathContext* pctx = nullptr;
-            if (r_spatial.rc.k > 2)
-            {
-                ctx = Replay_kGt2(sc, p.pos, p.normal, p.eta_next, p.surface, r_spatial.rc, prm.alpha_min).Quantize();
-                pctx = &ctx;
-            }
-            shift = Shift2(sc, p.pos, p.normal, p.eta_next, p.surface, r_spatial.rc, pctx, prm.alpha_min);
+        }
+        const bool needCtx = active && r_spatial.rc.k > 2;
+        ZR_PHASE();
+        OffsetPathContext ctx = Replay_kGt2_Sync(needCtx, sc, p.pos, p.normal, p.eta_next, p.surface, r_spatial.rc, prm.alpha_min);
+        if (needCtx)
+            ctx = ctx.Quantize();
+        const OffsetPath shift = Shift2_Sync(active, sc, p.pos, p.normal, p.eta_next, p.surface, r_spatial.rc, &ctx, prm.alpha_min);
+        if (active)
+        {
             const float targetLum_curr = Math::Luminance(shift.target);
             const float targetLum_spatial = r_spatial.W > 0 ? r_spatial.w_sum / r_spatial.W : 0;
             const float jacobian = r_spatial.rc.partialJacobian > 0 ? shift.partialJacobian / r_spatial.rc.partialJacobian : 0;
@@ -1000,13 +1102,13 @@ struct zr_indirect_pass
         {
             const uint32_t dispX = (width + 15) / 16, dispY = (height + 7) / 8;
             ZR_PROF("k_pathtrace", stream);
-            k_pathtrace<<<dim3(dispX, dispY), 128, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
+            k_pathtrace<<<(dispX * dispY + ZR_PT_THREADS / 128 - 1) / (ZR_PT_THREADS / 128), ZR_PT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
             ZR_LAUNCH_CHECK();
         }
         if (doTemporal && lastStage != ZR_RPT_STAGE_PATHTRACE)
         {
             ZR_PROF("k_temporal", stream);
-            k_temporal<<<dim3((width + 15) / 16, (rows + 7) / 8), 128, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
+            k_temporal<<<dim3((width + 31) / 32, (rows + ZR_RPT_THREADS / 32 - 1) / (ZR_RPT_THREADS / 32)), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
                 d_target, d_final);
             ZR_LAUNCH_CHECK();
         }
@@ -1029,7 +1131,7 @@ struct zr_indirect_pass
                 }
                 const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
                 ZR_PROF("k_spatial", stream);
-                k_spatial<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
+                k_spatial<<<(dispX * dispY + ZR_RPT_THREADS / 64 - 1) / (ZR_RPT_THREADS / 64), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
                     d_threadMap[1], dispX, dispY);
                 ZR_LAUNCH_CHECK();
             }

@@ -11,6 +11,38 @@
 #include "../../include/zr_fpmath.h"
 
 #define ZR_D __device__ __forceinline__
+// Call-graph shaping: the lighting kernels inline into megabytes of SASS if everything is forced inline, which
+// thrashes the instruction cache (ncu: ~80% of stall cycles "no instruction"). ZR_Fn functions become real calls
+// when ZR_NI_LEVEL >= n. Inlining does not change results (no fused contraction, no fast math).
+#ifndef ZR_NI_LEVEL
+#define ZR_NI_LEVEL 2
+#endif
+#define ZR_NI static __device__ __noinline__
+// Register budget of the lighting kernels: ZR_MAXREGS caps registers/thread through __launch_bounds__'s
+// min-blocks argument (0 = let ptxas take what it wants).
+#ifndef ZR_MAXREGS
+#define ZR_MAXREGS 0
+#endif
+#if ZR_MAXREGS > 0
+#define ZR_LB(threads) __launch_bounds__(threads, 65536 / ((threads) * ZR_MAXREGS))
+#else
+#define ZR_LB(threads) __launch_bounds__(threads)
+#endif
+#if ZR_NI_LEVEL >= 1
+#define ZR_F1 ZR_NI
+#else
+#define ZR_F1 ZR_D
+#endif
+#if ZR_NI_LEVEL >= 2
+#define ZR_F2 ZR_NI
+#else
+#define ZR_F2 ZR_D
+#endif
+#if ZR_NI_LEVEL >= 3
+#define ZR_F3 ZR_NI
+#else
+#define ZR_F3 ZR_D
+#endif
 
 namespace zr
 {

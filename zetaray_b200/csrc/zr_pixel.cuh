@@ -49,7 +49,7 @@ ZR_D GFlags FlagsAt(const uint4* __restrict__ core, uint32_t W, int x, int y, fl
 }
 
 // prev == false: current camera / jitter / frame number; true: previous frame's
-ZR_D Pixel LoadPixel(const FrameView& f, const SceneDev& sc, const uint4* __restrict__ core, const uint2* __restrict__ coat,
+ZR_F2 Pixel LoadPixel(const FrameView& f, const SceneDev& sc, const uint4* __restrict__ core, const uint2* __restrict__ coat,
     int px, int py, bool prev, int coatX, int coatY)
 {
     const zr_frame_constants& fc = f.fc;

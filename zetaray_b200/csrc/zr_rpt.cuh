@@ -273,19 +273,118 @@ namespace RPT
         return surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
     }
 
-    // ReSTIR_PT_NEE.hlsli:145-222
-    ZR_D DirectLightingEstimate NEE_Bsdf(const SceneDev& sc, float3 pos, float3 normal, const ShadingData& surface, int nextBounce,
-        int maxNumBounces, BSDF::BSDFSample& bsdfSample, HitEmissive& hitInfo, RNG& rng)
+    // -----------------------------------------------------------------------------------------------------------
+    // Block-synchronous phases.
+    //
+    // The lighting kernels execute far more code than the 32 KB instruction cache of an SM holds, and a warp
+    // walks through it almost linearly, so a free-running warp pays an L2 round trip per 128-byte instruction
+    // line (ncu: ~80% of stall cycles were "no instruction"). Every function below whose name ends in _Sync is
+    // therefore written as a sequence of predicated phases separated by ZR_PHASE() block barriers: all warps of a
+    // block enter a phase together, so a line fetched for the first warp is a cache hit for the others.
+    // Rules: a _Sync function is called from block-uniform control flow by every thread of the block, `act` says
+    // whether this thread has work; what used to be an early return clears a predicate instead. Per-thread results
+    // are unchanged -- the phases run the same statements in the same order for each thread.
+    // -----------------------------------------------------------------------------------------------------------
+#define ZR_PHASE() __syncthreads()
+
+    // ray set-up halves of Hit_Emissive::FindClosest / Hit::FindClosest / Visibility_Segment (zr_rt.cuh)
+    struct RaySetup { float3 o; float tmin, tmax; bool go; };
+
+    ZR_D RaySetup SetupClosestEmissive(float3 pos, float3 normal, float3 wi, bool transmissive)
+    {
+        RaySetup rs; rs.o = f3(0); rs.tmin = 0; rs.tmax = FLT_MAX_; rs.go = true;
+        const bool wiBackface = dot(normal, wi) <= 0;
+        if (wiBackface)
+        {
+            if (transmissive) normal = -normal;
+            else { rs.go = false; return rs; }
+        }
+        rs.o = RTU::OffsetRayRTG(pos, normal);
+        rs.tmin = wiBackface ? T_MIN_TR_RAY : T_MIN_REFL_RAY;
+        return rs;
+    }
+    ZR_D HitEmissive FinishClosestEmissive(const SceneDev& sc, const RaySetup& rs, const RayHit& h, float3 wi)
+    {
+        HitEmissive ret;
+        ret.hit = false;
+        ret.emissiveTriIdx = UINT32_MAX_;
+        ret.t = 0; ret.geoIdx = 0; ret.primIdx = 0; ret.bary = f2(0, 0); ret.lightPos = f3(0);
+        if (rs.go && h.hit)
+        {
+            ret.hit = true;
+            ret.bary = h.bary;
+            ret.t = h.t;
+            ret.geoIdx = __ldg(&sc.triMesh[h.tri]);
+            ret.primIdx = h.tri - __ldg(&sc.meshFirstTri[ret.geoIdx]);
+            const uint32_t baseEmissive = __ldg(&sc.instances[ret.geoIdx].BaseEmissiveTriOffset);
+            if (baseEmissive == UINT32_MAX_)
+                return ret;
+            ret.emissiveTriIdx = baseEmissive + ret.primIdx;
+            ret.lightPos = mad(h.t, wi, rs.o);
+        }
+        return ret;
+    }
+    ZR_D RaySetup SetupClosest(float3 pos, float3 normal, float3 wi, bool transmissive)
+    {
+        RaySetup rs; rs.o = f3(0); rs.tmin = 0; rs.tmax = FLT_MAX_; rs.go = true;
+        const float ndotwi = dot(normal, wi);
+        if (ndotwi == 0) { rs.go = false; return rs; }
+        const bool wiBackface = ndotwi < 0;
+        if (wiBackface)
+        {
+            if (!transmissive) { rs.go = false; return rs; }
+            normal = -normal;
+        }
+        rs.o = RTU::OffsetRayRTG(pos, normal);
+        rs.tmin = wiBackface ? T_MIN_TR_RAY : T_MIN_REFL_RAY;
+        return rs;
+    }
+    ZR_D Hit MissHit()
+    {
+        Hit ret;
+        ret.hit = false;
+        ret.ID = UINT32_MAX_;
+        ret.t = 0; ret.uv = f2(0, 0); ret.normal = f3(0); ret.meshIdx = 0; ret.matIdx = 0;
+        return ret;
+    }
+    ZR_D Hit FinishClosest(const SceneDev& sc, const RaySetup& rs, const RayHit& h)
+    {
+        if (!(rs.go && h.hit))
+            return MissHit();
+        const uint32_t mesh = __ldg(&sc.triMesh[h.tri]);
+        return HitAttributes(sc, mesh, h.tri - __ldg(&sc.meshFirstTri[mesh]), h.bary, h.t);
+    }
+    // go == false: the segment counts as occluded without tracing
+    ZR_D RaySetup SetupSegment(float3 origin, float3 wi, float rayT, float3 normal, uint32_t triID, bool transmissive)
+    {
+        RaySetup rs; rs.o = f3(0); rs.tmin = 0; rs.tmax = 0; rs.go = false;
+        if (triID == UINT32_MAX_) return rs;
+        if (rayT < 1e-6f) return rs;
+        const float ndotwi = dot(normal, wi);
+        if (ndotwi == 0) return rs;
+        const bool wiBackface = ndotwi < 0;
+        if (wiBackface)
+        {
+            if (transmissive) normal = -normal;
+            else return rs;
+        }
+        rs.o = RTU::OffsetRayRTG(origin, normal);
+        rs.tmin = 3e-6f;
+        rs.tmax = Math::PrevFloat32(rayT * 0.999f - Math::NextFloat32(rs.tmin));
+        rs.go = true;
+        return rs;
+    }
+
+    // ReSTIR_PT_NEE.hlsli:145-222 -- everything after the closest-hit query of the BSDF-sampled direction
+    ZR_D DirectLightingEstimate NEE_Bsdf_Finish(const SceneDev& sc, float3 pos, const ShadingData& surface, int nextBounce,
+        int maxNumBounces, BSDF::BSDFSample& bsdfSample, const HitEmissive& hitInfo)
     {
         DirectLightingEstimate ret = DirectLightingEstimate::Init();
         const bool specular = IsSpecularSurface(surface);
         const int numLightSamples = specular ? 0 : 1;
-        if (nextBounce <= maxNumBounces)
-            bsdfSample = BSDF::SampleBSDF(normal, surface, rng);
         const float wiPdf = bsdfSample.pdf;
         const float3 wi = bsdfSample.wi;
         const float3 f = bsdfSample.f;
-        hitInfo = FindClosestEmissive(sc, pos, normal, wi, surface.Transmissive());
         if (hitInfo.HitWasEmissive())
         {
             const zr_emissive_tri& emissive = sc.emissives[hitInfo.emissiveTriIdx];
@@ -317,97 +416,42 @@ namespace RPT
         return ret;
     }
 
-    // ReSTIR_PT_NEE.hlsli:224-302 (alias-table path)
-    ZR_D DirectLightingEstimate NEE_Emissive(const SceneDev& sc, float3 pos, float3 normal, ShadingData surface, RNG& rng)
+    // ReSTIR_PT_NEE.hlsli:224-302 (alias-table path) in three steps: light sample + BSDF value, shadow segment,
+    // sampler pdf + MIS. `surface` is the caller's copy with wi set (the reference passes it by value).
+    struct NeeLightState { DirectLightingEstimate ret; float3 ld; float t, lightPdf, dwdA; bool facing; };
+
+    ZR_D NeeLightState NEE_Emissive_Begin(const SceneDev& sc, float3 pos, float3 normal, ShadingData& surface, RNG& rng)
     {
-        DirectLightingEstimate ret = DirectLightingEstimate::Init();
-        ret.lt = Light::EMISSIVE;
-        ret.lobe = BSDF::ALL;
+        NeeLightState st;
+        st.ret = DirectLightingEstimate::Init();
+        st.ret.lt = Light::EMISSIVE;
+        st.ret.lobe = BSDF::ALL;
         Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
         const zr_emissive_tri& tri = sc.emissives[entry.idx];
         Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
         float3 le = Light::Le_EmissiveTriangle(tri);
-        const float lightPdf = entry.pdf * lightSample.pdf;
-        const uint32_t lightID = tri.ID;
-        const bool twoSided = Light::IsDoubleSided(tri);
-        const float t = length(lightSample.pos - pos);
-        const float3 wi = (lightSample.pos - pos) / t;
-        if ((dot(lightSample.normal, -wi) > 0) && (t > 0))
+        st.lightPdf = entry.pdf * lightSample.pdf;
+        st.t = length(lightSample.pos - pos);
+        const float3 wi = (lightSample.pos - pos) / st.t;
+        st.facing = (dot(lightSample.normal, -wi) > 0) && (st.t > 0);
+        st.ld = f3(0); st.dwdA = 0;
+        if (st.facing)
         {
-            const float dwdA = saturate(dot(lightSample.normal, -wi)) / (t * t);
+            st.dwdA = saturate(dot(lightSample.normal, -wi)) / (st.t * st.t);
             surface.SetWi(wi, normal);
-            float3 ld = le * BSDF::Unified(surface).f * dwdA;
-            if (dot(ld, ld) > 0)
-                ld *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
-            float bsdfPdf = 0;
-            if (dot(ld, ld) > 0)
-            {
-                bsdfPdf = BSDF::BSDFSamplerPdf(normal, surface, wi, rng);
-                bsdfPdf *= dwdA;
-            }
-            ret.ld = RT::PowerHeuristic(lightPdf, bsdfPdf, ld);
-            ret.le = le; ret.wi = wi; ret.pdf_solidAngle = lightPdf / dwdA; ret.dwdA = dwdA; ret.ID = lightID;
-            ret.pos = lightSample.pos; ret.normal = lightSample.normal; ret.pdf_light = lightPdf; ret.twoSided = twoSided;
+            st.ld = le * BSDF::Unified(surface).f * st.dwdA;
+            st.ret.le = le; st.ret.wi = wi; st.ret.ID = tri.ID;
+            st.ret.pos = lightSample.pos; st.ret.normal = lightSample.normal; st.ret.twoSided = Light::IsDoubleSided(tri);
         }
-        return ret;
+        return st;
     }
-
-    // ReSTIR_PT_NEE.hlsli:306-343
-    ZR_D DirectLightingEstimate EvalDirect_Emissive_Case2(float3 normal, ShadingData surface, float3 wi, float3 le, float dwdA,
-        float lightPdf, LOBE lobe, RNG& rngReplay, RNG& rngNEE)
+    ZR_D DirectLightingEstimate NEE_Emissive_Finish(const NeeLightState& st, float bsdfPdf)
     {
-        surface.SetWi(wi, normal);
-        float3 ld = le * BSDF::Unified(surface).f * dwdA;
-        DirectLightingEstimate ret = DirectLightingEstimate::Init();
-        if (dot(ld, ld) == 0)
-            return ret;
-        if (lobe == BSDF::ALL)
+        DirectLightingEstimate ret = st.ret;
+        if (st.facing)
         {
-            rngNEE.Uniform4D();
-            float bsdfPdf = BSDF::BSDFSamplerPdf(normal, surface, wi, rngNEE);
-            float bsdfPdf_area = bsdfPdf * dwdA;
-            ret.ld = RT::PowerHeuristic(lightPdf, bsdfPdf_area, ld);
-            ret.pdf_solidAngle = 1.0f;
-        }
-        else
-        {
-            BSDF::BSDFSamplerEval eval = BSDF::EvalBSDFSampler(normal, surface, wi, lobe, rngReplay);
-            const bool specular = IsSpecularSurface(surface);
-            float bsdfPdf_area = eval.pdf * dwdA;
-            ret.ld = specular ? (bsdfPdf_area > 0 ? ld / bsdfPdf_area : f3(0)) : RT::PowerHeuristic(bsdfPdf_area, lightPdf, ld);
-            ret.pdf_solidAngle = eval.pdf;
-        }
-        return ret;
-    }
-
-    // ReSTIR_PT_NEE.hlsli:345-391
-    ZR_D DirectLightingEstimate EvalDirect_Emissive_Case3(const SceneDev& sc, float3 pos, float3 normal, ShadingData surface, float3 wi,
-        float t, float3 le, float3 lightNormal, float lightPdf, uint32_t lightID, bool twoSided, LOBE lobe, RNG& rngReplay, RNG& rngNEE)
-    {
-        float wiDotLightNormal = dot(lightNormal, -wi);
-        float dwdA = fabsf(wiDotLightNormal) / (t * t);
-        surface.SetWi(wi, normal);
-        float3 ld = (wiDotLightNormal > 0) || twoSided ? le * BSDF::Unified(surface).f * dwdA : f3(0);
-        if (dot(ld, ld) > 0)
-            ld *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
-        DirectLightingEstimate ret = DirectLightingEstimate::Init();
-        if (dot(ld, ld) == 0)
-            return ret;
-        if (lobe == BSDF::ALL)
-        {
-            rngNEE.Uniform4D();
-            float bsdfPdf = BSDF::BSDFSamplerPdf(normal, surface, wi, rngNEE);
-            float bsdfPdf_area = bsdfPdf * dwdA;
-            ret.ld = RT::PowerHeuristic(lightPdf, bsdfPdf_area, ld);
-            ret.pdf_solidAngle = 1.0f;
-        }
-        else
-        {
-            BSDF::BSDFSamplerEval eval = BSDF::EvalBSDFSampler(normal, surface, wi, lobe, rngReplay);
-            const bool specular = IsSpecularSurface(surface);
-            float bsdfPdf_area = eval.pdf * dwdA;
-            ret.ld = specular ? (bsdfPdf_area > 0 ? ld / bsdfPdf_area : f3(0)) : RT::PowerHeuristic(bsdfPdf_area, lightPdf, ld);
-            ret.pdf_solidAngle = bsdfPdf_area;
+            ret.ld = RT::PowerHeuristic(st.lightPdf, bsdfPdf, st.ld);
+            ret.pdf_solidAngle = st.lightPdf / st.dwdA; ret.dwdA = st.dwdA; ret.pdf_light = st.lightPdf;
         }
         return ret;
     }
@@ -466,166 +510,276 @@ namespace RPT
         }
     };
 
-    // Shift.hlsli:377-474
-    ZR_D void Replay(const SceneDev& sc, int numBounces, BSDF::BSDFSample bsdfSample, float alpha_min, OffsetPathContext& ctx)
-    {
-        ctx.throughput = bsdfSample.bsdfOverPdf;
-        int bounce = 0;
-        ctx.eta_curr = dot(ctx.normal, bsdfSample.wi) < 0 ? ctx.eta_next : BSDF::ETA_AIR;
-        bool inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
-        float alpha_lobe_prev = BSDF::LobeAlpha(ctx.surface, bsdfSample.lobe);
-        LOBE lobe_prev = bsdfSample.lobe;
-        while (true)
-        {
-            Hit hitInfo = FindClosest(sc, ctx.pos, ctx.normal, bsdfSample.wi, ctx.surface.Transmissive());
-            if (!hitInfo.hit) { ctx.throughput = f3(0); return; }
-            if (!GetMaterialData(sc, -bsdfSample.wi, ctx.eta_curr, hitInfo, ctx.surface, ctx.eta_next)) { ctx.throughput = f3(0); return; }
-            ctx.pos = mad(hitInfo.t, bsdfSample.wi, ctx.pos);
-            ctx.normal = hitInfo.normal;
-            bounce++;
-            if (inTranslucentMedium && (ctx.surface.trDepth > 0))
-            {
-                float3 c = ctx.surface.baseColor_Fr0_TrCol;
-                float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / ctx.surface.trDepth;
-                ctx.throughput *= f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
-            }
-            if (bounce >= numBounces)
-                break;
-            bsdfSample = BSDF::SampleBSDF(ctx.normal, ctx.surface, ctx.rngReplay);
-            if (dot(bsdfSample.bsdfOverPdf, bsdfSample.bsdfOverPdf) == 0) { ctx.throughput = f3(0); return; }
-            const float alpha_lobe = BSDF::LobeAlpha(ctx.surface, bsdfSample.lobe);
-            if (CanReconnect(alpha_lobe_prev, alpha_lobe, lobe_prev, bsdfSample.lobe, alpha_min)) { ctx.throughput = f3(0); return; }
-            const bool transmitted = dot(ctx.normal, bsdfSample.wi) < 0;
-            ctx.eta_curr = transmitted ? (ctx.eta_curr == BSDF::ETA_AIR ? ctx.eta_next : BSDF::ETA_AIR) : ctx.eta_curr;
-            ctx.throughput *= bsdfSample.bsdfOverPdf;
-            inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
-            alpha_lobe_prev = alpha_lobe;
-            lobe_prev = bsdfSample.lobe;
-        }
-    }
-
-    // Shift.hlsli:818-859
-    ZR_D OffsetPathContext Replay_kGt2(const SceneDev& sc, float3 pos, float3 normal, float ior, const ShadingData& surface,
+    // Shift.hlsli:377-474 (Replay) + :818-859 (Replay_kGt2) as one phase loop: random replay of the first k-2
+    // bounces from a new primary vertex. Returns the unquantised context; throughput == 0 means the replay failed.
+    ZR_D OffsetPathContext Replay_kGt2_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, float ior, const ShadingData& surface,
         const Reconnection& rc, float alpha_min)
     {
         OffsetPathContext ctx = OffsetPathContext::Init();
-        ctx.pos = pos; ctx.normal = normal; ctx.surface = surface;
-        ctx.rngReplay = RNG::InitSeed(rc.seed_replay);
-        ctx.eta_curr = BSDF::ETA_AIR; ctx.eta_next = ior;
-        ctx.throughput = f3(1);
+        BSDF::BSDFSample bsdfSample = BSDF::BSDFSample::Init();
         const int numBounces = (int)rc.k - 2;
-        BSDF::BSDFSample bsdfSample = BSDF::SampleBSDF(ctx.normal, ctx.surface, ctx.rngReplay);
-        if (dot(bsdfSample.bsdfOverPdf, bsdfSample.bsdfOverPdf) == 0) { ctx.throughput = f3(0); return ctx; }
-        Replay(sc, numBounces, bsdfSample, alpha_min, ctx);
+        int bounce = 0;
+        bool go = act, inTranslucentMedium = false;
+        float alpha_lobe_prev = 0;
+        LOBE lobe_prev = BSDF::DIFFUSE_R;
+        if (go)
+        {
+            ctx.pos = pos; ctx.normal = normal; ctx.surface = surface;
+            ctx.rngReplay = RNG::InitSeed(rc.seed_replay);
+            ctx.eta_curr = BSDF::ETA_AIR; ctx.eta_next = ior;
+            ctx.throughput = f3(1);
+            bsdfSample = BSDF::SampleBSDF(ctx.normal, ctx.surface, ctx.rngReplay);
+            if (dot(bsdfSample.bsdfOverPdf, bsdfSample.bsdfOverPdf) == 0) { ctx.throughput = f3(0); go = false; }
+            else
+            {
+                ctx.throughput = bsdfSample.bsdfOverPdf;
+                ctx.eta_curr = dot(ctx.normal, bsdfSample.wi) < 0 ? ctx.eta_next : BSDF::ETA_AIR;
+                inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
+                alpha_lobe_prev = BSDF::LobeAlpha(ctx.surface, bsdfSample.lobe);
+                lobe_prev = bsdfSample.lobe;
+            }
+        }
+        while (__syncthreads_or(go))
+        {
+            RaySetup rs; rs.go = false;
+            RayHit h; h.hit = false;
+            if (go)
+            {
+                rs = SetupClosest(ctx.pos, ctx.normal, bsdfSample.wi, ctx.surface.Transmissive());
+                if (rs.go)
+                    h = TraceClosest(sc, rs.o, bsdfSample.wi, rs.tmin, FLT_MAX_);
+            }
+            ZR_PHASE();
+            if (go)
+            {
+                Hit hitInfo = FinishClosest(sc, rs, h);
+                if (!hitInfo.hit) { ctx.throughput = f3(0); go = false; }
+                else if (!GetMaterialData(sc, -bsdfSample.wi, ctx.eta_curr, hitInfo, ctx.surface, ctx.eta_next)) { ctx.throughput = f3(0); go = false; }
+                else
+                {
+                    ctx.pos = mad(hitInfo.t, bsdfSample.wi, ctx.pos);
+                    ctx.normal = hitInfo.normal;
+                    bounce++;
+                    if (inTranslucentMedium && (ctx.surface.trDepth > 0))
+                    {
+                        float3 c = ctx.surface.baseColor_Fr0_TrCol;
+                        float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / ctx.surface.trDepth;
+                        ctx.throughput *= f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
+                    }
+                    if (bounce >= numBounces)
+                        go = false;         // replay complete
+                }
+            }
+            ZR_PHASE();
+            if (go)
+            {
+                bsdfSample = BSDF::SampleBSDF(ctx.normal, ctx.surface, ctx.rngReplay);
+                if (dot(bsdfSample.bsdfOverPdf, bsdfSample.bsdfOverPdf) == 0) { ctx.throughput = f3(0); go = false; }
+                else
+                {
+                    const float alpha_lobe = BSDF::LobeAlpha(ctx.surface, bsdfSample.lobe);
+                    if (CanReconnect(alpha_lobe_prev, alpha_lobe, lobe_prev, bsdfSample.lobe, alpha_min)) { ctx.throughput = f3(0); go = false; }
+                    else
+                    {
+                        const bool transmitted = dot(ctx.normal, bsdfSample.wi) < 0;
+                        ctx.eta_curr = transmitted ? (ctx.eta_curr == BSDF::ETA_AIR ? ctx.eta_next : BSDF::ETA_AIR) : ctx.eta_curr;
+                        ctx.throughput *= bsdfSample.bsdfOverPdf;
+                        inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
+                        alpha_lobe_prev = alpha_lobe;
+                        lobe_prev = bsdfSample.lobe;
+                    }
+                }
+            }
+        }
         return ctx;
     }
 
-    // Shift.hlsli:476-546
-    ZR_D float StepPath(const SceneDev& sc, OffsetPathContext& ctx, float alpha_min, const Reconnection& rc)
+    // Shift.hlsli:662-816 (Emissive == true) with StepPath (:476-546) and EvalDirect_Emissive_Case2/3
+    // (ReSTIR_PT_NEE.hlsli:306-391) unrolled into seven phases:
+    //   sampler eval at x_{k-1} | closest hit towards x_k | attributes + material at y_k | BSDF value at the
+    //   reconnection vertex | shadow segment (case 3) | sampler eval (case 1, or lobe-sampled NEE) | sampler pdf (light-sampled NEE)
+    // `replayed` = context from Replay_kGt2_Sync (already quantised) when k > 2.
+    ZR_D OffsetPath Shift2_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, float ior, const ShadingData& surface,
+        const Reconnection& rc, const OffsetPathContext* replayed, float alpha_min)
     {
-        if (!BSDF::IsLobeValid(ctx.surface, rc.lobe_k_min_1))
-            return 0;
-        float alpha_lobe_k_min_1 = BSDF::LobeAlpha(ctx.surface, rc.lobe_k_min_1);
-        if (!CanReconnect(alpha_lobe_k_min_1, 1, rc.lobe_k_min_1, rc.lobe_k, alpha_min))
-            return 0;
-        float3 w_k_min_1 = normalize(rc.x_k - ctx.pos);
-        BSDF::BSDFSamplerEval eval = BSDF::EvalBSDFSampler(ctx.normal, ctx.surface, w_k_min_1, rc.lobe_k_min_1, ctx.rngReplay);
-        if (dot(eval.bsdfOverPdf, eval.bsdfOverPdf) == 0)
-            return 0;
-        Hit hitInfo = FindClosest(sc, ctx.pos, ctx.normal, w_k_min_1, ctx.surface.Transmissive());
-        if (!hitInfo.hit || (hitInfo.ID != rc.ID))
-            return 0;
-        const float3 y_k = mad(hitInfo.t, w_k_min_1, ctx.pos);
-        const bool transmitted = dot(ctx.normal, w_k_min_1) < 0;
-        ctx.eta_curr = transmitted ? (ctx.eta_curr == BSDF::ETA_AIR ? ctx.eta_next : BSDF::ETA_AIR) : ctx.eta_curr;
-        const bool inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
-        if (!GetMaterialData(sc, -w_k_min_1, ctx.eta_curr, hitInfo, ctx.surface, ctx.eta_next))
-            return 0;
-        if (inTranslucentMedium && (ctx.surface.trDepth > 0))
-        {
-            float3 c = ctx.surface.baseColor_Fr0_TrCol;
-            float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / ctx.surface.trDepth;
-            ctx.throughput *= f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
-        }
-        float partialJacobian = eval.pdf;
-        partialJacobian *= fabsf(dot(-w_k_min_1, hitInfo.normal));
-        partialJacobian /= (hitInfo.t * hitInfo.t);
-        ctx.pos = y_k;
-        ctx.normal = hitInfo.normal;
-        ctx.throughput *= eval.bsdfOverPdf;
-        return partialJacobian;
-    }
-
-    // Shift.hlsli:662-816 (Emissive == true). `replayed` = context from Replay_kGt2 (already quantised) when k > 2.
-    ZR_D OffsetPath Shift2(const SceneDev& sc, float3 pos, float3 normal, float ior, const ShadingData& surface, const Reconnection& rc,
-        const OffsetPathContext* replayed, float alpha_min)
-    {
-        OffsetPathContext ctx = OffsetPathContext::Init();
-        ctx.pos = pos; ctx.normal = normal; ctx.surface = surface;
-        ctx.rngReplay = RNG::InitSeed(rc.seed_replay);
-        ctx.eta_curr = BSDF::ETA_AIR; ctx.eta_next = ior;
-        ctx.throughput = f3(1);
         OffsetPath ret; ret.target = f3(0); ret.partialJacobian = 0; ret.surfKMin1Tramsmissive = false;
-        const int numBounces = (int)rc.k - 2;
-        if (numBounces != 0)
+        OffsetPathContext ctx = OffsetPathContext::Init();
+        const bool case1 = rc.IsCase1(), case2 = rc.IsCase2(), case3 = rc.IsCase3();
+        bool go = act;
+        if (go)
         {
-            ctx = *replayed;
-            if (dot(ctx.throughput, ctx.throughput) == 0)
-                return ret;
-            // OffsetPathContext::Load leaves rngReplay at 0; the reference then advances it (Shift.hlsli:705-713)
-            ctx.rngReplay.State = 0;
-            for (int bounce = 0; bounce < numBounces; bounce++)
+            ctx.pos = pos; ctx.normal = normal; ctx.surface = surface;
+            ctx.rngReplay = RNG::InitSeed(rc.seed_replay);
+            ctx.eta_curr = BSDF::ETA_AIR; ctx.eta_next = ior;
+            ctx.throughput = f3(1);
+            const int numBounces = (int)rc.k - 2;
+            if (numBounces != 0)
             {
-                ctx.rngReplay.Uniform4D();
-                ctx.rngReplay.Uniform4D();
-                ctx.rngReplay.Uniform();
+                ctx = *replayed;
+                if (dot(ctx.throughput, ctx.throughput) == 0)
+                    go = false;
+                else
+                {
+                    // OffsetPathContext::Load leaves rngReplay at 0; the reference then advances it (Shift.hlsli:705-713)
+                    ctx.rngReplay.State = 0;
+                    for (int bounce = 0; bounce < numBounces; bounce++)
+                    {
+                        ctx.rngReplay.Uniform4D();
+                        ctx.rngReplay.Uniform4D();
+                        ctx.rngReplay.Uniform();
+                    }
+                }
             }
+            if (go)
+                ret.surfKMin1Tramsmissive = ctx.surface.specTr;
         }
-        ret.surfKMin1Tramsmissive = ctx.surface.specTr;
-        if (!rc.IsCase3())
-        {
-            ret.partialJacobian = StepPath(sc, ctx, alpha_min, rc);
-            if (ret.partialJacobian == 0)
-                return ret;
-            if (rc.IsCase1())
-            {
-                float3 w_k = rc.w_k_lightNormal_w_sky;
-                BSDF::BSDFSamplerEval eval = BSDF::EvalBSDFSampler(ctx.normal, ctx.surface, w_k, rc.lobe_k, ctx.rngReplay);
-                ctx.throughput *= eval.bsdfOverPdf;
-                ret.target = ctx.throughput * rc.L;
-                ret.partialJacobian *= eval.pdf;
-                return ret;
-            }
-        }
-        else
+        // ---- StepPath (cases 1, 2): x_{k-1} -> x_k ----
+        bool step = go && !case3;
+        float3 w_k_min_1 = f3(0);
+        if (step)
         {
             if (!BSDF::IsLobeValid(ctx.surface, rc.lobe_k_min_1))
-                return ret;
-            float alpha_lobe_k_min_1 = BSDF::LobeAlpha(ctx.surface, rc.lobe_k_min_1);
-            if (alpha_lobe_k_min_1 < alpha_min)
-                return ret;
+                step = false;
+            else
+            {
+                const float alpha_lobe_k_min_1 = BSDF::LobeAlpha(ctx.surface, rc.lobe_k_min_1);
+                if (!CanReconnect(alpha_lobe_k_min_1, 1, rc.lobe_k_min_1, rc.lobe_k, alpha_min))
+                    step = false;
+            }
+            if (step) w_k_min_1 = normalize(rc.x_k - ctx.pos);
+            else go = false;
         }
+        if (go && case3)
+        {
+            if (!BSDF::IsLobeValid(ctx.surface, rc.lobe_k_min_1))
+                go = false;
+            else if (BSDF::LobeAlpha(ctx.surface, rc.lobe_k_min_1) < alpha_min)
+                go = false;
+        }
+        ZR_PHASE();
+        BSDF::BSDFSamplerEval eval; eval.pdf = 0; eval.bsdfOverPdf = f3(0); eval.f = f3(0);
+        if (step)
+        {
+            eval = BSDF::EvalBSDFSampler(ctx.normal, ctx.surface, w_k_min_1, rc.lobe_k_min_1, ctx.rngReplay);
+            if (dot(eval.bsdfOverPdf, eval.bsdfOverPdf) == 0) { step = false; go = false; }
+        }
+        ZR_PHASE();
+        RaySetup rs; rs.go = false;
+        RayHit h; h.hit = false;
+        if (step)
+        {
+            rs = SetupClosest(ctx.pos, ctx.normal, w_k_min_1, ctx.surface.Transmissive());
+            if (rs.go)
+                h = TraceClosest(sc, rs.o, w_k_min_1, rs.tmin, FLT_MAX_);
+        }
+        ZR_PHASE();
+        if (step)
+        {
+            Hit hitInfo = FinishClosest(sc, rs, h);
+            if (!hitInfo.hit || (hitInfo.ID != rc.ID)) { step = false; go = false; }
+            else
+            {
+                const float3 y_k = mad(hitInfo.t, w_k_min_1, ctx.pos);
+                const bool transmitted = dot(ctx.normal, w_k_min_1) < 0;
+                ctx.eta_curr = transmitted ? (ctx.eta_curr == BSDF::ETA_AIR ? ctx.eta_next : BSDF::ETA_AIR) : ctx.eta_curr;
+                const bool inTranslucentMedium = ctx.eta_curr != BSDF::ETA_AIR;
+                if (!GetMaterialData(sc, -w_k_min_1, ctx.eta_curr, hitInfo, ctx.surface, ctx.eta_next)) { step = false; go = false; }
+                else
+                {
+                    if (inTranslucentMedium && (ctx.surface.trDepth > 0))
+                    {
+                        float3 c = ctx.surface.baseColor_Fr0_TrCol;
+                        float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / ctx.surface.trDepth;
+                        ctx.throughput *= f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
+                    }
+                    float partialJacobian = eval.pdf;
+                    partialJacobian *= fabsf(dot(-w_k_min_1, hitInfo.normal));
+                    partialJacobian /= (hitInfo.t * hitInfo.t);
+                    ctx.pos = y_k;
+                    ctx.normal = hitInfo.normal;
+                    ctx.throughput *= eval.bsdfOverPdf;
+                    ret.partialJacobian = partialJacobian;
+                    if (partialJacobian == 0) go = false;
+                }
+            }
+        }
+        // ---- the reconnection vertex: case 1 re-evaluates the sampler towards x_{k+1}; cases 2/3 re-evaluate NEE ----
+        const bool nee = go && !case1;
+        ShadingData surfWi = ctx.surface;          // EvalDirect_* take the surface by value and set wi on the copy
+        float3 wiE = rc.w_k_lightNormal_w_sky;      // case 1 / 2: w_k
+        float3 nrmE = ctx.normal;
+        LOBE lobeE = rc.lobe_k;
+        float dwdA = rc.dwdA, tE = 0, lightPdfE = rc.lightPdf;
+        float3 ld = f3(0);
         RNG rngNEE = RNG::InitSeed(rc.seed_nee);
-        if (rc.IsCase2())
+        bool needBsdf = nee;
+        if (nee && case3)
         {
-            float3 w_k = rc.w_k_lightNormal_w_sky;
-            DirectLightingEstimate ls = EvalDirect_Emissive_Case2(ctx.normal, ctx.surface, w_k, rc.L, rc.dwdA, rc.lightPdf,
-                rc.lobe_k, ctx.rngReplay, rngNEE);
-            ret.target = ctx.throughput * ls.ld;
-            ret.partialJacobian *= ls.pdf_solidAngle;
-        }
-        else
-        {
-            float3 wi_k_min_1 = rc.x_k - ctx.pos;
-            float t = length(wi_k_min_1);
-            wi_k_min_1 /= t;
-            float3 lightNormal = rc.w_k_lightNormal_w_sky;
-            bool twoSided = rc.lightPdf > 0;
+            wiE = rc.x_k - ctx.pos;
+            tE = length(wiE);
+            wiE /= tE;
+            const float3 lightNormal = rc.w_k_lightNormal_w_sky;
+            const bool twoSided = rc.lightPdf > 0;
+            lightPdfE = fabsf(rc.lightPdf);
             // note: the reference passes ctx.pos for the normal argument (Shift.hlsli:765-767)
-            DirectLightingEstimate ls = EvalDirect_Emissive_Case3(sc, ctx.pos, ctx.pos, ctx.surface, wi_k_min_1, t, rc.L, lightNormal,
-                fabsf(rc.lightPdf), rc.ID, twoSided, rc.lobe_k_min_1, ctx.rngReplay, rngNEE);
-            ret.target = ctx.throughput * ls.ld;
-            ret.partialJacobian = ls.pdf_solidAngle;
+            nrmE = ctx.pos;
+            lobeE = rc.lobe_k_min_1;
+            const float wiDotLightNormal = dot(lightNormal, -wiE);
+            dwdA = fabsf(wiDotLightNormal) / (tE * tE);
+            needBsdf = (wiDotLightNormal > 0) || twoSided;
+        }
+        if (nee)
+            surfWi.SetWi(wiE, nrmE);
+        ZR_PHASE();
+        if (nee && needBsdf)
+            ld = rc.L * BSDF::Unified(surfWi).f * dwdA;
+        ZR_PHASE();
+        if (nee && case3 && (dot(ld, ld) > 0))
+        {
+            const RaySetup seg = SetupSegment(ctx.pos, wiE, tE, nrmE, rc.ID, surfWi.Transmissive());
+            const bool visible = seg.go ? !TraceAnyExcept(sc, seg.o, wiE, seg.tmin, seg.tmax, rc.ID) : false;
+            ld *= visible ? 1.0f : 0.0f;
+        }
+        ZR_PHASE();
+        const bool lit = nee && !(dot(ld, ld) == 0);
+        const bool lightSampled = lit && (lobeE == BSDF::ALL);
+        const bool useEval = (go && case1) || (lit && !lightSampled);
+        BSDF::BSDFSamplerEval ev; ev.pdf = 0; ev.bsdfOverPdf = f3(0); ev.f = f3(0);
+        if (useEval)
+            ev = BSDF::EvalBSDFSampler(nrmE, surfWi, wiE, lobeE, ctx.rngReplay);
+        ZR_PHASE();
+        float bsdfPdf = 0;
+        if (lightSampled)
+        {
+            rngNEE.Uniform4D();
+            bsdfPdf = BSDF::BSDFSamplerPdf(nrmE, surfWi, wiE, rngNEE);
+        }
+        if (go && case1)
+        {
+            ctx.throughput *= ev.bsdfOverPdf;
+            ret.target = ctx.throughput * rc.L;
+            ret.partialJacobian *= ev.pdf;
+        }
+        else if (nee)
+        {
+            float3 ls_ld = f3(0);
+            float ls_pdf_solidAngle = 0;
+            if (lightSampled)
+            {
+                const float bsdfPdf_area = bsdfPdf * dwdA;
+                ls_ld = RT::PowerHeuristic(lightPdfE, bsdfPdf_area, ld);
+                ls_pdf_solidAngle = 1.0f;
+            }
+            else if (lit)
+            {
+                const bool specular = IsSpecularSurface(surfWi);
+                const float bsdfPdf_area = ev.pdf * dwdA;
+                ls_ld = specular ? (bsdfPdf_area > 0 ? ld / bsdfPdf_area : f3(0)) : RT::PowerHeuristic(bsdfPdf_area, lightPdfE, ld);
+                ls_pdf_solidAngle = case2 ? ev.pdf : bsdfPdf_area;
+            }
+            ret.target = ctx.throughput * ls_ld;
+            if (case2) ret.partialJacobian *= ls_pdf_solidAngle;
+            else ret.partialJacobian = ls_pdf_solidAngle;
         }
         return ret;
     }

@@ -71,7 +71,7 @@ ZR_D uint32_t TriID(const SceneDev& sc, uint32_t tri)
 
 // Mode: 0 = closest hit, 1 = any hit whose ID differs from ignoreID (UINT32_MAX = none ignored)
 template<int Mode>
-ZR_D RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax, uint32_t ignoreID)
+ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float tmax, uint32_t ignoreID)
 {
     RayHit best;
     best.hit = false; best.t = tmax; best.bary = f2(0, 0); best.tri = 0xffffffffu;
