@@ -142,83 +142,111 @@ struct EmissiveData
     }
 };
 
-ZR_D Reservoir RIS_InitialCandidates(const SceneDev& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface,
+// RIS over BSDF and light samples (Resampling.hlsli:116-331) as block-synchronous phases (zr_rpt.cuh): every
+// thread of the block walks the same 2 + 3 sample slots, `act` / the per-pixel sample counts predicate the work.
+#define ZR_PHASE() __syncthreads()
+ZR_D Reservoir RIS_InitialCandidates_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface,
     int numBsdfSamples, RNG& rng)
 {
     Reservoir r = Reservoir::Init();
     const bool specular = surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
     const int numLightSamples = !specular ? 3 : 0;
-    for (int s_b = 0; s_b < numBsdfSamples; s_b++)
+    for (int s_b = 0; s_b < 2; s_b++)
     {
-        BSDF::BSDFSample bsdfSample = BSDF::SampleBSDF_NoDiffuse(normal, surface, rng);
-        float3 wi = bsdfSample.wi;
-        float pdf_w = bsdfSample.pdf;
-        BSDFHitInfo hitInfo = FindClosestHitDI(sc, pos, normal, wi, surface.Transmissive());
-        float w_b = 0;
-        float3 le = f3(0), lightNormal = f3(0), target = f3(0);
-        uint32_t emissiveID = UINT32_MAX_;
-        bool doubleSided = false;
-        if (hitInfo.hit)
+        const bool go = act && (s_b < numBsdfSamples);
+        BSDF::BSDFSample bsdfSample = BSDF::BSDFSample::Init();
+        ZR_PHASE();
+        if (go)
+            bsdfSample = BSDF::SampleBSDF_NoDiffuse(normal, surface, rng);
+        ZR_PHASE();
+        BSDFHitInfo hitInfo;
+        hitInfo.hit = false;
+        if (go)
+            hitInfo = FindClosestHitDI(sc, pos, normal, bsdfSample.wi, surface.Transmissive());
+        ZR_PHASE();
+        if (go)
         {
-            const zr_emissive_tri& emissive = sc.emissives[hitInfo.emissiveTriIdx];
-            le = Light::Le_EmissiveTriangle(emissive);
-            const float3 vtx0 = Light::Vtx0(emissive);
-            const float3 vtx1 = Light::DecodeEmissiveTriV1(emissive);
-            const float3 vtx2 = Light::DecodeEmissiveTriV2(emissive);
-            lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
-            float twoArea = length(lightNormal);
-            lightNormal = dot(lightNormal, lightNormal) == 0 ? f3(0) : lightNormal / twoArea;
-            lightNormal = Light::IsDoubleSided(emissive) && dot(-wi, lightNormal) < 0 ? -lightNormal : lightNormal;
-            doubleSided = Light::IsDoubleSided(emissive);
-            emissiveID = emissive.ID;
-            if (dot(-wi, lightNormal) > 0)
+            float3 wi = bsdfSample.wi;
+            float pdf_w = bsdfSample.pdf;
+            float w_b = 0;
+            float3 le = f3(0), lightNormal = f3(0), target = f3(0);
+            uint32_t emissiveID = UINT32_MAX_;
+            bool doubleSided = false;
+            if (hitInfo.hit)
             {
-                const float lightSourcePdf = sc.aliasTable[hitInfo.emissiveTriIdx].CachedP_Orig;
-                const float pdf_light = lightSourcePdf * (1.0f / (0.5f * twoArea));
-                const float dwdA = saturate(dot(lightNormal, -wi)) / (hitInfo.t * hitInfo.t);
-                pdf_w *= dwdA;
-                const bool sampleIsSpecular = (surface.GlossSpecular() && bsdfSample.lobe == BSDF::GLOSSY_R) ||
-                    (surface.CoatSpecular() && bsdfSample.lobe == BSDF::COAT);
-                float denom = (float)numBsdfSamples * pdf_w + (!sampleIsSpecular ? 1.0f : 0.0f) * (float)numLightSamples * pdf_light;
-                const float m_i = 1.0f / denom;
-                target = le * bsdfSample.f * dwdA;
-                w_b = m_i * Math::Luminance(target);
+                const zr_emissive_tri& emissive = sc.emissives[hitInfo.emissiveTriIdx];
+                le = Light::Le_EmissiveTriangle(emissive);
+                const float3 vtx0 = Light::Vtx0(emissive);
+                const float3 vtx1 = Light::DecodeEmissiveTriV1(emissive);
+                const float3 vtx2 = Light::DecodeEmissiveTriV2(emissive);
+                lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
+                float twoArea = length(lightNormal);
+                lightNormal = dot(lightNormal, lightNormal) == 0 ? f3(0) : lightNormal / twoArea;
+                lightNormal = Light::IsDoubleSided(emissive) && dot(-wi, lightNormal) < 0 ? -lightNormal : lightNormal;
+                doubleSided = Light::IsDoubleSided(emissive);
+                emissiveID = emissive.ID;
+                if (dot(-wi, lightNormal) > 0)
+                {
+                    const float lightSourcePdf = sc.aliasTable[hitInfo.emissiveTriIdx].CachedP_Orig;
+                    const float pdf_light = lightSourcePdf * (1.0f / (0.5f * twoArea));
+                    const float dwdA = saturate(dot(lightNormal, -wi)) / (hitInfo.t * hitInfo.t);
+                    pdf_w *= dwdA;
+                    const bool sampleIsSpecular = (surface.GlossSpecular() && bsdfSample.lobe == BSDF::GLOSSY_R) ||
+                        (surface.CoatSpecular() && bsdfSample.lobe == BSDF::COAT);
+                    float denom = (float)numBsdfSamples * pdf_w + (!sampleIsSpecular ? 1.0f : 0.0f) * (float)numLightSamples * pdf_light;
+                    const float m_i = 1.0f / denom;
+                    target = le * bsdfSample.f * dwdA;
+                    w_b = m_i * Math::Luminance(target);
+                }
+            }
+            if (r.Update(w_b, le, hitInfo.emissiveTriIdx, hitInfo.bary, rng))
+            {
+                r.target = target; r.lightID = emissiveID; r.lightPos = hitInfo.lightPos; r.lightNormal = lightNormal; r.doubleSided = doubleSided;
             }
         }
-        if (r.Update(w_b, le, hitInfo.emissiveTriIdx, hitInfo.bary, rng))
-        {
-            r.target = target; r.lightID = emissiveID; r.lightPos = hitInfo.lightPos; r.lightNormal = lightNormal; r.doubleSided = doubleSided;
-        }
     }
-    for (int s_l = 0; s_l < numLightSamples; s_l++)
+    for (int s_l = 0; s_l < 3; s_l++)
     {
-        Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
-        const zr_emissive_tri& tri = sc.emissives[entry.idx];
-        Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
-        float3 le = Light::Le_EmissiveTriangle(tri);
-        const float pdf_light = entry.pdf * lightSample.pdf;
-        const uint32_t emissiveIdx = entry.idx;
-        const uint32_t lightID = tri.ID;
-        const bool doubleSided = Light::IsDoubleSided(tri);
-        float3 target = f3(0);
-        float3 wi = lightSample.pos - pos;
-        const bool isZero = dot(wi, wi) == 0;
-        const float t = isZero ? 0 : length(wi);
-        wi = isZero ? wi : wi / t;
-        const float dwdA = isZero ? 0 : saturate(dot(lightSample.normal, -wi)) / (t * t);
-        surface.SetWi(wi, normal);
-        if (dot(lightSample.normal, -wi) > 0)
+        const bool go = act && (s_l < numLightSamples);
+        Light::EmissiveTriSample lightSample;
+        float3 le = f3(0), target = f3(0), wi = f3(0);
+        float pdf_light = 0, t = 0, dwdA = 0;
+        uint32_t emissiveIdx = 0, lightID = UINT32_MAX_;
+        bool doubleSided = false, facing = false;
+        ZR_PHASE();
+        if (go)
         {
-            target = le * BSDF::Unified(surface).f * dwdA;
-            if (dot(target, target) > 0)
-                target *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
+            Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+            const zr_emissive_tri& tri = sc.emissives[entry.idx];
+            lightSample = Light::SampleEmissiveTri(pos, tri, rng);
+            le = Light::Le_EmissiveTriangle(tri);
+            pdf_light = entry.pdf * lightSample.pdf;
+            emissiveIdx = entry.idx;
+            lightID = tri.ID;
+            doubleSided = Light::IsDoubleSided(tri);
+            wi = lightSample.pos - pos;
+            const bool isZero = dot(wi, wi) == 0;
+            t = isZero ? 0 : length(wi);
+            wi = isZero ? wi : wi / t;
+            dwdA = isZero ? 0 : saturate(dot(lightSample.normal, -wi)) / (t * t);
+            surface.SetWi(wi, normal);
+            facing = dot(lightSample.normal, -wi) > 0;
+            if (facing)
+                target = le * BSDF::Unified(surface).f * dwdA;
         }
-        const float denom = (float)numLightSamples * pdf_light + (float)numBsdfSamples * BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi) * dwdA;
-        const float m_l = denom > 0 ? 1.0f / denom : 0;
-        const float w_l = m_l * Math::Luminance(target);
-        if (r.Update(w_l, le, emissiveIdx, lightSample.bary, rng))
+        ZR_PHASE();
+        if (go && facing && (dot(target, target) > 0))
+            target *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
+        ZR_PHASE();
+        if (go)
         {
-            r.target = target; r.lightID = lightID; r.lightNormal = lightSample.normal; r.lightPos = lightSample.pos; r.doubleSided = doubleSided;
+            const float denom = (float)numLightSamples * pdf_light + (float)numBsdfSamples * BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi) * dwdA;
+            const float m_l = denom > 0 ? 1.0f / denom : 0;
+            const float w_l = m_l * Math::Luminance(target);
+            if (r.Update(w_l, le, emissiveIdx, lightSample.bary, rng))
+            {
+                r.target = target; r.lightID = lightID; r.lightNormal = lightSample.normal; r.lightPos = lightSample.pos; r.doubleSided = doubleSided;
+            }
         }
     }
     float targetLum = Math::Luminance(r.target);
@@ -254,56 +282,72 @@ ZR_D TemporalCandidate FindTemporalCandidate(const FrameView& f, const SceneDev&
     return c;
 }
 
-ZR_D float OffsetPathTarget_CtT(const SceneDev& sc, const Reservoir& r_curr, TemporalCandidate candidate)
-{
-    float3 wi_offset = r_curr.lightPos - candidate.pos;
-    const bool isZero = dot(wi_offset, wi_offset) == 0;
-    float t_offset = isZero ? 0 : length(wi_offset);
-    wi_offset = isZero ? wi_offset : wi_offset / t_offset;
-    candidate.surface.SetWi(wi_offset, candidate.normal);
-    float3 lightNormal = r_curr.lightNormal;
-    if (r_curr.doubleSided && dot(-wi_offset, lightNormal) < 0)
-        lightNormal = -lightNormal;
-    float cosThetaPrime = saturate(dot(lightNormal, -wi_offset));
-    const float dwdA = isZero ? 0 : cosThetaPrime / (t_offset * t_offset);
-    float3 target_offset = r_curr.le * dwdA;
-    target_offset *= BSDF::Unified(candidate.surface).f;
-    float targetLum_offset = Math::Luminance(target_offset);
-    if (targetLum_offset > 0)
-        targetLum_offset *= Visibility_Segment(sc, candidate.pos, wi_offset, t_offset, candidate.normal, r_curr.lightID,
-            candidate.surface.Transmissive()) ? 1.0f : 0.0f;
-    return targetLum_offset;
-}
-
-ZR_D float3 OffsetPathTarget_TtC(const SceneDev& sc, const Reservoir& r_prev, float3 pos, float3 normal, BSDF::ShadingData surface)
-{
-    EmissiveData prevEmissive = EmissiveData::Init(sc, r_prev.lightIdx, r_prev.bary);
-    prevEmissive.SetSurfacePos(pos);
-    float dwdA = prevEmissive.dWdA();
-    surface.SetWi(prevEmissive.wi, normal);
-    float3 target_offset = r_prev.le * dwdA;
-    target_offset *= BSDF::Unified(surface).f;
-    if (dot(target_offset, target_offset) > 0)
-        target_offset *= Visibility_Segment(sc, pos, prevEmissive.wi, prevEmissive.t, normal, prevEmissive.ID, surface.Transmissive()) ? 1.0f : 0.0f;
-    return target_offset;
-}
-
-ZR_D void TemporalResample1(const SceneDev& sc, float3 pos, float3 normal, const BSDF::ShadingData& surface, const TemporalCandidate& candidate,
+// Resampling.hlsli temporal resample (OffsetPathTarget_CtT / _TtC + TemporalResample1) as phases:
+// BSDF value at the temporal pixel | its shadow segment | BSDF value at the current pixel | its shadow segment
+ZR_D void TemporalResample1_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, const BSDF::ShadingData& surface, TemporalCandidate candidate,
     const zr_rdi_reservoir* prevRes, uint32_t W, Reservoir& r_curr, RNG& rng)
 {
-    Reservoir r_prev = Reservoir::Load(prevRes[(size_t)candidate.py * W + candidate.px]);
+    Reservoir r_prev = Reservoir::Init();
+    if (act)
+        r_prev = Reservoir::Load(prevRes[(size_t)candidate.py * W + candidate.px]);
     const uint32_t newM = r_curr.M + r_prev.M;
-    if (r_curr.w_sum != 0)
+    // ---- current sample in the temporal domain ----
+    const bool doCtT = act && (r_curr.w_sum != 0);
+    float3 wi_offset = f3(0);
+    float t_offset = 0, targetLum_offset = 0;
+    float3 target_offset = f3(0);
+    if (doCtT)
     {
-        float targetLum_prev = OffsetPathTarget_CtT(sc, r_curr, candidate);
+        wi_offset = r_curr.lightPos - candidate.pos;
+        const bool isZero = dot(wi_offset, wi_offset) == 0;
+        t_offset = isZero ? 0 : length(wi_offset);
+        wi_offset = isZero ? wi_offset : wi_offset / t_offset;
+        candidate.surface.SetWi(wi_offset, candidate.normal);
+        float3 lightNormal = r_curr.lightNormal;
+        if (r_curr.doubleSided && dot(-wi_offset, lightNormal) < 0)
+            lightNormal = -lightNormal;
+        float cosThetaPrime = saturate(dot(lightNormal, -wi_offset));
+        const float dwdA = isZero ? 0 : cosThetaPrime / (t_offset * t_offset);
+        target_offset = r_curr.le * dwdA;
+    }
+    ZR_PHASE();
+    if (doCtT)
+    {
+        target_offset *= BSDF::Unified(candidate.surface).f;
+        targetLum_offset = Math::Luminance(target_offset);
+    }
+    ZR_PHASE();
+    if (doCtT)
+    {
+        if (targetLum_offset > 0)
+            targetLum_offset *= Visibility_Segment(sc, candidate.pos, wi_offset, t_offset, candidate.normal, r_curr.lightID,
+                candidate.surface.Transmissive()) ? 1.0f : 0.0f;
         const float numerator = (float)r_curr.M * Math::Luminance(r_curr.target);
-        const float denom = numerator + (float)r_prev.M * targetLum_prev * 1.0f;
+        const float denom = numerator + (float)r_prev.M * targetLum_offset * 1.0f;
         const float m_curr = denom > 0 ? numerator / denom : 0;
         r_curr.w_sum *= m_curr;
     }
-    if (r_prev.lightIdx != UINT32_MAX_)
+    // ---- temporal sample in the current domain ----
+    const bool doTtC = act && (r_prev.lightIdx != UINT32_MAX_);
+    EmissiveData prevEmissive;
+    BSDF::ShadingData surfaceWi = surface;
+    float3 target_curr = f3(0);
+    if (doTtC)
     {
-        const float3 target_curr = OffsetPathTarget_TtC(sc, r_prev, pos, normal, surface);
+        prevEmissive = EmissiveData::Init(sc, r_prev.lightIdx, r_prev.bary);
+        prevEmissive.SetSurfacePos(pos);
+        const float dwdA = prevEmissive.dWdA();
+        surfaceWi.SetWi(prevEmissive.wi, normal);
+        target_curr = r_prev.le * dwdA;
+    }
+    ZR_PHASE();
+    if (doTtC)
+        target_curr *= BSDF::Unified(surfaceWi).f;
+    ZR_PHASE();
+    if (doTtC)
+    {
+        if (dot(target_curr, target_curr) > 0)
+            target_curr *= Visibility_Segment(sc, pos, prevEmissive.wi, prevEmissive.t, normal, prevEmissive.ID, surfaceWi.Transmissive()) ? 1.0f : 0.0f;
         const float targetLum_curr = Math::Luminance(target_curr);
         if (targetLum_curr > 0)
         {
@@ -316,9 +360,12 @@ ZR_D void TemporalResample1(const SceneDev& sc, float3 pos, float3 normal, const
                 r_curr.target = target_curr;
         }
     }
-    float targetLum = Math::Luminance(r_curr.target);
-    r_curr.W = targetLum > 0.0f ? r_curr.w_sum / targetLum : 0.0f;
-    r_curr.M = newM;
+    if (act)
+    {
+        float targetLum = Math::Luminance(r_curr.target);
+        r_curr.W = targetLum > 0.0f ? r_curr.w_sum / targetLum : 0.0f;
+        r_curr.M = newM;
+    }
 }
 
 // ---- PairwiseMIS.hlsli ----
@@ -347,51 +394,68 @@ struct PairwiseMIS
         const float denom = numerator + ((float)r_c.M / (float)k) * p_c_y_c;
         m_c += 1 - (numerator / denom);
     }
-    ZR_D void Stream(const SceneDev& sc, const Reservoir& r_c, float3 pos_c, float3 normal_c, BSDF::ShadingData surface_c, const Reservoir& r_i,
+    // phases: shadow segment c<-i | BSDF value c<-i | shadow segment i<-c | BSDF value i<-c
+    ZR_D void Stream_Sync(bool act, const SceneDev& sc, const Reservoir& r_c, float3 pos_c, float3 normal_c, BSDF::ShadingData surface_c, const Reservoir& r_i,
         float3 pos_i, float3 normal_i, BSDF::ShadingData surface_i, RNG& rng)
     {
         float3 target_c_y_i = f3(0), target_i_y_c = f3(0.0f);
         float m_i = 0;
-        if (r_i.lightIdx != UINT32_MAX_)
+        const bool has_i = act && (r_i.lightIdx != UINT32_MAX_);
+        const float jacobian_i_to_c = 1;      // IsShiftInvertible == true, halfVectorCopyShift == false
+        EmissiveData emissive_i;
+        if (has_i)
         {
-            float jacobian_i_to_c = 1;      // IsShiftInvertible == true, halfVectorCopyShift == false
-            EmissiveData emissive_i = EmissiveData::Init(sc, r_i.lightIdx, r_i.bary);
+            emissive_i = EmissiveData::Init(sc, r_i.lightIdx, r_i.bary);
             emissive_i.SetSurfacePos(pos_c);
             float dwdA = emissive_i.dWdA();
             surface_c.SetWi(emissive_i.wi, normal_c);
             target_c_y_i = r_i.le * dwdA;
-            if (dot(target_c_y_i, target_c_y_i) > 0)
-                target_c_y_i *= Visibility_Segment(sc, pos_c, emissive_i.wi, emissive_i.t, normal_c, emissive_i.ID, surface_c.Transmissive()) ? 1.0f : 0.0f;
+        }
+        ZR_PHASE();
+        if (has_i && (dot(target_c_y_i, target_c_y_i) > 0))
+            target_c_y_i *= Visibility_Segment(sc, pos_c, emissive_i.wi, emissive_i.t, normal_c, emissive_i.ID, surface_c.Transmissive()) ? 1.0f : 0.0f;
+        ZR_PHASE();
+        if (has_i)
+        {
             target_c_y_i *= BSDF::Unified(surface_c).f;
             const float targetLum = Math::Luminance(target_c_y_i);
             m_i = Compute_m_i(r_c, r_i, targetLum, jacobian_i_to_c);
         }
         float jacobian_c_to_i = 0;
-        if (r_c.lightIdx != UINT32_MAX_)
+        const bool has_c = act && (r_c.lightIdx != UINT32_MAX_);
+        float3 wi_i = f3(0);
+        float t_i = 0;
+        if (has_c)
         {
             jacobian_c_to_i = 1;
-            float3 wi_i = r_c.lightPos - pos_i;
+            wi_i = r_c.lightPos - pos_i;
             const bool isZero = dot(wi_i, wi_i) == 0;
-            float t_i = isZero ? 0 : length(wi_i);
+            t_i = isZero ? 0 : length(wi_i);
             wi_i = isZero ? f3(0) : wi_i / t_i;
             surface_i.SetWi(wi_i, normal_i);
             const float3 lightNormal = dot(r_c.lightNormal, -wi_i) < 0 && r_c.doubleSided ? -r_c.lightNormal : r_c.lightNormal;
             const float cosThetaPrime = saturate(dot(lightNormal, -wi_i));
             const float dwdA = isZero ? 0 : cosThetaPrime / (t_i * t_i);
             target_i_y_c = r_c.le * dwdA;
-            if (dot(target_i_y_c, target_i_y_c) > 0)
-                target_i_y_c *= Visibility_Segment(sc, pos_i, wi_i, t_i, normal_i, r_c.lightID, surface_i.Transmissive()) ? 1.0f : 0.0f;
+        }
+        ZR_PHASE();
+        if (has_c && (dot(target_i_y_c, target_i_y_c) > 0))
+            target_i_y_c *= Visibility_Segment(sc, pos_i, wi_i, t_i, normal_i, r_c.lightID, surface_i.Transmissive()) ? 1.0f : 0.0f;
+        ZR_PHASE();
+        if (has_c)
             target_i_y_c *= BSDF::Unified(surface_i).f;
-        }
-        const float targetLum = Math::Luminance(target_i_y_c);
-        Update_m_c(r_c, r_i, targetLum, jacobian_c_to_i);
-        if (r_i.lightIdx != UINT32_MAX_)
+        if (act)
         {
-            const float w_i = m_i * Math::Luminance(target_c_y_i) * r_i.W;
-            if (r_s.Update(w_i, r_i.le, r_i.lightIdx, r_i.bary, rng))
-                r_s.target = target_c_y_i;
+            const float targetLum = Math::Luminance(target_i_y_c);
+            Update_m_c(r_c, r_i, targetLum, jacobian_c_to_i);
+            if (r_i.lightIdx != UINT32_MAX_)
+            {
+                const float w_i = m_i * Math::Luminance(target_c_y_i) * r_i.W;
+                if (r_s.Update(w_i, r_i.le, r_i.lightIdx, r_i.bary, rng))
+                    r_s.target = target_c_y_i;
+            }
+            M_s = to_half(M_s + (float)r_i.M);
         }
-        M_s = to_half(M_s + (float)r_i.M);
     }
     ZR_D void End(const Reservoir& r_c, RNG& rng)
     {
@@ -443,41 +507,66 @@ struct PairwiseMIS
             finalImg[idx] = f4(le.x, le.y, le.z, 0.0f);
     }
 
-    // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting
-    __global__ void ZR_LB(64) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
+#ifndef ZR_RDI_THREADS
+#define ZR_RDI_THREADS 1024
+#endif
+    // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting. A block is ZR_RDI_THREADS/64 consecutive 8x8 groups of the
+    // reference's swizzled dispatch, walking the resampling phases together (no thread leaves before the last barrier).
+    __global__ void ZR_LB(ZR_RDI_THREADS) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
         const zr_rdi_reservoir* __restrict__ resPrev, uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
-        uint2 sg;
-        const uint2 px = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 7, threadIdx.x >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
-        if (px.x >= f.W || px.y >= f.H) return;
+        uint2 sg = make_uint2(0, 0);
+        const uint32_t groupFlat = blockIdx.x * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t tInGroup = threadIdx.x & 63;
+        uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
+        if (groupFlat < dispX * dispY)
+            px = SwizzleThreadGroup(groupFlat, 0, tInGroup & 7, tInGroup >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
+        bool act = !(px.x >= f.W || px.y >= f.H);
         const uint32_t x = px.x, y = px.y;
-        const size_t idx = (size_t)y * f.W + x;
-        const GFlags flags = FlagsAt(f.core, f.W, x, y);
-        if (flags.invalid)
+        const size_t idx = act ? (size_t)y * f.W + x : 0;
+        if (act)
         {
-            // the sky / sun-disk background belongs to the sun-sky path (not in this build)
-            finalImg[idx] = f4(0, 0, 0, 0);
-            return;
+            const GFlags flags = FlagsAt(f.core, f.W, x, y);
+            if (flags.invalid)
+            {
+                // the sky / sun-disk background belongs to the sun-sky path (not in this build)
+                finalImg[idx] = f4(0, 0, 0, 0);
+                act = false;
+            }
+            else if (flags.emissive && !prm.spatial)
+            {
+                WriteEmissive(fc, f, finalImg, idx);
+                act = false;
+            }
         }
-        if (flags.emissive && !prm.spatial)
+        Pixel p;
+        p.surface = BSDF::ShadingData::InitEmpty();
+        p.pos = f3(0); p.normal = f3(0); p.roughness = 0;
+        RNG rng_thread; rng_thread.State = 0;
+        int numBsdfSamples = 0;
+        if (act)
         {
-            WriteEmissive(fc, f, finalImg, idx);
-            return;
+            p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
+            rng_thread = RNG::Init(x, y, fc.FrameNum);
+            numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
         }
-        const Pixel p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
-        RNG rng_thread = RNG::Init(x, y, fc.FrameNum);
-        const int numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
-        Reservoir r = RIS_InitialCandidates(sc, p.pos, p.normal, p.roughness, p.surface, numBsdfSamples, rng_thread);
+        Reservoir r = RIS_InitialCandidates_Sync(act, sc, p.pos, p.normal, p.roughness, p.surface, numBsdfSamples, rng_thread);
         if (prm.temporal)
         {
-            const float2 motionVec = unpack_snorm16x2(__ldg(&f.me[idx].x));
-            const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / f2((float)f.W, (float)f.H);
-            const float2 prevUV = currUV - motionVec;
-            const TemporalCandidate tc = FindTemporalCandidate(f, sc, p.pos, p.normal, p.roughness, p.surface, prevUV);
-            if (tc.valid)
-                TemporalResample1(sc, p.pos, p.normal, p.surface, tc, resPrev, f.W, r, rng_thread);
-            if (prm.spatial)
+            float2 motionVec = f2(0, 0);
+            TemporalCandidate tc; tc.valid = false; tc.px = tc.py = 0; tc.pos = tc.normal = f3(0);
+            tc.surface = BSDF::ShadingData::InitEmpty();
+            ZR_PHASE();
+            if (act)
+            {
+                motionVec = unpack_snorm16x2(__ldg(&f.me[idx].x));
+                const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / f2((float)f.W, (float)f.H);
+                const float2 prevUV = currUV - motionVec;
+                tc = FindTemporalCandidate(f, sc, p.pos, p.normal, p.roughness, p.surface, prevUV);
+            }
+            TemporalResample1_Sync(act && tc.valid, sc, p.pos, p.normal, p.surface, tc, resPrev, f.W, r, rng_thread);
+            if (act && prm.spatial)
             {
                 const bool disoccluded = !tc.valid && (dot(motionVec, motionVec) > 0);
                 r.target = disoccluded ? -r.target : r.target;
@@ -485,6 +574,8 @@ struct PairwiseMIS
                 r.target = Math::Sanitize(r.target);
             }
         }
+        if (!act)
+            return;
         if (prm.temporal || prm.reset)
         {
             zr_rdi_reservoir rec;
@@ -496,15 +587,19 @@ struct PairwiseMIS
     }
 
     // ReSTIR_DI_Spatial.hlsl main + SpatialResample
-    __global__ void ZR_LB(64) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
+    __global__ void ZR_LB(ZR_RDI_THREADS) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
         const uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
-        uint2 sg;
-        const uint2 px = SwizzleThreadGroup(blockIdx.x, blockIdx.y, threadIdx.x & 7, threadIdx.x >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
+        uint2 sg = make_uint2(0, 0);
+        const uint32_t groupFlat = blockIdx.x * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t tInGroup = threadIdx.x & 63;
+        uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
+        if (groupFlat < dispX * dispY)
+            px = SwizzleThreadGroup(groupFlat, 0, tInGroup & 7, tInGroup >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
         bool active = px.x < f.W && px.y < f.H;
         const int x = (int)px.x, y = (int)px.y;
-        const size_t idx = (size_t)y * f.W + x;
+        const size_t idx = active ? (size_t)y * f.W + x : 0;
         if (active)
         {
             const GFlags flags = FlagsAt(f.core, f.W, x, y);
@@ -516,6 +611,8 @@ struct PairwiseMIS
             }
         }
         Pixel p;
+        p.surface = BSDF::ShadingData::InitEmpty();
+        p.pos = f3(0); p.normal = f3(0); p.roughness = 0; p.z = 0;
         Reservoir r = Reservoir::Init();
         bool disoccluded = false;
         if (active)
@@ -541,8 +638,7 @@ struct PairwiseMIS
             }
         }
         const uint32_t waveDisoccluded = __popc(__ballot_sync(0xffffffffu, active && disoccluded));
-        if (!active) return;
-        RNG rng_group = RNG::Init(blockIdx.x, blockIdx.y, fc.FrameNum);
+        RNG rng_group = RNG::Init(groupFlat % dispX, groupFlat / dispX, fc.FrameNum);
         rng_group.Uniform();    // sample-set index (unused without presampled sets)
         const bool extra = !prm.stochasticSpatial || (rng_group.Uniform() < 0.6f);
         if (prm.extraDisocclusion)
@@ -557,8 +653,10 @@ struct PairwiseMIS
         zr_sincosf(theta, &sinTheta, &cosTheta);
         PairwiseMIS pairwiseMIS = PairwiseMIS::Init((uint32_t)numSamples, r);
         float3 samplePos[4]; int spx[4], spy[4]; uint32_t k = 0;
-        for (int i = 0; i < numSamples; i++)
+        ZR_PHASE();
+        for (int i = 0; i < 4; i++)
         {
+            if (!(active && i < numSamples)) continue;
             const float2 sampleUV = f2(c_disk32[((offset + i) & 31) * 2], c_disk32[((offset + i) & 31) * 2 + 1]);
             float2 rotated;
             rotated.x = dot(sampleUV, f2(cosTheta, -sinTheta));
@@ -578,22 +676,36 @@ struct PairwiseMIS
             k++;
         }
         pairwiseMIS.k = k;
-        for (uint32_t i = 0; i < k; i++)
+        for (uint32_t i = 0; i < 4; i++)
         {
-            const Pixel pi = LoadPixel(f, sc, f.core, f.coat, spx[i], spy[i], false, spx[i], spy[i]);
-            // the neighbour surface is rebuilt with transmission depth = 0 (Resampling.hlsli:507-510)
-            const uint4 c = ld128(&f.core[(size_t)spy[i] * f.W + spx[i]]);
-            const float3 bc = f3((float)(c.z & 0xff) / 255.0f, (float)((c.z >> 8) & 0xff) / 255.0f, (float)((c.z >> 16) & 0xff) / 255.0f);
-            const float bw = pi.flags.subsurface ? (float)(c.z >> 24) / 255.0f : 0.0f;
-            const float3 wo_i = normalize(pi.origin - samplePos[i]);
-            const BSDF::ShadingData surface_i = BSDF::ShadingData::Init(pi.normal, wo_i, pi.flags.metallic, pi.roughness, bc, BSDF::ETA_AIR,
-                pi.eta_next, pi.flags.transmissive, 0.0f, to_half(bw), pi.surface.coat_weight, pi.surface.coat_color,
-                pi.coatRoughness, pi.coatIor, sc.rho);
-            zr_rdi_reservoir recN;
-            LoadRdi(&resCurr[(size_t)spy[i] * f.W + spx[i]], recN);
-            const Reservoir r_spatial = Reservoir::Load(recN);
-            pairwiseMIS.Stream(sc, r, p.pos, p.normal, p.surface, r_spatial, samplePos[i], pi.normal, surface_i, rng);
+            const bool go = active && (i < k);
+            if (!__syncthreads_or(go))
+                break;
+            Pixel pi;
+            pi.normal = f3(0);
+            BSDF::ShadingData surface_i = BSDF::ShadingData::InitEmpty();
+            Reservoir r_spatial = Reservoir::Init();
+            float3 pos_i = f3(0);
+            if (go)
+            {
+                pi = LoadPixel(f, sc, f.core, f.coat, spx[i], spy[i], false, spx[i], spy[i]);
+                // the neighbour surface is rebuilt with transmission depth = 0 (Resampling.hlsli:507-510)
+                const uint4 c = ld128(&f.core[(size_t)spy[i] * f.W + spx[i]]);
+                const float3 bc = f3((float)(c.z & 0xff) / 255.0f, (float)((c.z >> 8) & 0xff) / 255.0f, (float)((c.z >> 16) & 0xff) / 255.0f);
+                const float bw = pi.flags.subsurface ? (float)(c.z >> 24) / 255.0f : 0.0f;
+                pos_i = samplePos[i];
+                const float3 wo_i = normalize(pi.origin - pos_i);
+                surface_i = BSDF::ShadingData::Init(pi.normal, wo_i, pi.flags.metallic, pi.roughness, bc, BSDF::ETA_AIR,
+                    pi.eta_next, pi.flags.transmissive, 0.0f, to_half(bw), pi.surface.coat_weight, pi.surface.coat_color,
+                    pi.coatRoughness, pi.coatIor, sc.rho);
+                zr_rdi_reservoir recN;
+                LoadRdi(&resCurr[(size_t)spy[i] * f.W + spx[i]], recN);
+                r_spatial = Reservoir::Load(recN);
+            }
+            pairwiseMIS.Stream_Sync(go, sc, r, p.pos, p.normal, p.surface, r_spatial, pos_i, pi.normal, surface_i, rng);
         }
+        if (!active)
+            return;
         pairwiseMIS.End(r, rng);
         const Reservoir rs = pairwiseMIS.r_s;
         WriteFinal(fc, finalImg, idx, rs.target * rs.W);
@@ -716,12 +828,12 @@ struct zr_direct_pass
         const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
         const int cur = currTemporalIdx;
         ZR_PROF("k_di_temporal", stream);
-        k_di_temporal<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
+        k_di_temporal<<<(dispX * dispY + ZR_RDI_THREADS / 64 - 1) / (ZR_RDI_THREADS / 64), ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
         ZR_LAUNCH_CHECK();
         if (doSpatial)
         {
             ZR_PROF("k_di_spatial", stream);
-            k_di_spatial<<<dim3(dispX, dispY), 64, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
+            k_di_spatial<<<(dispX * dispY + ZR_RDI_THREADS / 64 - 1) / (ZR_RDI_THREADS / 64), ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
             ZR_LAUNCH_CHECK();
         }
         isTemporalReservoirValid = true;
