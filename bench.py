@@ -114,7 +114,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": mp, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": len(per),
         "warmup": args.warmup, "ms_per_step": 1000.0 * sum(p[1] for p in per) / len(per), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "CPU port of the reference's shader math (the reference ships no CPU renderer)"},
         "cpu_baseline": {"value": mp, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": mp, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -151,19 +151,28 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # an explicit stream (not the legacy default one): the halo exchanges interleave torch / NCCL work with the passes'
+    # kernels on the same stream handle
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     st = C.c_void_p(stream.cuda_stream)
 
-    # Multi-GPU: pixels are independent except for neighbour reads. This round runs weak scaling with one
-    # full 1080p frame per GPU and no data-path collective ("replicas", DESIGN.md multi-GPU); value = all frames / time.
+    # Multi-GPU: ONE 1080p frame is split into horizontal strips, one per GPU (strong scaling). Strip
+    # boundaries come from the per-band SM-cycle cost measured during the unsharded warm-up frames; reservoir / final
+    # halos move with one NCCL all-gather per exchange point (zetaray_b200/sharding.py); the finished strips are
+    # all-gathered every frame so the image is complete on every rank before the next frame starts.
+    from zetaray_b200.sharding import ShardedFrame, StripPlan
     flat = scene_util.cornell()
     scene = Scene(flat)
     scene.prelighting(st)
     gb = GBuffers(W, H)
-    gpass, di, ind, comp, taa = GBufferRT(), DirectLighting(W, H), IndirectLighting(W, H), Compositing(W, H), TAA(W, H)
+    passes = dict(gbuffer=GBufferRT(), direct=DirectLighting(W, H), indirect=IndirectLighting(W, H),
+                  compositing=Compositing(W, H), taa=TAA(W, H))
+    taa = passes["taa"]
     seq = rpt_util.FrameSequence(W, H)
     fi = _lib.FrameInputs()
     fi.scene = scene.handle
+    sharded = ShardedFrame(passes, gb, W, H, rank, world)
 
     # DirectLighting and IndirectLighting both depend only on the G-buffer (two independent render-graph nodes in the
     # reference, PathTracer.cpp:149-323), so DirectLighting is recorded on a second stream and joined before Compositing.
@@ -172,20 +181,8 @@ def main():
     ev_g, ev_d = torch.cuda.Event(), torch.cuda.Event()
 
     def frame(fc):
-        gb.flip()
-        fi.frame = fc
-        gb.fill_inputs(fi)
-        gpass.Render(fi, st)
-        if side is not None:
-            ev_g.record(stream)
-            side.wait_event(ev_g)
-        di.Render(fi, st_side)
-        ind.Render(fi, st)
-        if side is not None:
-            ev_d.record(side)
-            stream.wait_event(ev_d)
-        comp.Render(fi, di.GetOutput(0).d_ptr, ind.GetOutput(0).d_ptr, st)
-        taa.Render(fi, comp.GetOutput().d_ptr, st)
+        sharded.render(fi, fc, stream, st, side, st_side, ev_g, ev_d)
+        sharded.gather_output(stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,9 +190,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also brings temporal + spatial reuse to steady state: frame >= 3) ----
+    # ---- warm-up: unsharded frames bring temporal + spatial reuse to steady state (frame >= 3) and measure the cost
+    # of every 32-row band; then the strips are cut and the same number of sharded warm-up frames follows ----
+    plan_info = None
+    if world > 1:
+        sharded.begin_cost_measurement()
     for _ in range(args.warmup):
         frame(seq.next())
+    if world > 1:
+        costs = sharded.end_cost_measurement()
+        plan = StripPlan.balanced(H, world, costs)
+        sharded.shard(plan)
+        sc = plan.strip_costs(costs)
+        plan_info = {"bounds": plan.bounds, "strip_cost_max_over_mean": round(max(sc) / (sum(sc) / world), 3)}
+        for _ in range(args.warmup):
+            frame(seq.next())
     # per-frame working set: G-buffers 2 x 36 B/px, PT reservoirs 2 x 64, DI 2 x 32, targets/finals ~ 90 B/px => ~0.8 GB
     # at 1080p, larger than the 126 MB L2, so no explicit flush between frames is needed.
 
@@ -219,9 +228,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = world * W * H * args.steps / (ms_total * 1e-3) / 1e6
+    value = W * H * args.steps / (ms_total * 1e-3) / 1e6
 
-    # ---- e2e: host buffers in, host image out, every frame ----
+    # ---- e2e: host buffers in, host image out, every frame (rank 0 holds the host side) ----
     n_e2e = max(3, min(args.steps, 20))
     fc_host = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8).pin_memory()
     fc_dev = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8, device="cuda")
@@ -234,23 +243,25 @@ def main():
         C.memmove(fc_host.data_ptr(), C.addressof(fc), C.sizeof(fc))
         fc_dev.copy_(fc_host, non_blocking=True)            # H2D of the per-frame inputs
         frame(fc)
-        img = taa.GetOutput()
-        check(lib.zr_memcpy_d2h(C.c_void_p(out_host.data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st))
+        if rank == 0:
+            img = taa.GetOutput()
+            check(lib.zr_memcpy_d2h(C.c_void_p(out_host.data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st))
         stream.synchronize()                                 # the caller consumes the image before the next frame
     e3.record(stream)
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * W * H * n_e2e / (float(t2.item()) * 1e-3) / 1e6
+    e2e_value = W * H * n_e2e / (float(t2.item()) * 1e-3) / 1e6
+    halo_bytes = 0 if sharded.halo is None or not sharded.halo.calls else sharded.halo.bytes_sent // max(1, sharded.halo.calls)
 
     # ---- per-kernel timing (CUDA events on the launching stream around every launch) ----
     kern = {}
-    if rank == 0:
-        check(lib.zr_profile_enable(1))
-        nprof = 5
-        for _ in range(nprof):
-            frame(seq.next())
+    nprof = 5
+    check(lib.zr_profile_enable(1))
+    for _ in range(nprof):          # every rank renders (the frame holds collectives) and times its own launches
+        frame(seq.next())
+    if True:
         buf = C.create_string_buffer(8192)
         check(lib.zr_profile_collect(buf, 8192))
         check(lib.zr_profile_enable(0))
@@ -258,6 +269,12 @@ def main():
             if item:
                 name, calls, total = item.split(":")
                 kern[name] = float(total) / nprof      # ms per frame (all launches of that kernel)
+    rank_kernel_ms = None
+    if world > 1:
+        mine = torch.tensor([sum(kern.values())], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        rank_kernel_ms = [round(float(v.item()), 3) for v in allv]
     roofline, kernels = None, []
     if rank == 0 and kern:
         peaks = {}
@@ -268,9 +285,10 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         tot = sum(kern.values())
+        own_rows = H if sharded.plan is None else (sharded.plan.rows(rank)[1] - sharded.plan.rows(rank)[0])    # rank 0's strip
         for name, msf in sorted(kern.items(), key=lambda kv: -kv[1]):
             ab = ALG_BYTES.get(name)
-            gbs = (ab * W * H / (msf * 1e-3) / 1e9) if ab else None
+            gbs = (ab * W * own_rows / (msf * 1e-3) / 1e9) if ab else None
             kernels.append({"kernel": name, "ms_per_frame": round(msf, 4), "share": round(msf / tot, 4),
                             "alg_bytes_per_px": ab, "achieved_gbs": None if gbs is None else round(gbs, 1),
                             "frac": None if gbs is None else round(gbs / peak, 4)})
@@ -291,10 +309,11 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [W, H], "spp": 1, "bounces": 3, "restir_pt": "temporal + 1 spatial pass",
-                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "replicas x%d" % world, "streams": 1 if side is None else 2,
+                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halo all-gather)" % world if world > 1 else "single GPU",
+                       "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2,
                        "l2": "per-frame working set ~0.8 GB >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_value, 3), "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(_lib.FrameConstants),
                     "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},

@@ -268,6 +268,17 @@ typedef struct zr_image2d
     uint32_t texel_bytes;
 } zr_image2d;
 
+/* ---- Strip-sharded frames (multi-GPU; no reference counterpart) ---------------------------------
+ * A frame is split into horizontal strips whose boundaries are multiples of 32 rows (the sort tile of
+ * ReSTIR_PT_Sort.hlsl:10 and a multiple of every thread-group height), one strip per device. Every pass has
+ * set_rows(y0, y1): it then computes and writes rows [y0, y1) only, while reading up to 32 rows beyond them
+ * (spatial neighbours <= 15 px for ReSTIR PT, Util.hlsli:9; <= 23 px for ReSTIR DI, Resampling.hlsli:418-423;
+ * 1-2 px for the stencils). The lighting passes call the halo-exchange hook at the points where rows they just
+ * wrote are about to be read by other strips (after temporal resampling and after every spatial pass); the hook
+ * must make the 32 rows either side of [y0, y1) of each plane coherent across devices on `stream` (this
+ * repository: one NCCL all-gather per call, zetaray_b200/sharding.py). */
+typedef void (*zr_halo_exchange_fn)(void* user, const zr_image2d* planes, int n_planes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Scene: flat buffers named in ZetaCore/Scene/SceneRenderer.h:15-33 + the acceleration structure
  * that replaces the DXR TLAS (ZetaCore/RayTracing/RtAccelerationStructure.cpp).
@@ -347,6 +358,7 @@ typedef struct zr_resource_use { uint32_t id; uint32_t write; } zr_resource_use;
 typedef struct zr_gbuffer_pass zr_gbuffer_pass;
 ZR_API zr_status zr_gbuffer_pass_create(zr_gbuffer_pass** out);
 ZR_API zr_status zr_gbuffer_pass_render(zr_gbuffer_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_gbuffer_pass_set_rows(zr_gbuffer_pass* p, uint32_t y0, uint32_t y1);
 ZR_API zr_status zr_gbuffer_pass_describe_io(zr_gbuffer_pass* p, zr_resource_use* uses, int* n);
 ZR_API void zr_gbuffer_pass_destroy(zr_gbuffer_pass* p);
 
@@ -368,6 +380,10 @@ ZR_API zr_status zr_direct_pass_reset_temporal(zr_direct_pass* p);
 ZR_API zr_status zr_direct_pass_default_params(zr_direct_params* out);
 ZR_API zr_status zr_direct_pass_set_params(zr_direct_pass* p, const zr_direct_params* params);
 ZR_API zr_status zr_direct_pass_render(zr_direct_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_direct_pass_set_rows(zr_direct_pass* p, uint32_t y0, uint32_t y1);
+ZR_API zr_status zr_direct_pass_set_halo_exchange(zr_direct_pass* p, zr_halo_exchange_fn fn, void* user);
+/* optional: d_cycles[ceil(H/32)] (uint64, device) accumulates the SM cycles each 32-row band costs; used to balance strips */
+ZR_API zr_status zr_direct_pass_set_cost_map(zr_direct_pass* p, void* d_cycles);
 ZR_API zr_status zr_direct_pass_get_output(zr_direct_pass* p, zr_direct_output id, zr_image2d* out);
 ZR_API zr_status zr_direct_pass_describe_io(zr_direct_pass* p, zr_resource_use* uses, int* n);
 ZR_API void zr_direct_pass_destroy(zr_direct_pass* p);
@@ -410,6 +426,8 @@ ZR_API zr_status zr_indirect_pass_get_output(zr_indirect_pass* p, zr_indirect_ou
 ZR_API zr_status zr_indirect_pass_describe_io(zr_indirect_pass* p, zr_resource_use* uses, int* n);
 /* multi-GPU: rows [y0, y1) this rank owns; halo rows are read from the (all-gathered) planes */
 ZR_API zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1);
+ZR_API zr_status zr_indirect_pass_set_halo_exchange(zr_indirect_pass* p, zr_halo_exchange_fn fn, void* user);
+ZR_API zr_status zr_indirect_pass_set_cost_map(zr_indirect_pass* p, void* d_cycles);
 ZR_API void zr_indirect_pass_destroy(zr_indirect_pass* p);
 
 /* ---- Compositing + FireflyFilter (Compositing/Compositing.cpp:83-145) ---- */
@@ -425,6 +443,7 @@ ZR_API zr_status zr_compositing_pass_render(zr_compositing_pass* p, const zr_fra
  * render() fuses both -- kept so tests can check the fusion changes nothing */
 ZR_API zr_status zr_compositing_pass_render_unfused(zr_compositing_pass* p, const zr_frame_inputs* in,
     const void* d_direct, const void* d_indirect, void* stream);
+ZR_API zr_status zr_compositing_pass_set_rows(zr_compositing_pass* p, uint32_t y0, uint32_t y1);
 ZR_API zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out);
 ZR_API void zr_compositing_pass_destroy(zr_compositing_pass* p);
 
@@ -432,6 +451,7 @@ ZR_API void zr_compositing_pass_destroy(zr_compositing_pass* p);
 typedef struct zr_taa_pass zr_taa_pass;
 ZR_API zr_status zr_taa_pass_create(uint32_t width, uint32_t height, zr_taa_pass** out);
 ZR_API zr_status zr_taa_pass_resize(zr_taa_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_taa_pass_set_rows(zr_taa_pass* p, uint32_t y0, uint32_t y1);
 ZR_API zr_status zr_taa_pass_set_blend_weight(zr_taa_pass* p, float w);  /* default 0.1, TAA.h:72 */
 /* d_signal: float4[w*h]; output RGBA16F (half4, 8 B/px) */
 ZR_API zr_status zr_taa_pass_render(zr_taa_pass* p, const zr_frame_inputs* in, const void* d_signal, void* stream);

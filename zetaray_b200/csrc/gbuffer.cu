@@ -17,13 +17,14 @@ namespace
     ZR_D float EncodeIOR(float ior) { return (ior - 1.0f) / (2.5f - 1.0f); }
 
     __global__ void __launch_bounds__(64) k_gbuffer(SceneDev sc, zr_frame_constants fc, uint4* __restrict__ core,
-        float* __restrict__ depthPlane, uint2* __restrict__ me, uint2* __restrict__ coat, uint2* __restrict__ tridiff)
+        float* __restrict__ depthPlane, uint2* __restrict__ me, uint2* __restrict__ coat, uint2* __restrict__ tridiff,
+        uint32_t rowBegin, uint32_t rowEnd)
     {
-        // 8x8 groups like GBUFFER_RT_GROUP_DIM (GBufferRT_Common.h:6-7)
+        // 8x8 groups like GBUFFER_RT_GROUP_DIM (GBufferRT_Common.h:6-7); rows [rowBegin, rowEnd) of the frame
         const uint32_t x = blockIdx.x * 8 + (threadIdx.x & 7);
-        const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 3);
+        const uint32_t y = rowBegin + blockIdx.y * 8 + (threadIdx.x >> 3);
         const uint32_t W = fc.RenderWidth, H = fc.RenderHeight;
-        if (x >= W || y >= H) return;
+        if (x >= W || y >= H || y >= rowEnd) return;
         const size_t idx = (size_t)y * W + x;
 
         float2 lensSample = f2(0, 0);
@@ -199,6 +200,7 @@ struct zr_gbuffer_pass
 {
     // GBufferRT (GBuffer/GBufferRT.h): no resources of its own -- the renderer owns the G-buffers
     // (ZetaRenderer/Default/DefaultRendererImpl.h:111-121)
+    uint32_t rowBegin = 0, rowEnd = 0xffffffffu;    // rows this device renders (strip-sharded frames); all by default
     zr_status Render(const zr_frame_inputs* in, cudaStream_t stream)
     {
         using namespace zr;
@@ -209,10 +211,12 @@ struct zr_gbuffer_pass
         }
         const uint32_t W = in->frame.RenderWidth, H = in->frame.RenderHeight;
         if (!W || !H) { set_error("zr_gbuffer_pass_render: zero render size"); return ZR_ERR_INVALID_ARG; }
-        dim3 grid((W + 7) / 8, (H + 7) / 8);
+        const uint32_t y1 = rowEnd < H ? rowEnd : H;
+        if (rowBegin >= y1) { set_error("zr_gbuffer_pass_render: empty row range"); return ZR_ERR_INVALID_ARG; }
+        dim3 grid((W + 7) / 8, (y1 - rowBegin + 7) / 8);
         ZR_PROF("k_gbuffer", stream);
         k_gbuffer<<<grid, 64, 0, stream>>>(in->scene->dev, in->frame, (uint4*)in->curr.d_core, (float*)in->curr.d_depth,
-            (uint2*)in->curr.d_motion_emissive, (uint2*)in->curr.d_coat, (uint2*)in->curr.d_tridiff);
+            (uint2*)in->curr.d_motion_emissive, (uint2*)in->curr.d_coat, (uint2*)in->curr.d_tridiff, rowBegin, y1);
         ZR_LAUNCH_CHECK();
         return ZR_OK;
     }
@@ -247,6 +251,12 @@ extern "C"
     {
         if (!out) return ZR_ERR_INVALID_ARG;
         *out = new zr_gbuffer_pass();
+        return ZR_OK;
+    }
+    zr_status zr_gbuffer_pass_set_rows(zr_gbuffer_pass* p, uint32_t y0, uint32_t y1)
+    {
+        if (!p || y0 >= y1) { zr::set_error("zr_gbuffer_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        p->rowBegin = y0; p->rowEnd = y1;
         return ZR_OK;
     }
     zr_status zr_gbuffer_pass_render(zr_gbuffer_pass* p, const zr_frame_inputs* in, void* stream)

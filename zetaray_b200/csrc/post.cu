@@ -22,6 +22,7 @@ namespace
         uint32_t numFramesAccumulated;
         float blendWeight;
         uint32_t temporalIsValid;
+        uint32_t rowBegin, rowEnd;      // rows this device owns (strip-sharded frames); the whole image by default
     };
 
     ZR_D float3 composite_px(const uint4* __restrict__ core, const float4* __restrict__ direct,
@@ -48,8 +49,8 @@ namespace
         const float4* __restrict__ direct, const float4* __restrict__ indirect, float4* __restrict__ out, PostParams p)
     {
         const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
-        const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
-        if (x >= p.W || y >= p.H) return;
+        const uint32_t y = p.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
+        if (x >= p.W || y >= p.rowEnd) return;
         const size_t i = (size_t)y * p.W + x;
         float3 c = composite_px(core, direct, indirect, i, p);
         out[i] = f4(c.x, c.y, c.z, 0.0f);
@@ -63,9 +64,9 @@ namespace
         PostParams p)
     {
         const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-        const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+        const int y = (int)p.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
         const int W = (int)p.W, H = (int)p.H;
-        if (x >= W || y >= H) return;
+        if (x >= W || y >= (int)p.rowEnd) return;
         const size_t idx = (size_t)y * W + x;
         auto load = [&](size_t i) -> float3 {
             if (Fused)
@@ -188,9 +189,9 @@ namespace
         const uint2* __restrict__ prevOut, uint2* __restrict__ out, PostParams p)
     {
         const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-        const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+        const int y = (int)p.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
         const int W = (int)p.W, H = (int)p.H;
-        if (x >= W || y >= H) return;
+        if (x >= W || y >= (int)p.rowEnd) return;
         const size_t idx = (size_t)y * W + x;
         const float depth = __ldg(&depthPlane[idx]);
         const float4 s4 = __ldg(&signal[idx]);
@@ -262,6 +263,7 @@ namespace
         p.numFramesAccumulated = p.accumulate ? fc.NumFramesCameraStatic : 1u;
         p.blendWeight = 0.1f;
         p.temporalIsValid = 0;
+        p.rowBegin = 0; p.rowEnd = p.H;
         return p;
     }
 }
@@ -277,6 +279,12 @@ struct zr_compositing_pass
     float4* d_composited = nullptr;     // output of compositing (and of the fused firefly variant)
     float4* d_scratch = nullptr;        // unfused path: compositing result before the filter
     zr_compositing_params params{ 1, 1, 1 };
+    uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
+    void SetRows(zr::PostParams& p, dim3& grid) const
+    {
+        p.rowBegin = rowBegin; p.rowEnd = rowEnd < height ? rowEnd : height;
+        grid = dim3((width + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8);
+    }
 
     zr_status Init(uint32_t w, uint32_t h) { return OnWindowResized(w, h); }
     zr_status OnWindowResized(uint32_t w, uint32_t h)
@@ -310,7 +318,8 @@ struct zr_compositing_pass
         PostParams p = make_params(in->frame);
         const float4* direct = params.emissive_di ? (const float4*)d_direct : nullptr;
         const float4* indirect = params.indirect ? (const float4*)d_indirect : nullptr;
-        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        dim3 grid;
+        SetRows(p, grid);
         if (params.firefly_filter)
         {
             ZR_PROF("k_firefly", stream);
@@ -331,7 +340,8 @@ struct zr_compositing_pass
     {
         using namespace zr;
         PostParams p = make_params(in->frame);
-        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        dim3 grid;
+        SetRows(p, grid);
         ZR_PROF("k_compositing", stream);
         k_compositing<<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float4*)d_direct,
             (const float4*)d_indirect, d_scratch, p);
@@ -352,6 +362,7 @@ struct zr_taa_pass
     int outIdx = 0;
     bool isTemporalTexValid = false;
     float blendWeight = 0.1f;       // DefaultParamVals::BlendWeight
+    uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
 
     zr_status OnWindowResized(uint32_t w, uint32_t h)
     {
@@ -385,7 +396,8 @@ struct zr_taa_pass
         PostParams p = make_params(in->frame);
         p.blendWeight = blendWeight;
         p.temporalIsValid = isTemporalTexValid ? 1u : 0u;
-        dim3 grid((width + 31) / 32, (height + 7) / 8);
+        p.rowBegin = rowBegin; p.rowEnd = rowEnd < height ? rowEnd : height;
+        dim3 grid((width + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8);
         outIdx ^= 1;
         ZR_PROF("k_taa", stream);
         k_taa<<<grid, 256, 0, stream>>>((const float*)in->curr.d_depth, (const uint2*)in->curr.d_motion_emissive,
@@ -430,6 +442,12 @@ extern "C"
         if (!p) return ZR_ERR_INVALID_ARG;
         return p->RenderUnfused(in, d_direct, d_indirect, (cudaStream_t)stream);
     }
+    zr_status zr_compositing_pass_set_rows(zr_compositing_pass* p, uint32_t y0, uint32_t y1)
+    {
+        if (!p || y0 >= y1 || y0 >= p->height) { zr::set_error("zr_compositing_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        p->rowBegin = y0; p->rowEnd = y1;
+        return ZR_OK;
+    }
     zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out)
     {
         if (!p || !out) return ZR_ERR_INVALID_ARG;
@@ -451,6 +469,12 @@ extern "C"
     {
         if (!p) return ZR_ERR_INVALID_ARG;
         return p->OnWindowResized(width, height);
+    }
+    zr_status zr_taa_pass_set_rows(zr_taa_pass* p, uint32_t y0, uint32_t y1)
+    {
+        if (!p || y0 >= y1 || y0 >= p->height) { zr::set_error("zr_taa_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        p->rowBegin = y0; p->rowEnd = y1;
+        return ZR_OK;
     }
     zr_status zr_taa_pass_set_blend_weight(zr_taa_pass* p, float w)
     {

@@ -14,7 +14,12 @@ namespace zr
 {
 namespace
 {
-    struct DIParams { uint32_t temporal, spatial, stochasticSpatial, extraDisocclusion, M_max; float alpha_min; uint32_t reset; };
+    struct DIParams
+    {
+        uint32_t temporal, spatial, stochasticSpatial, extraDisocclusion, M_max; float alpha_min; uint32_t reset;
+        uint32_t rowBegin, rowEnd;              // rows this device owns (strip-sharded frames)
+        unsigned long long* costMap;            // optional: SM cycles spent per 32-row band
+    };
 
     __constant__ float c_disk32[64];
 
@@ -522,7 +527,8 @@ struct PairwiseMIS
         uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
             px = SwizzleThreadGroup(groupFlat, 0, tInGroup & 7, tInGroup >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
-        bool act = !(px.x >= f.W || px.y >= f.H);
+        const long long t0 = clock64();
+        bool act = !(px.x >= f.W || px.y >= f.H || px.y < prm.rowBegin || px.y >= prm.rowEnd);
         const uint32_t x = px.x, y = px.y;
         const size_t idx = act ? (size_t)y * f.W + x : 0;
         if (act)
@@ -574,6 +580,8 @@ struct PairwiseMIS
                 r.target = Math::Sanitize(r.target);
             }
         }
+        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
+            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
         if (!act)
             return;
         if (prm.temporal || prm.reset)
@@ -597,7 +605,8 @@ struct PairwiseMIS
         uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
             px = SwizzleThreadGroup(groupFlat, 0, tInGroup & 7, tInGroup >> 3, 8, 8, dispX, 16, 4, 16 * dispY, sg);
-        bool active = px.x < f.W && px.y < f.H;
+        const long long t0 = clock64();
+        bool active = px.x < f.W && px.y < f.H && px.y >= prm.rowBegin && px.y < prm.rowEnd;
         const int x = (int)px.x, y = (int)px.y;
         const size_t idx = active ? (size_t)y * f.W + x : 0;
         if (active)
@@ -704,6 +713,8 @@ struct PairwiseMIS
             }
             pairwiseMIS.Stream_Sync(go, sc, r, p.pos, p.normal, p.surface, r_spatial, pos_i, pi.normal, surface_i, rng);
         }
+        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
+            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
         if (!active)
             return;
         pairwiseMIS.End(r, rng);
@@ -732,6 +743,11 @@ struct zr_direct_pass
     bool resetTemporalTextures = true;
     bool patternLoaded = false;
     zr_direct_params params{};
+    // strip-sharded frames: owned rows, halo-exchange hook, optional cost map
+    uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
+    zr_halo_exchange_fn exchange = nullptr;
+    void* exchangeUser = nullptr;
+    unsigned long long* d_costMap = nullptr;
 
     static void Defaults(zr_direct_params* p)
     {
@@ -824,12 +840,18 @@ struct zr_direct_pass
         f.pcore = (const uint4*)in->prev.d_core; f.pcoat = (const uint2*)in->prev.d_coat;
         f.W = width; f.H = height;
         DIParams prm{ doTemporal, doSpatial, params.stochastic_spatial, params.extra_disocclusion_sampling, params.M_max,
-            params.alpha_min, resetTemporalTextures };
+            params.alpha_min, resetTemporalTextures, rowBegin, rowEnd < height ? rowEnd : height, d_costMap };
         const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
         const int cur = currTemporalIdx;
         ZR_PROF("k_di_temporal", stream);
         k_di_temporal<<<(dispX * dispY + ZR_RDI_THREADS / 64 - 1) / (ZR_RDI_THREADS / 64), ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
         ZR_LAUNCH_CHECK();
+        // the temporal output is what neighbours read in the spatial pass and what the next frame reprojects into
+        if (exchange)
+        {
+            const zr_image2d plane{ d_res[cur], width, height, width * 32u, 32u };
+            exchange(exchangeUser, &plane, 1, stream);
+        }
         if (doSpatial)
         {
             ZR_PROF("k_di_spatial", stream);
@@ -878,6 +900,24 @@ extern "C"
     {
         if (!p) return ZR_ERR_INVALID_ARG;
         return p->Render(in, (cudaStream_t)stream);
+    }
+    zr_status zr_direct_pass_set_rows(zr_direct_pass* p, uint32_t y0, uint32_t y1)
+    {
+        if (!p || y0 >= y1 || y0 >= p->height) { zr::set_error("zr_direct_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        p->rowBegin = y0; p->rowEnd = y1;
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_set_halo_exchange(zr_direct_pass* p, zr_halo_exchange_fn fn, void* user)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->exchange = fn; p->exchangeUser = user;
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_set_cost_map(zr_direct_pass* p, void* d_cycles)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->d_costMap = (unsigned long long*)d_cycles;
+        return ZR_OK;
     }
     zr_status zr_direct_pass_get_output(zr_direct_pass* p, zr_direct_output id, zr_image2d* out)
     {

@@ -35,6 +35,7 @@ namespace
         float alpha_min;
         uint32_t temporalResample, resetTemporal, spatialFlag;
         uint32_t rowBegin, rowEnd;      // rows this rank owns (multi-GPU); whole image by default
+        unsigned long long* costMap;    // optional: SM cycles spent per 32-row band
     };
 
     __constant__ float c_disk512[1024];
@@ -85,6 +86,7 @@ namespace
         float4* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
+        const long long t0 = clock64();
         uint2 sg = make_uint2(0, 0);
         const uint32_t groupFlat = blockIdx.x * (ZR_PT_THREADS / 128) + (threadIdx.x >> 7);
         const uint32_t tInGroup = threadIdx.x & 127;
@@ -308,6 +310,8 @@ namespace
             }
         }
 
+        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
+            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
         if (!inBounds)
             return;
         r.rc.seed_replay = seedReplay0;
@@ -396,6 +400,7 @@ namespace
         const zr_rpt_reservoir* __restrict__ resPrev, float4* __restrict__ target, float4* __restrict__ finalImg)
     {
         const zr_frame_constants& fc = f.fc;
+        const long long t0 = clock64();
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int x = (int)(blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7));
         const int y = (int)(prm.rowBegin + blockIdx.y * (ZR_RPT_THREADS / 32) + (warp >> 2) * 4 + (lane >> 3));
@@ -518,6 +523,8 @@ namespace
         if (needCtx && okReplay)
             ctx = ctx.Quantize();
         const OffsetPath shift = Shift2_Sync(ok, sc, cur.pos, cur.normal, cur.eta_next, cur.surface, r_prev.rc, &ctx, prm.alpha_min);
+        if (prm.costMap && threadIdx.x == 0 && y < (int)f.H)
+            atomicAdd(&prm.costMap[y >> 5], (unsigned long long)(clock64() - t0));
         if (!ok)
             return;         // past the last barrier
         const float targetLum_curr = Math::Luminance(shift.target);
@@ -792,6 +799,7 @@ namespace
         const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap, uint32_t dispX, uint32_t dispY)
     {
         const zr_frame_constants& fc = f.fc;
+        const long long t0 = clock64();
         uint2 sg = make_uint2(0, 0);
         const uint32_t groupFlat = blockIdx.x * (ZR_RPT_THREADS / 64) + (threadIdx.x >> 6);
         const uint32_t tInGroup = threadIdx.x & 63;
@@ -941,6 +949,8 @@ namespace
             if (active)
                 SuppressOutlier((total - r_curr.w_sum) / 32.0f, r_curr);
         }
+        if (prm.costMap && threadIdx.x == 0 && sp.y < f.H)
+            atomicAdd(&prm.costMap[sp.y >> 5], (unsigned long long)(clock64() - t0));
         if (!active)
             return;
         if (changed)
@@ -985,7 +995,11 @@ struct zr_indirect_pass
     bool isTemporalReservoirValid = false;
     bool resetTemporalTextures = true;
     bool patternLoaded = false;
+    // strip-sharded frames: owned rows, halo-exchange hook, optional cost map
     uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
+    zr_halo_exchange_fn exchange = nullptr;
+    void* exchangeUser = nullptr;
+    unsigned long long* d_costMap = nullptr;
     zr_indirect_params params{};
 
     static void Defaults(zr_indirect_params* p)
@@ -1096,6 +1110,7 @@ struct zr_indirect_pass
         prm.boilingSuppression = params.boiling_suppression; prm.sortSpatial = params.sort_spatial; prm.alpha_min = params.alpha_min;
         prm.temporalResample = doTemporal; prm.resetTemporal = resetTemporalTextures; prm.spatialFlag = doSpatial;
         prm.rowBegin = rowBegin; prm.rowEnd = rowEnd < height ? rowEnd : height;
+        prm.costMap = d_costMap;
         const uint32_t rows = prm.rowEnd - prm.rowBegin;
 
         int cur = currTemporalIdx;
@@ -1111,6 +1126,12 @@ struct zr_indirect_pass
             k_temporal<<<dim3((width + 31) / 32, (rows + ZR_RPT_THREADS / 32 - 1) / (ZR_RPT_THREADS / 32)), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
                 d_target, d_final);
             ZR_LAUNCH_CHECK();
+        }
+        // reservoirs written so far are read by neighbours (spatial pass) and by the next frame's temporal pass
+        if (exchange)
+        {
+            const zr_image2d plane{ d_res[cur], width, height, width * 64u, 64u };
+            exchange(exchangeUser, &plane, 1, stream);
         }
         if (doSpatial && lastStage != ZR_RPT_STAGE_PATHTRACE && lastStage != ZR_RPT_STAGE_TEMPORAL)
         {
@@ -1134,6 +1155,11 @@ struct zr_indirect_pass
                 k_spatial<<<(dispX * dispY + ZR_RPT_THREADS / 64 - 1) / (ZR_RPT_THREADS / 64), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
                     d_threadMap[1], dispX, dispY);
                 ZR_LAUNCH_CHECK();
+                if (exchange)
+                {
+                    const zr_image2d plane{ rout, width, height, width * 64u, 64u };
+                    exchange(exchangeUser, &plane, 1, stream);
+                }
             }
         }
         isTemporalReservoirValid = true;
@@ -1217,6 +1243,18 @@ extern "C"
         uses[3] = zr_resource_use{ ZR_RES_ALIAS_TABLE, 0 };
         uses[4] = zr_resource_use{ ZR_RES_INDIRECT_FINAL, 1 };
         *n = 5;
+        return ZR_OK;
+    }
+    zr_status zr_indirect_pass_set_halo_exchange(zr_indirect_pass* p, zr_halo_exchange_fn fn, void* user)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->exchange = fn; p->exchangeUser = user;
+        return ZR_OK;
+    }
+    zr_status zr_indirect_pass_set_cost_map(zr_indirect_pass* p, void* d_cycles)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->d_costMap = (unsigned long long*)d_cycles;
         return ZR_OK;
     }
     zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1)

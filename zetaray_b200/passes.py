@@ -126,6 +126,9 @@ class GBufferRT(_Pass):
         self.handle = C.c_void_p()
         check(lib.zr_gbuffer_pass_create(C.byref(self.handle)))
 
+    def SetRows(self, y0, y1):
+        check(lib.zr_gbuffer_pass_set_rows(self.handle, y0, y1))
+
     def Render(self, fi, stream=None):
         check(lib.zr_gbuffer_pass_render(self.handle, C.byref(fi), stream))
 
@@ -149,6 +152,17 @@ class DirectLighting(_Pass):
 
     def ResetTemporal(self):
         check(lib.zr_direct_pass_reset_temporal(self.handle))
+
+    def SetRows(self, y0, y1):
+        check(lib.zr_direct_pass_set_rows(self.handle, y0, y1))
+
+    def SetHaloExchange(self, fn):
+        """fn: a _lib.HALO_EXCHANGE_FN instance (kept alive here) or None."""
+        self._halo_fn = fn
+        check(lib.zr_direct_pass_set_halo_exchange(self.handle, fn if fn is not None else _lib.HALO_EXCHANGE_FN(), None))
+
+    def SetCostMap(self, d_cycles):
+        check(lib.zr_direct_pass_set_cost_map(self.handle, C.c_void_p(d_cycles)))
 
     def Render(self, fi, stream=None):
         check(lib.zr_direct_pass_render(self.handle, C.byref(fi), stream))
@@ -182,6 +196,13 @@ class IndirectLighting(_Pass):
     def SetRows(self, y0, y1):
         check(lib.zr_indirect_pass_set_rows(self.handle, y0, y1))
 
+    def SetHaloExchange(self, fn):
+        self._halo_fn = fn
+        check(lib.zr_indirect_pass_set_halo_exchange(self.handle, fn if fn is not None else _lib.HALO_EXCHANGE_FN(), None))
+
+    def SetCostMap(self, d_cycles):
+        check(lib.zr_indirect_pass_set_cost_map(self.handle, C.c_void_p(d_cycles)))
+
     def Render(self, fi, stream=None, until=0):
         if until:
             check(lib.zr_indirect_pass_render_until(self.handle, C.byref(fi), until, stream))
@@ -205,6 +226,9 @@ class Compositing(_Pass):
         p = _lib.CompositingParams(emissive_di, indirect, firefly_filter)
         check(lib.zr_compositing_pass_set_params(self.handle, C.byref(p)))
 
+    def SetRows(self, y0, y1):
+        check(lib.zr_compositing_pass_set_rows(self.handle, y0, y1))
+
     def Render(self, fi, d_direct, d_indirect, stream=None):
         check(lib.zr_compositing_pass_render(self.handle, C.byref(fi), C.c_void_p(d_direct), C.c_void_p(d_indirect), stream))
 
@@ -220,6 +244,9 @@ class TAA(_Pass):
     def __init__(self, w, h):
         self.handle = C.c_void_p()
         check(lib.zr_taa_pass_create(w, h, C.byref(self.handle)))
+
+    def SetRows(self, y0, y1):
+        check(lib.zr_taa_pass_set_rows(self.handle, y0, y1))
 
     def Render(self, fi, d_signal, stream=None):
         check(lib.zr_taa_pass_render(self.handle, C.byref(fi), C.c_void_p(d_signal), stream))
