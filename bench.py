@@ -129,6 +129,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--expensive-first", action="store_true",
+                    help="launch the lighting kernels' thread blocks most-expensive-tile-first instead of in plain order (measured: no gain)")
     ap.add_argument("--single-stream", action="store_true", help="record DirectLighting on the main stream instead of a second one")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -193,12 +195,14 @@ def main():
     # ---- warm-up: unsharded frames bring temporal + spatial reuse to steady state (frame >= 3) and measure the cost
     # of every 32-row band; then the strips are cut and the same number of sharded warm-up frames follows ----
     plan_info = None
-    if world > 1:
-        sharded.begin_cost_measurement()
+    sharded.begin_cost_measurement()
     for _ in range(args.warmup):
         frame(seq.next())
+    costs = sharded.end_cost_measurement(schedule=args.expensive_first)
+    if world == 1:
+        for _ in range(args.warmup):
+            frame(seq.next())
     if world > 1:
-        costs = sharded.end_cost_measurement()
         plan = StripPlan.balanced(H, world, costs)
         sharded.shard(plan)
         sc = plan.strip_costs(costs)
@@ -313,7 +317,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [W, H], "spp": 1, "bounces": 3, "restir_pt": "temporal + 1 spatial pass",
                        "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halo all-gather)" % world if world > 1 else "single GPU",
-                       "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2,
+                       "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2, "block_order": "expensive tiles first" if args.expensive_first else "plain",
                        "l2": "per-frame working set ~0.8 GB >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_value, 3), "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(_lib.FrameConstants),
                     "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},

@@ -382,8 +382,12 @@ ZR_API zr_status zr_direct_pass_set_params(zr_direct_pass* p, const zr_direct_pa
 ZR_API zr_status zr_direct_pass_render(zr_direct_pass* p, const zr_frame_inputs* in, void* stream);
 ZR_API zr_status zr_direct_pass_set_rows(zr_direct_pass* p, uint32_t y0, uint32_t y1);
 ZR_API zr_status zr_direct_pass_set_halo_exchange(zr_direct_pass* p, zr_halo_exchange_fn fn, void* user);
-/* optional: d_cycles[ceil(H/32)] (uint64, device) accumulates the SM cycles each 32-row band costs; used to balance strips */
+/* Cost feedback (optional). set_cost_map: d_cycles[ceil(H/32)][ceil(W/32)] (uint64, device, row-major) accumulates the SM
+ * cycles each 32x32-pixel tile costs while set. set_schedule_costs: the pass then launches only the thread blocks that
+ * touch its rows, most expensive tile first (csrc/zr_schedule.h); h_tile_cost == NULL restores plain order. Strip
+ * boundaries are chosen from the same numbers (zetaray_b200/sharding.py). Results do not depend on either call. */
 ZR_API zr_status zr_direct_pass_set_cost_map(zr_direct_pass* p, void* d_cycles);
+ZR_API zr_status zr_direct_pass_set_schedule_costs(zr_direct_pass* p, const double* h_tile_cost, uint32_t tiles_x, uint32_t tiles_y);
 ZR_API zr_status zr_direct_pass_get_output(zr_direct_pass* p, zr_direct_output id, zr_image2d* out);
 ZR_API zr_status zr_direct_pass_describe_io(zr_direct_pass* p, zr_resource_use* uses, int* n);
 ZR_API void zr_direct_pass_destroy(zr_direct_pass* p);
@@ -428,6 +432,7 @@ ZR_API zr_status zr_indirect_pass_describe_io(zr_indirect_pass* p, zr_resource_u
 ZR_API zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1);
 ZR_API zr_status zr_indirect_pass_set_halo_exchange(zr_indirect_pass* p, zr_halo_exchange_fn fn, void* user);
 ZR_API zr_status zr_indirect_pass_set_cost_map(zr_indirect_pass* p, void* d_cycles);
+ZR_API zr_status zr_indirect_pass_set_schedule_costs(zr_indirect_pass* p, const double* h_tile_cost, uint32_t tiles_x, uint32_t tiles_y);
 ZR_API void zr_indirect_pass_destroy(zr_indirect_pass* p);
 
 /* ---- Compositing + FireflyFilter (Compositing/Compositing.cpp:83-145) ---- */

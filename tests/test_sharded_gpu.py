@@ -60,7 +60,7 @@ def _worker(rank, world, port, W, H, warm, frames, out_dir):
             fc = seq.next()
             A.render(fiA, fc, stream, st)
             B.render(fiB, fc, stream, st)
-        costs = B.end_cost_measurement()
+        costs = B.end_cost_measurement(schedule=(world == 2))     # world 2 also exercises the expensive-first block order
         assert sum(costs) > 0, "cost map stayed empty"
         plan = StripPlan.balanced(H, world, costs)
         B.shard(plan)

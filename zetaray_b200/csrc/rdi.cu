@@ -9,6 +9,7 @@
 // the RGBA16F target plane is a uint2 (8 B/px). k_di_spatial keeps the reference's 8x8 group / swizzle so one
 // warp is one reference wave (the disocclusion vote is a wave op) and the group RNG is seeded by the block id.
 #include "zr_pixel.cuh"
+#include "zr_schedule.h"
 
 namespace zr
 {
@@ -18,8 +19,13 @@ namespace
     {
         uint32_t temporal, spatial, stochasticSpatial, extraDisocclusion, M_max; float alpha_min; uint32_t reset;
         uint32_t rowBegin, rowEnd;              // rows this device owns (strip-sharded frames)
-        unsigned long long* costMap;            // optional: SM cycles spent per 32-row band
+        unsigned long long* costMap;            // optional: SM cycles spent per 32x32-pixel tile
     };
+    ZR_D void AccountCost(unsigned long long* costMap, uint32_t W, uint32_t H, uint32_t x, uint32_t y, long long t0)
+    {
+        if (costMap && threadIdx.x == 0 && x < W && y < H)
+            atomicAdd(&costMap[(size_t)(y >> 5) * ((W + 31) >> 5) + (x >> 5)], (unsigned long long)(clock64() - t0));
+    }
 
     __constant__ float c_disk32[64];
 
@@ -518,11 +524,12 @@ struct PairwiseMIS
     // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting. A block is ZR_RDI_THREADS/64 consecutive 8x8 groups of the
     // reference's swizzled dispatch, walking the resampling phases together (no thread leaves before the last barrier).
     __global__ void ZR_LB(ZR_RDI_THREADS) k_di_temporal(SceneDev sc, FrameView f, DIParams prm, zr_rdi_reservoir* __restrict__ resCurr,
-        const zr_rdi_reservoir* __restrict__ resPrev, uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
+        const zr_rdi_reservoir* __restrict__ resPrev, uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY,
+        const uint32_t* __restrict__ order)
     {
         const zr_frame_constants& fc = f.fc;
         uint2 sg = make_uint2(0, 0);
-        const uint32_t groupFlat = blockIdx.x * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t groupFlat = order[blockIdx.x] * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
         const uint32_t tInGroup = threadIdx.x & 63;
         uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
@@ -580,8 +587,7 @@ struct PairwiseMIS
                 r.target = Math::Sanitize(r.target);
             }
         }
-        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
-            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
+        AccountCost(prm.costMap, f.W, f.H, px.x, px.y, t0);
         if (!act)
             return;
         if (prm.temporal || prm.reset)
@@ -596,11 +602,12 @@ struct PairwiseMIS
 
     // ReSTIR_DI_Spatial.hlsl main + SpatialResample
     __global__ void ZR_LB(ZR_RDI_THREADS) k_di_spatial(SceneDev sc, FrameView f, DIParams prm, const zr_rdi_reservoir* __restrict__ resCurr,
-        const uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
+        const uint2* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY,
+        const uint32_t* __restrict__ order)
     {
         const zr_frame_constants& fc = f.fc;
         uint2 sg = make_uint2(0, 0);
-        const uint32_t groupFlat = blockIdx.x * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t groupFlat = order[blockIdx.x] * (ZR_RDI_THREADS / 64) + (threadIdx.x >> 6);
         const uint32_t tInGroup = threadIdx.x & 63;
         uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
@@ -713,8 +720,7 @@ struct PairwiseMIS
             }
             pairwiseMIS.Stream_Sync(go, sc, r, p.pos, p.normal, p.surface, r_spatial, pos_i, pi.normal, surface_i, rng);
         }
-        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
-            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
+        AccountCost(prm.costMap, f.W, f.H, px.x, px.y, t0);
         if (!active)
             return;
         pairwiseMIS.End(r, rng);
@@ -748,6 +754,8 @@ struct zr_direct_pass
     zr_halo_exchange_fn exchange = nullptr;
     void* exchangeUser = nullptr;
     unsigned long long* d_costMap = nullptr;
+    zr::TileCosts tileCosts;
+    zr::BlockSchedule sched;        // both kernels share the 8x8-group geometry
 
     static void Defaults(zr_direct_params* p)
     {
@@ -758,6 +766,7 @@ struct zr_direct_pass
     void Release()
     {
         for (int i = 0; i < 2; i++) { if (d_res[i]) cudaFree(d_res[i]); d_res[i] = nullptr; }
+        sched.Release();
         if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final);
         d_target = nullptr; d_final = nullptr;
     }
@@ -843,8 +852,11 @@ struct zr_direct_pass
             params.alpha_min, resetTemporalTextures, rowBegin, rowEnd < height ? rowEnd : height, d_costMap };
         const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
         const int cur = currTemporalIdx;
+        if (!sched.UpToDate(prm.rowBegin, prm.rowEnd, tileCosts.version))
+            ZR_CUDA(sched.Upload(zr::ScheduleSwizzled(dispX, dispY, 8, 8, ZR_RDI_THREADS / 64, prm.rowBegin, prm.rowEnd, tileCosts),
+                prm.rowBegin, prm.rowEnd, tileCosts.version));
         ZR_PROF("k_di_temporal", stream);
-        k_di_temporal<<<(dispX * dispY + ZR_RDI_THREADS / 64 - 1) / (ZR_RDI_THREADS / 64), ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY);
+        k_di_temporal<<<sched.count, ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, dispX, dispY, sched.d_order);
         ZR_LAUNCH_CHECK();
         // the temporal output is what neighbours read in the spatial pass and what the next frame reprojects into
         if (exchange)
@@ -855,7 +867,7 @@ struct zr_direct_pass
         if (doSpatial)
         {
             ZR_PROF("k_di_spatial", stream);
-            k_di_spatial<<<(dispX * dispY + ZR_RDI_THREADS / 64 - 1) / (ZR_RDI_THREADS / 64), ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
+            k_di_spatial<<<sched.count, ZR_RDI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY, sched.d_order);
             ZR_LAUNCH_CHECK();
         }
         isTemporalReservoirValid = true;
@@ -911,6 +923,19 @@ extern "C"
     {
         if (!p) return ZR_ERR_INVALID_ARG;
         p->exchange = fn; p->exchangeUser = user;
+        return ZR_OK;
+    }
+    zr_status zr_direct_pass_set_schedule_costs(zr_direct_pass* p, const double* h_tile_cost, uint32_t tiles_x, uint32_t tiles_y)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        if (h_tile_cost && (tiles_x != (p->width + 31) / 32 || tiles_y != (p->height + 31) / 32))
+        {
+            zr::set_error("zr_direct_pass_set_schedule_costs: expected %u x %u tiles", (p->width + 31) / 32, (p->height + 31) / 32);
+            return ZR_ERR_INVALID_ARG;
+        }
+        p->tileCosts.cost.assign(h_tile_cost ? h_tile_cost : nullptr, h_tile_cost ? h_tile_cost + (size_t)tiles_x * tiles_y : nullptr);
+        p->tileCosts.tilesX = h_tile_cost ? tiles_x : 0;
+        p->tileCosts.version++;
         return ZR_OK;
     }
     zr_status zr_direct_pass_set_cost_map(zr_direct_pass* p, void* d_cycles)

@@ -17,6 +17,7 @@
 // Per-pixel state moves as 128-bit accesses: 64-byte reservoir records, float4 target/final, uint4 G-buffer.
 #include "zr_rpt.cuh"
 #include "zr_pixel.cuh"
+#include "zr_schedule.h"
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -35,8 +36,15 @@ namespace
         float alpha_min;
         uint32_t temporalResample, resetTemporal, spatialFlag;
         uint32_t rowBegin, rowEnd;      // rows this rank owns (multi-GPU); whole image by default
-        unsigned long long* costMap;    // optional: SM cycles spent per 32-row band
+        unsigned long long* costMap;    // optional: SM cycles spent per 32x32-pixel tile ((W + 31) / 32 per row)
     };
+
+    // accounts the cycles a block took to the tile of its first pixel
+    ZR_D void AccountCost(unsigned long long* costMap, uint32_t W, uint32_t H, uint32_t x, uint32_t y, long long t0)
+    {
+        if (costMap && threadIdx.x == 0 && x < W && y < H)
+            atomicAdd(&costMap[(size_t)(y >> 5) * ((W + 31) >> 5) + (x >> 5)], (unsigned long long)(clock64() - t0));
+    }
 
     __constant__ float c_disk512[1024];
 
@@ -83,12 +91,12 @@ namespace
     // A block is ZR_PT_THREADS/128 consecutive 16x8 groups of the reference's swizzled dispatch; each warp is one
     // reference wave. The warps of a block walk the bounce phases together (zr_rpt.cuh "block-synchronous phases").
     __global__ void ZR_LB(ZR_PT_THREADS) k_pathtrace(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ res,
-        float4* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY)
+        float4* __restrict__ target, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY, const uint32_t* __restrict__ order)
     {
         const zr_frame_constants& fc = f.fc;
         const long long t0 = clock64();
         uint2 sg = make_uint2(0, 0);
-        const uint32_t groupFlat = blockIdx.x * (ZR_PT_THREADS / 128) + (threadIdx.x >> 7);
+        const uint32_t groupFlat = order[blockIdx.x] * (ZR_PT_THREADS / 128) + (threadIdx.x >> 7);
         const uint32_t tInGroup = threadIdx.x & 127;
         uint2 px = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
@@ -310,8 +318,7 @@ namespace
             }
         }
 
-        if (prm.costMap && threadIdx.x == 0 && px.y < f.H)
-            atomicAdd(&prm.costMap[px.y >> 5], (unsigned long long)(clock64() - t0));
+        AccountCost(prm.costMap, f.W, f.H, px.x, px.y, t0);
         if (!inBounds)
             return;
         r.rc.seed_replay = seedReplay0;
@@ -397,14 +404,16 @@ namespace
 #define ZR_RPT_THREADS 512
 #endif
     __global__ void ZR_LB(ZR_RPT_THREADS) k_temporal(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ resCurr,
-        const zr_rpt_reservoir* __restrict__ resPrev, float4* __restrict__ target, float4* __restrict__ finalImg)
+        const zr_rpt_reservoir* __restrict__ resPrev, float4* __restrict__ target, float4* __restrict__ finalImg,
+        uint32_t gridX, const uint32_t* __restrict__ order)
     {
         const zr_frame_constants& fc = f.fc;
         const long long t0 = clock64();
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int x = (int)(blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7));
-        const int y = (int)(prm.rowBegin + blockIdx.y * (ZR_RPT_THREADS / 32) + (warp >> 2) * 4 + (lane >> 3));
-        bool act = !(x >= (int)f.W || y >= (int)f.H || y >= (int)prm.rowEnd);
+        const uint32_t bid = order[blockIdx.x];
+        const int x = (int)((bid % gridX) * 32 + (warp & 3) * 8 + (lane & 7));
+        const int y = (int)((bid / gridX) * (ZR_RPT_THREADS / 32) + (warp >> 2) * 4 + (lane >> 3));
+        bool act = !(x >= (int)f.W || y >= (int)f.H || y < (int)prm.rowBegin || y >= (int)prm.rowEnd);
         const size_t idx = act ? (size_t)y * f.W + x : 0;
         if (act)
         {
@@ -523,8 +532,7 @@ namespace
         if (needCtx && okReplay)
             ctx = ctx.Quantize();
         const OffsetPath shift = Shift2_Sync(ok, sc, cur.pos, cur.normal, cur.eta_next, cur.surface, r_prev.rc, &ctx, prm.alpha_min);
-        if (prm.costMap && threadIdx.x == 0 && y < (int)f.H)
-            atomicAdd(&prm.costMap[y >> 5], (unsigned long long)(clock64() - t0));
+        AccountCost(prm.costMap, f.W, f.H, (uint32_t)x, (uint32_t)y, t0);
         if (!ok)
             return;         // past the last barrier
         const float targetLum_curr = Math::Luminance(shift.target);
@@ -796,12 +804,13 @@ namespace
     // A block is ZR_RPT_THREADS/64 consecutive 8x8 groups of the reference's swizzled dispatch (two waves each).
     __global__ void ZR_LB(ZR_RPT_THREADS) k_spatial(SceneDev sc, FrameView f, RptParams prm, const zr_rpt_reservoir* __restrict__ resIn,
         zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target, float4* __restrict__ finalImg,
-        const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap, uint32_t dispX, uint32_t dispY)
+        const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap, uint32_t dispX, uint32_t dispY,
+        const uint32_t* __restrict__ order)
     {
         const zr_frame_constants& fc = f.fc;
         const long long t0 = clock64();
         uint2 sg = make_uint2(0, 0);
-        const uint32_t groupFlat = blockIdx.x * (ZR_RPT_THREADS / 64) + (threadIdx.x >> 6);
+        const uint32_t groupFlat = order[blockIdx.x] * (ZR_RPT_THREADS / 64) + (threadIdx.x >> 6);
         const uint32_t tInGroup = threadIdx.x & 63;
         uint2 sp = make_uint2(0xffffffffu, 0xffffffffu);
         if (groupFlat < dispX * dispY)
@@ -949,8 +958,7 @@ namespace
             if (active)
                 SuppressOutlier((total - r_curr.w_sum) / 32.0f, r_curr);
         }
-        if (prm.costMap && threadIdx.x == 0 && sp.y < f.H)
-            atomicAdd(&prm.costMap[sp.y >> 5], (unsigned long long)(clock64() - t0));
+        AccountCost(prm.costMap, f.W, f.H, sp.x, sp.y, t0);
         if (!active)
             return;
         if (changed)
@@ -1000,6 +1008,21 @@ struct zr_indirect_pass
     zr_halo_exchange_fn exchange = nullptr;
     void* exchangeUser = nullptr;
     unsigned long long* d_costMap = nullptr;
+    // block schedules (zr_schedule.h), rebuilt when the rows or the tile costs change
+    zr::TileCosts tileCosts;
+    zr::BlockSchedule schedPathTrace, schedTemporal, schedSpatial;
+    zr_status UpdateSchedules()
+    {
+        const uint32_t y0 = rowBegin, y1 = rowEnd < height ? rowEnd : height, v = tileCosts.version;
+        if (!schedPathTrace.UpToDate(y0, y1, v))
+            ZR_CUDA(schedPathTrace.Upload(zr::ScheduleSwizzled((width + 15) / 16, (height + 7) / 8, 16, 8, ZR_PT_THREADS / 128, y0, y1, tileCosts), y0, y1, v));
+        if (!schedTemporal.UpToDate(y0, y1, v))
+            ZR_CUDA(schedTemporal.Upload(zr::ScheduleTiles((width + 31) / 32, (height + ZR_RPT_THREADS / 32 - 1) / (ZR_RPT_THREADS / 32), 32,
+                ZR_RPT_THREADS / 32, y0, y1, tileCosts), y0, y1, v));
+        if (!schedSpatial.UpToDate(y0, y1, v))
+            ZR_CUDA(schedSpatial.Upload(zr::ScheduleSwizzled((width + 7) / 8, (height + 7) / 8, 8, 8, ZR_RPT_THREADS / 64, y0, y1, tileCosts), y0, y1, v));
+        return ZR_OK;
+    }
     zr_indirect_params params{};
 
     static void Defaults(zr_indirect_params* p)
@@ -1013,6 +1036,7 @@ struct zr_indirect_pass
     void Release()
     {
         for (int i = 0; i < 2; i++) { if (d_res[i]) cudaFree(d_res[i]); d_res[i] = nullptr; if (d_threadMap[i]) cudaFree(d_threadMap[i]); d_threadMap[i] = nullptr; }
+        schedPathTrace.Release(); schedTemporal.Release(); schedSpatial.Release();
         if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final); if (d_neighbor) cudaFree(d_neighbor);
         d_target = d_final = nullptr; d_neighbor = nullptr;
     }
@@ -1111,20 +1135,23 @@ struct zr_indirect_pass
         prm.temporalResample = doTemporal; prm.resetTemporal = resetTemporalTextures; prm.spatialFlag = doSpatial;
         prm.rowBegin = rowBegin; prm.rowEnd = rowEnd < height ? rowEnd : height;
         prm.costMap = d_costMap;
+        st = UpdateSchedules();
+        if (st != ZR_OK) return st;
         const uint32_t rows = prm.rowEnd - prm.rowBegin;
 
         int cur = currTemporalIdx;
         {
             const uint32_t dispX = (width + 15) / 16, dispY = (height + 7) / 8;
             ZR_PROF("k_pathtrace", stream);
-            k_pathtrace<<<(dispX * dispY + ZR_PT_THREADS / 128 - 1) / (ZR_PT_THREADS / 128), ZR_PT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY);
+            k_pathtrace<<<schedPathTrace.count, ZR_PT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY,
+                schedPathTrace.d_order);
             ZR_LAUNCH_CHECK();
         }
         if (doTemporal && lastStage != ZR_RPT_STAGE_PATHTRACE)
         {
             ZR_PROF("k_temporal", stream);
-            k_temporal<<<dim3((width + 31) / 32, (rows + ZR_RPT_THREADS / 32 - 1) / (ZR_RPT_THREADS / 32)), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
-                d_target, d_final);
+            k_temporal<<<schedTemporal.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
+                d_target, d_final, (width + 31) / 32, schedTemporal.d_order);
             ZR_LAUNCH_CHECK();
         }
         // reservoirs written so far are read by neighbours (spatial pass) and by the next frame's temporal pass
@@ -1152,8 +1179,8 @@ struct zr_indirect_pass
                 }
                 const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
                 ZR_PROF("k_spatial", stream);
-                k_spatial<<<(dispX * dispY + ZR_RPT_THREADS / 64 - 1) / (ZR_RPT_THREADS / 64), ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
-                    d_threadMap[1], dispX, dispY);
+                k_spatial<<<schedSpatial.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
+                    d_threadMap[1], dispX, dispY, schedSpatial.d_order);
                 ZR_LAUNCH_CHECK();
                 if (exchange)
                 {
@@ -1249,6 +1276,19 @@ extern "C"
     {
         if (!p) return ZR_ERR_INVALID_ARG;
         p->exchange = fn; p->exchangeUser = user;
+        return ZR_OK;
+    }
+    zr_status zr_indirect_pass_set_schedule_costs(zr_indirect_pass* p, const double* h_tile_cost, uint32_t tiles_x, uint32_t tiles_y)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        if (h_tile_cost && (tiles_x != (p->width + 31) / 32 || tiles_y != (p->height + 31) / 32))
+        {
+            zr::set_error("zr_indirect_pass_set_schedule_costs: expected %u x %u tiles", (p->width + 31) / 32, (p->height + 31) / 32);
+            return ZR_ERR_INVALID_ARG;
+        }
+        p->tileCosts.cost.assign(h_tile_cost ? h_tile_cost : nullptr, h_tile_cost ? h_tile_cost + (size_t)tiles_x * tiles_y : nullptr);
+        p->tileCosts.tilesX = h_tile_cost ? tiles_x : 0;
+        p->tileCosts.version++;
         return ZR_OK;
     }
     zr_status zr_indirect_pass_set_cost_map(zr_indirect_pass* p, void* d_cycles)

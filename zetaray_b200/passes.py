@@ -164,6 +164,11 @@ class DirectLighting(_Pass):
     def SetCostMap(self, d_cycles):
         check(lib.zr_direct_pass_set_cost_map(self.handle, C.c_void_p(d_cycles)))
 
+    def SetScheduleCosts(self, tile_costs, tiles_x, tiles_y):
+        """tile_costs: sequence of tiles_x * tiles_y floats (row-major) or None."""
+        arr = None if tile_costs is None else (C.c_double * (tiles_x * tiles_y))(*tile_costs)
+        check(lib.zr_direct_pass_set_schedule_costs(self.handle, arr, tiles_x, tiles_y))
+
     def Render(self, fi, stream=None):
         check(lib.zr_direct_pass_render(self.handle, C.byref(fi), stream))
 
@@ -202,6 +207,10 @@ class IndirectLighting(_Pass):
 
     def SetCostMap(self, d_cycles):
         check(lib.zr_indirect_pass_set_cost_map(self.handle, C.c_void_p(d_cycles)))
+
+    def SetScheduleCosts(self, tile_costs, tiles_x, tiles_y):
+        arr = None if tile_costs is None else (C.c_double * (tiles_x * tiles_y))(*tile_costs)
+        check(lib.zr_indirect_pass_set_schedule_costs(self.handle, arr, tiles_x, tiles_y))
 
     def Render(self, fi, stream=None, until=0):
         if until:

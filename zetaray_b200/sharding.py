@@ -214,8 +214,8 @@ class ShardedFrame:
         self.group = group
         self.plan = StripPlan(height, [0, height]) if world == 1 else None
         self.halo = None
-        n_units = StripPlan.num_units(height)
-        self.cost = torch.zeros(n_units, dtype=torch.int64, device="cuda")
+        self.tiles_x, self.tiles_y = (width + UNIT - 1) // UNIT, StripPlan.num_units(height)
+        self.cost = torch.zeros(self.tiles_x * self.tiles_y, dtype=torch.int64, device="cuda")
         self._hook = _lib.HALO_EXCHANGE_FN(self._on_exchange)
         self._lib = _lib
         self._streams = {}
@@ -228,13 +228,20 @@ class ShardedFrame:
         self.p["direct"].SetCostMap(self.cost.data_ptr())
         self.p["indirect"].SetCostMap(self.cost.data_ptr())
 
-    def end_cost_measurement(self):
+    def end_cost_measurement(self, schedule=False):
+        """Returns the cost of every 32-row band (for StripPlan.balanced). With schedule=True the per-tile costs also
+        become the lighting passes' block schedule (expensive tiles first; measured on B200: no gain over plain order,
+        the compact per-strip grid is what matters)."""
         self.p["direct"].SetCostMap(0)
         self.p["indirect"].SetCostMap(0)
         c = self.cost.to(torch.float64)
         if self.world > 1:
             dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.group)     # identical plan on every rank
-        return [float(v) for v in c.tolist()]
+        tiles = [float(v) for v in c.tolist()]
+        if schedule:
+            self.p["direct"].SetScheduleCosts(tiles, self.tiles_x, self.tiles_y)
+            self.p["indirect"].SetScheduleCosts(tiles, self.tiles_x, self.tiles_y)
+        return [sum(tiles[b * self.tiles_x:(b + 1) * self.tiles_x]) for b in range(self.tiles_y)]
 
     # ---- sharding ----
     def shard(self, plan):
