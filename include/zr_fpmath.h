@@ -16,6 +16,9 @@
 #define ZR_FPMATH_H
 
 #include <stdint.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 #include <string.h>
 #include <math.h>
 
@@ -129,6 +132,12 @@ ZR_HD float zr_powf(float x, float y) { return zr_expf(y * zr_logf(x)); }
 /* ---- binary16 <-> binary32, round-to-nearest-even (== F16C / __float2half_rn) ---- */
 ZR_HD uint16_t zr_f32_to_f16(float f)
 {
+#if defined(__CUDA_ARCH__)
+    /* cvt.rn.f16.f32 is the same IEEE round-to-nearest-even conversion (overflow to inf, subnormal halves); only the
+       NaN payload rule below is this file's own, so NaNs take the software path */
+    if (f == f)
+        return __half_as_ushort(__float2half_rn(f));
+#endif
     const uint32_t x = zr_f2u(f);
     const uint32_t sign = (x >> 16) & 0x8000u;
     const uint32_t ax = x & 0x7fffffffu;
@@ -160,6 +169,10 @@ ZR_HD uint16_t zr_f32_to_f16(float f)
 
 ZR_HD float zr_f16_to_f32(uint16_t h)
 {
+#if defined(__CUDA_ARCH__)
+    if (((uint32_t)h & 0x7c00u) != 0x7c00u)     /* finite: the hardware conversion is exact */
+        return __half2float(__ushort_as_half(h));
+#endif
     const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
     const uint32_t exp = ((uint32_t)h >> 10) & 0x1fu;
     uint32_t man = (uint32_t)h & 0x3ffu;

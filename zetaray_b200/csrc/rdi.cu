@@ -519,7 +519,7 @@ struct PairwiseMIS
     }
 
 #ifndef ZR_RDI_THREADS
-#define ZR_RDI_THREADS 512
+#define ZR_RDI_THREADS 1024
 #endif
     // ReSTIR_DI_Temporal.hlsl main + EstimateDirectLighting. A block is ZR_RDI_THREADS/64 consecutive 8x8 groups of the
     // reference's swizzled dispatch, walking the resampling phases together (no thread leaves before the last barrier).

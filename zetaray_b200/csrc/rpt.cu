@@ -401,7 +401,7 @@ namespace
     // so no thread leaves before the last barrier.
     // -------------------------------------------------------------------------------------------
 #ifndef ZR_RPT_THREADS
-#define ZR_RPT_THREADS 512
+#define ZR_RPT_THREADS 1024
 #endif
     __global__ void ZR_LB(ZR_RPT_THREADS) k_temporal(SceneDev sc, FrameView f, RptParams prm, zr_rpt_reservoir* __restrict__ resCurr,
         const zr_rpt_reservoir* __restrict__ resPrev, float4* __restrict__ target, float4* __restrict__ finalImg,

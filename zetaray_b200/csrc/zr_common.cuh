@@ -15,7 +15,7 @@
 // thrashes the instruction cache (ncu: ~80% of stall cycles "no instruction"). ZR_Fn functions become real calls
 // when ZR_NI_LEVEL >= n. Inlining does not change results (no fused contraction, no fast math).
 #ifndef ZR_NI_LEVEL
-#define ZR_NI_LEVEL 2
+#define ZR_NI_LEVEL 0
 #endif
 #define ZR_NI static __device__ __noinline__
 // Register budget of the lighting kernels: ZR_MAXREGS caps registers/thread through __launch_bounds__'s
