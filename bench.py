@@ -297,8 +297,13 @@ def main():
                             "alg_bytes_per_px": ab, "achieved_gbs": None if gbs is None else round(gbs, 1),
                             "frac": None if gbs is None else round(gbs / peak, 4)})
         top = kernels[0]
+        traffic = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")))[top["kernel"]]["dram_bytes"]
+        except Exception:
+            pass
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
                     "note": "algorithmic bytes/px x pixels / CUDA-event duration; traversal-bound kernels are listed for share, "
                             "their HBM fraction is informational (SURVEY 8d)"}
 
