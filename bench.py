@@ -263,8 +263,9 @@ def main():
     kern = {}
     nprof = 5
     check(lib.zr_profile_enable(1))
-    for _ in range(nprof):          # every rank renders (the frame holds collectives) and times its own launches
-        frame(seq.next())
+    for _ in range(nprof):          # every rank renders (the frame holds collectives) and times its own launches;
+        sharded.render(fi, seq.next(), stream)      # single stream here, so a kernel's events do not include waiting for the other stream
+        sharded.gather_output(stream)
     if True:
         buf = C.create_string_buffer(8192)
         check(lib.zr_profile_collect(buf, 8192))
