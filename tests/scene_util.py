@@ -29,6 +29,24 @@ def glossy_cornell():
     return s
 
 
+def glass_cornell():
+    """Cornell variant with transmissive materials (not a reference asset): a clear-glass short box (specular
+    transmission -> the 4-bounce glossy/transmissive budget, eta tracking, T_MIN_TR_RAY shadow rays), a rough coloured
+    glass tall box with a transmission depth (in-medium extinction through zr_logf / zr_expf) and a thin-walled
+    translucent back wall (subsurface lobe)."""
+    s = cornell()
+    m = s.materials.copy()
+    m[7] = zscene.make_material(base_color=(1.0, 1.0, 1.0, 1), roughness=0.0, ior=1.5, transmission=1.0, double_sided=True)
+    m[8] = zscene.make_material(base_color=(0.6, 0.85, 0.7, 1), roughness=0.3, ior=1.33, transmission=1.0, transmission_depth=0.5,
+                                double_sided=True)
+    m[3] = zscene.make_material(base_color=(0.8, 0.7, 0.5, 1), roughness=0.5, thin_walled=True, subsurface=0.6, double_sided=True)
+    s.materials = m
+    return s
+
+
+SCENES = {"cornell": cornell, "glossy": glossy_cornell, "glass": glass_cornell}
+
+
 class OracleScene:
     def __init__(self, flat):
         self.o = orc.load()

@@ -7,12 +7,16 @@ from zetaray_b200._lib import FrameConstants
 FLT_MAX = np.float32(3.402823466e+38)
 
 
-def look_at_frame_constants(w, h, frame=1, jitter=(0.0, 0.0), prev_jitter=(0.0, 0.0), cam=(0.0, 1.2, -4.043)):
-    """cbFrameConstants for the default camera: left-handed, +Z forward, vfov 60 deg."""
+def look_at_frame_constants(w, h, frame=1, jitter=(0.0, 0.0), prev_jitter=(0.0, 0.0), cam=(0.0, 1.2, -4.043), prev_cam=None):
+    """cbFrameConstants for the default camera: left-handed, +Z forward, vfov 60 deg.
+    prev_cam: last frame's camera position (a translating camera); defaults to cam (static)."""
     fc = FrameConstants()
+    pc = cam if prev_cam is None else prev_cam
     view = np.array([[1, 0, 0, -cam[0]], [0, 1, 0, -cam[1]], [0, 0, 1, -cam[2]]], dtype=np.float32)
     inv = np.array([[1, 0, 0, cam[0]], [0, 1, 0, cam[1]], [0, 0, 1, cam[2]]], dtype=np.float32)
-    for name, m in (("CurrView", view), ("PrevView", view), ("CurrViewInv", inv), ("PrevViewInv", inv)):
+    pview = np.array([[1, 0, 0, -pc[0]], [0, 1, 0, -pc[1]], [0, 0, 1, -pc[2]]], dtype=np.float32)
+    pinv = np.array([[1, 0, 0, pc[0]], [0, 1, 0, pc[1]], [0, 0, 1, pc[2]]], dtype=np.float32)
+    for name, m in (("CurrView", view), ("PrevView", pview), ("CurrViewInv", inv), ("PrevViewInv", pinv)):
         arr = getattr(fc, name)
         for i, v in enumerate(m.reshape(-1)):
             arr[i] = float(v)

@@ -6,11 +6,11 @@ import pytest
 from tests.test_rpt_gpu import _diff_report
 
 
-def _frame_loop(which, w, h, nframes, full=False, di_params=None):
+def _frame_loop(which, w, h, nframes, full=False, di_params=None, cam_path=None, accumulate=False):
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, DirectLighting, IndirectLighting, Compositing, TAA, download_image
     from tests import scene_util, rpt_util
-    flat = scene_util.cornell() if which == "cornell" else scene_util.glossy_cornell()
+    flat = scene_util.SCENES[which]()
     R = rpt_util.OracleRenderer(flat, w, h)
     sc = Scene(flat)
     sc.prelighting()
@@ -23,7 +23,7 @@ def _frame_loop(which, w, h, nframes, full=False, di_params=None):
     ind = IndirectLighting(w, h) if full else None
     comp = Compositing(w, h) if full else None
     taa = TAA(w, h) if full else None
-    seq = rpt_util.FrameSequence(w, h)
+    seq = rpt_util.FrameSequence(w, h, cam_path=cam_path, accumulate=accumulate)
     taa_prev = np.zeros((w * h, 2), dtype=np.uint32)
     problems = []
     for fr in range(nframes):
@@ -84,4 +84,18 @@ def test_rdi_variants():
 def test_full_frame_pipeline(which, w, h):
     # G-buffer -> pre-lighting -> ReSTIR DI -> ReSTIR PT -> compositing + firefly -> TAA, 4 frames
     problems, R = _frame_loop(which, w, h, 4, full=True)
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_full_frame_pipeline_glass_moving_camera():
+    # transmissive scene + translating camera through the whole frame (DI disocclusion vote, TAA history reprojection)
+    path = lambda f: (0.04 * f, 1.2, -4.043 + 0.03 * f)
+    problems, _ = _frame_loop("glass", 320, 180, 5, full=True, cam_path=path)
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_full_frame_pipeline_accumulate():
+    problems, _ = _frame_loop("glossy", 256, 144, 4, full=True, accumulate=True)
     assert not problems, "\n".join(problems)

@@ -26,12 +26,12 @@ def _diff_report(name, a, b, fields=None):
     return "%s differs at %d/%d entries; first idx %d got %s want %s" % (name, len(d), len(a), d[0], a[d[0]], b[d[0]])
 
 
-def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None):
+def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, cam_path=None, accumulate=False):
     import torch
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, IndirectLighting, download_image
     from tests import scene_util, rpt_util
-    flat = scene_util.cornell() if which == "cornell" else scene_util.glossy_cornell()
+    flat = scene_util.SCENES[which]()
     R = rpt_util.OracleRenderer(flat, w, h)
     sc = Scene(flat)
     sc.prelighting()
@@ -42,7 +42,7 @@ def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None):
         for k, v in params.items():
             setattr(R.params, k, v)
         ind.SetParams(**params)
-    seq = rpt_util.FrameSequence(w, h, jitter=jitter)
+    seq = rpt_util.FrameSequence(w, h, jitter=jitter, cam_path=cam_path, accumulate=accumulate)
     problems = []
     for fr in range(nframes):
         fc = seq.next()
@@ -109,6 +109,35 @@ def test_rpt_variants():
     problems, _ = _run("glossy", 320, 180, 3, params=dict(sort_spatial=0, boiling_suppression=0, max_non_tr_bounces=5))
     assert not problems, "\n".join(problems)
     problems, _ = _run("glossy", 256, 144, 3, dof=True)
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_rpt_glass_scene():
+    # specular + rough transmission, in-medium extinction, thin-walled translucency; 4 transmissive bounces so the
+    # wave-wide Russian roulette (bounce >= 3) runs; then the same with 5/6 bounces and two spatial passes
+    problems, R = _run("glass", 320, 180, 4)
+    assert not problems, "\n".join(problems)
+    k = R.curr_reservoirs()["meta"] & 0xf
+    assert ((k > 0) & (k < 15)).sum() > 0, "glass scene must exercise k > 2 replay"
+    problems, _ = _run("glass", 256, 144, 4, params=dict(max_non_tr_bounces=5, max_glossy_tr_bounces=6, num_spatial_passes=2))
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["glossy", "glass"])
+def test_rpt_moving_camera(which):
+    # a translating camera: non-zero motion vectors, reprojection into other pixels, disocclusions at the box edges
+    path = lambda f: (0.03 * f, 1.2 + 0.02 * f, -4.043 + 0.05 * f)
+    problems, _ = _run(which, 320, 180, 5, cam_path=path)
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_rpt_accumulate_and_two_spatial_passes():
+    problems, _ = _run("glossy", 256, 144, 4, accumulate=True)
+    assert not problems, "\n".join(problems)
+    problems, _ = _run("cornell", 256, 144, 4, params=dict(num_spatial_passes=2))
     assert not problems, "\n".join(problems)
 
 
