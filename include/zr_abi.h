@@ -330,6 +330,30 @@ ZR_API zr_status zr_estimate_emissive_power(const zr_scene* scene, float* d_powe
 /* Convenience used by the pre-lighting node: power estimate + alias build into the scene's own
  * alias table (frame-1 protocol, ZetaRenderer/Default/PathTracer.cpp:195-240). */
 ZR_API zr_status zr_prelighting_render(zr_scene* scene, void* stream);
+
+/* ---- Presampled emissive sets (PreLighting/PresampleEmissives.hlsl:19-44; SURVEY a-5) ----
+ * num_sets x set_size power-proportional light samples drawn once per frame; every thread group of the lighting passes
+ * then picks ONE set and samples it uniformly, so a group's light fetches stay inside set_size records instead of
+ * scattering over the emissive buffer. The reference enables 128 x 512 when the scene has >= 13107 emissive triangles
+ * (ZetaRenderer/Default/DefaultRendererImpl.h:37-41, DefaultRenderer.cpp:362) and compiles the *_WPS shader variants;
+ * here the host makes the same decision with zr_scene_set_presampling and the kernels branch on it. */
+typedef struct zr_presampled_tri       /* RT::PresampledEmissiveTriangle, ZetaCore/RayTracing/RtCommon.h:312-322 (40 bytes) */
+{
+    float pos[3];
+    uint32_t normal;        /* octahedral, 2 x UNORM16 */
+    float pdf;
+    uint32_t ID;
+    uint32_t idx;
+    uint32_t bary;          /* 2 x UNORM16 */
+    uint16_t le[3];         /* half3 */
+    uint16_t twoSided;
+} zr_presampled_tri;
+#define ZR_PRESAMPLING_MIN_EMISSIVES 13107u
+#define ZR_PRESAMPLING_NUM_SETS 128u
+#define ZR_PRESAMPLING_SET_SIZE 512u
+ZR_API zr_status zr_scene_set_presampling(zr_scene* scene, uint32_t num_sets, uint32_t set_size);  /* 0, 0 = off (default) */
+ZR_API zr_status zr_presample_emissives(zr_scene* scene, uint32_t frame_num, void* stream);       /* once per frame, before lighting */
+ZR_API zr_status zr_scene_get_sample_sets(zr_scene* scene, void** d_sets, uint32_t* num_sets, uint32_t* set_size);
 ZR_API zr_status zr_scene_get_alias_table(const zr_scene* scene, const zr_alias_entry** d_table, uint32_t* n);
 
 /* ------------------------------------------------------------------------------------------

@@ -252,6 +252,34 @@ extern "C"
 
 extern "C"
 {
+    // PresampleEmissives.hlsl:19-44
+    void orc_presample(void* scene_, uint32_t frameNum, uint32_t numTotal, zr_presampled_tri* out)
+    {
+        const Scene& sc = *(Scene*)scene_;
+        for (uint32_t i = 0; i < numTotal; i++)
+        {
+            RNG rng = RNG::InitIdx(i, frameNum);
+            Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+            const zr_emissive_tri& tri = sc.emissives[entry.idx];
+            Light::EmissiveTriSample ls = Light::SampleEmissiveTri(f3(0.0f), tri, rng, false);
+            const float3 le = Light::Le_EmissiveTriangle(tri);
+            zr_presampled_tri s;
+            s.pos[0] = ls.pos.x; s.pos[1] = ls.pos.y; s.pos[2] = ls.pos.z;
+            s.normal = Math::EncodeOct32u(ls.normal);
+            s.pdf = entry.pdf * ls.pdf;
+            s.ID = tri.ID;
+            s.idx = entry.idx;
+            s.bary = Math::EncodeUNorm2(ls.bary);
+            s.le[0] = zr_f32_to_f16(le.x); s.le[1] = zr_f32_to_f16(le.y); s.le[2] = zr_f32_to_f16(le.z);
+            s.twoSided = Light::IsDoubleSided(tri) ? 1 : 0;
+            out[i] = s;
+        }
+    }
+    void orc_scene_set_sample_sets(void* scene_, const zr_presampled_tri* sets, uint32_t numSets, uint32_t setSize)
+    {
+        Scene& sc = *(Scene*)scene_;
+        sc.sampleSets = sets; sc.numSampleSets = numSets; sc.sampleSetSize = setSize;
+    }
     // EstimateTriEmissivePower.hlsl:30-79 without emissive textures
     void orc_estimate_power(void* scene_, float* power)
     {

@@ -143,7 +143,18 @@ namespace
         }
     };
 
-    Reservoir RIS_InitialCandidates(const Scene& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface,
+    // inverse of the thread-group swizzle: which dispatched group (SV_GroupID) renders the pixels of swizzled group (sgx, sgy)
+    void UnswizzleGroup(uint32_t sgx, uint32_t sgy, uint32_t dispX, uint32_t dispY, uint32_t& Gx, uint32_t& Gy)
+    {
+        const uint32_t tileWidth = 16, numGroupsInTile = 16 * dispY;
+        const uint32_t tileID = sgx / tileWidth, gx = sgx % tileWidth, gy = sgy;
+        const uint32_t numFullTiles = dispX / tileWidth;
+        const uint32_t w = tileID < numFullTiles ? tileWidth : dispX - tileWidth * numFullTiles;
+        const uint32_t flat = tileID * numGroupsInTile + gy * w + gx;
+        Gx = flat % dispX; Gy = flat / dispX;
+    }
+
+    Reservoir RIS_InitialCandidates(const Scene& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface, uint32_t sampleSetIdx,
         int numBsdfSamples, RNG& rng)
     {
         Reservoir r = Reservoir::Init();
@@ -193,14 +204,12 @@ namespace
         }
         for (int s_l = 0; s_l < numLightSamples; s_l++)
         {
-            Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
-            const zr_emissive_tri& tri = sc.emissives[entry.idx];
-            Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
-            float3 le = Light::Le_EmissiveTriangle(tri);
-            const float pdf_light = entry.pdf * lightSample.pdf;
-            const uint32_t emissiveIdx = entry.idx;
-            const uint32_t lightID = tri.ID;
-            const bool doubleSided = Light::IsDoubleSided(tri);
+            const Light::LightSample lightSample = Light::SampleLight(sc, pos, sampleSetIdx, rng, false);
+            float3 le = lightSample.le;
+            const float pdf_light = lightSample.pdf;
+            const uint32_t emissiveIdx = lightSample.idx;
+            const uint32_t lightID = lightSample.ID;
+            const bool doubleSided = lightSample.twoSided;
             float3 target = f3(0);
             float3 wi = lightSample.pos - pos;
             const bool isZero = dot(wi, wi) == 0;
@@ -366,7 +375,12 @@ namespace
                     Pixel p = LoadPixel(f, f.core, f.coat, x, y, false, x, y);
                     RNG rng_thread = RNG::Init(x, y, fc.FrameNum);
                     const int numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
-                    Reservoir r = RIS_InitialCandidates(*f.sc, p.pos, p.normal, p.roughness, p.surface, numBsdfSamples, rng_thread);
+                    // group-uniform sample set (ReSTIR_DI_Temporal.hlsl:368-370): Gid of the 8x8 group that renders this pixel
+                    uint32_t Gx, Gy;
+                    UnswizzleGroup(x / 8, y / 8, (f.W + 7) / 8, (f.H + 7) / 8, Gx, Gy);
+                    RNG rng_group = RNG::Init(Gx, Gy, fc.FrameNum);
+                    const uint32_t sampleSetIdx = rng_group.UniformUintBounded_Faster(f.sc->numSampleSets);
+                    Reservoir r = RIS_InitialCandidates(*f.sc, p.pos, p.normal, p.roughness, p.surface, sampleSetIdx, numBsdfSamples, rng_thread);
                     if (prm.temporal)
                     {
                         float2 motionVec = unpack_snorm16x2(f.me[idx].x);
@@ -532,7 +546,7 @@ namespace
                 uint32_t waveDisoccluded = 0;
                 for (int l = 0; l < 32; l++) if (lanes[l].active && lanes[l].disoccluded) waveDisoccluded++;
                 RNG rng_group = RNG::Init(Gx, Gy, fc.FrameNum);
-                rng_group.Uniform();    // sample-set index
+                rng_group.UniformUintBounded_Faster(f.sc->numSampleSets);    // sample-set index: drawn, unused here (ReSTIR_DI_Spatial.hlsl:137)
                 const bool extra = !prm.stochasticSpatial || (rng_group.Uniform() < 0.6f);
                 for (int l = 0; l < 32; l++)
                 {

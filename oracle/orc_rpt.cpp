@@ -66,7 +66,7 @@ namespace
         float3 pos, normal; ShadingData surface; BSDF::BSDFSample bsdfSample; HitEmissive nextHit;
         Reconnection rc; Reservoir r; float3 li, throughput, throughput_k; PrevHit prevHit;
         float eta_curr; bool inTranslucentMedium; int bounce; int maxNumBounces;
-        RNG rngReplay, rngThread, rngGroup; uint32_t seedReplay0;
+        RNG rngReplay, rngThread, rngGroup; uint32_t seedReplay0; uint32_t sampleSetIdx = 0;
         // carried over the wave op
         Hit hitInfo; float eta_next; float3 tr; float prevBsdfSamplePdf; LOBE prevBsdfSampleLobe; int pathVertex;
     };
@@ -131,7 +131,7 @@ namespace
             if (!specular)
             {
                 const uint32_t seed_nee = s.rngThread.State;
-                DirectLightingEstimate ls = NEE_Emissive(sc, s.pos, s.hitInfo.normal, s.surface, s.rngThread);
+                DirectLightingEstimate ls = NEE_Emissive(sc, s.pos, s.hitInfo.normal, s.surface, s.sampleSetIdx, s.rngThread);
                 const float3 fOverPdf = s.throughput * ls.ld;
                 s.li += fOverPdf;
                 if (s.rc.IsCase2() || s.rc.IsCase3())
@@ -238,8 +238,8 @@ namespace
                         s.alive = false;    // returns an empty reservoir, li = 0
                         continue;
                     }
-                    // sampleSetIdx: rngGroup.UniformUintBounded_Faster(numSampleSets) -- one Uniform() consumed
-                    s.rngGroup.Uniform();
+                    // one presampled set for all threads of this group (ReSTIR_PT_PathTrace.hlsl:406-408)
+                    s.sampleSetIdx = s.rngGroup.UniformUintBounded_Faster(f.sc->numSampleSets);
                     // PathTrace prologue
                     s.pos = p.pos; s.normal = p.normal; s.surface = p.surface;
                     s.bounce = 0;

@@ -320,18 +320,16 @@ namespace RPT
     }
 
     // ReSTIR_PT_NEE.hlsli:224-302 (alias-table path)
-    inline DirectLightingEstimate NEE_Emissive(const Scene& sc, float3 pos, float3 normal, ShadingData surface, RNG& rng)
+    inline DirectLightingEstimate NEE_Emissive(const Scene& sc, float3 pos, float3 normal, ShadingData surface, uint32_t sampleSetIdx, RNG& rng)
     {
         DirectLightingEstimate ret = DirectLightingEstimate::Init();
         ret.lt = Light::EMISSIVE;
         ret.lobe = BSDF::ALL;
-        Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
-        const zr_emissive_tri& tri = sc.emissives[entry.idx];
-        Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
-        float3 le = Light::Le_EmissiveTriangle(tri);
-        const float lightPdf = entry.pdf * lightSample.pdf;
-        const uint32_t lightID = tri.ID;
-        const bool twoSided = Light::IsDoubleSided(tri);
+        const Light::LightSample lightSample = Light::SampleLight(sc, pos, sampleSetIdx, rng, true);
+        float3 le = lightSample.le;
+        const float lightPdf = lightSample.pdf;
+        const uint32_t lightID = lightSample.ID;
+        const bool twoSided = lightSample.twoSided;
         const float t = length(lightSample.pos - pos);
         const float3 wi = (lightSample.pos - pos) / t;
         if ((dot(lightSample.normal, -wi) > 0) && (t > 0))

@@ -59,6 +59,9 @@ struct Scene
     const zr_emissive_tri* emissives = nullptr;
     uint32_t numEmissives = 0;
     const zr_alias_entry* aliasTable = nullptr;
+    // presampled emissive sets (PresampleEmissives.hlsl); sampleSetSize == 0: alias-table sampling
+    const zr_presampled_tri* sampleSets = nullptr;
+    uint32_t numSampleSets = 0, sampleSetSize = 0;
     // derived
     std::vector<float3> v0, e1, e2;
     std::vector<uint32_t> triMesh, triPrim, meshFirstTri;
@@ -370,6 +373,38 @@ namespace Light
         ret.normal = normalIs0 ? ret.normal : ret.normal / twoArea;
         ret.normal = reverseNormalIfTwoSided && IsDoubleSided(tri) && dot(pos - ret.pos, ret.normal) < 0 ? -ret.normal : ret.normal;
         return ret;
+    }
+
+    // One NEE light sample from a presampled set (ReSTIR_PT_NEE.hlsli:217-236, ReSTIR_DI_Temporal.hlsl:119-136,
+    // LightSource.hlsli:99-106) or from alias table + uniform point on the triangle (the #else branches there).
+    struct LightSample { float3 pos, normal, le; float2 bary; float pdf; uint32_t idx, ID; bool twoSided; };
+    inline LightSample SampleLight(const Scene& sc, float3 pos, uint32_t sampleSetIdx, RNG& rng, bool advanceRng)
+    {
+        LightSample ls;
+        if (sc.sampleSetSize > 0)
+        {
+            const uint32_t u = rng.UniformUintBounded_Faster(sc.sampleSetSize);
+            const zr_presampled_tri& t = sc.sampleSets[(size_t)sampleSetIdx * sc.sampleSetSize + u];
+            ls.pos = f3(t.pos[0], t.pos[1], t.pos[2]);
+            ls.normal = Math::DecodeOct32(t.normal);
+            ls.bary = Math::DecodeUNorm2(t.bary);
+            ls.le = f3(zr_f16_to_f32(t.le[0]), zr_f16_to_f32(t.le[1]), zr_f16_to_f32(t.le[2]));
+            ls.pdf = t.pdf; ls.idx = t.idx; ls.ID = t.ID; ls.twoSided = t.twoSided != 0;
+            if (ls.twoSided && dot(pos - ls.pos, ls.normal) < 0)
+                ls.normal = -ls.normal;
+            if (advanceRng)
+                rng.Uniform3D();
+        }
+        else
+        {
+            AliasTableSample entry = SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+            const zr_emissive_tri& tri = sc.emissives[entry.idx];
+            EmissiveTriSample ts = SampleEmissiveTri(pos, tri, rng);
+            ls.pos = ts.pos; ls.normal = ts.normal; ls.bary = ts.bary;
+            ls.le = Le_EmissiveTriangle(tri);
+            ls.pdf = entry.pdf * ts.pdf; ls.idx = entry.idx; ls.ID = tri.ID; ls.twoSided = IsDoubleSided(tri);
+        }
+        return ls;
     }
 }
 } // namespace orc

@@ -122,6 +122,7 @@ class OracleRenderer:
         self.gb = [empty, empty]
 
     def gbuffer(self, fc):
+        self.osc.presample(fc.FrameNum)       # PreLighting runs before the lighting passes; no-op unless presampling is on
         self.cur ^= 1
         self.gb[self.cur] = self.osc.gbuffer(fc, tridiff=False, nthreads=self.nthreads)
         return self.gb[self.cur]

@@ -67,6 +67,16 @@ class OracleScene:
             w = self.power.copy()
             self.o.orc_alias_build_emissive(ptr(w), C.c_int64(len(w)), 0, ptr(self.alias))
 
+    def set_presampling(self, num_sets, set_size):
+        """PresampleEmissives: num_sets x set_size records of 40 bytes; 0, 0 switches back to alias-table sampling."""
+        self.num_sets, self.set_size = num_sets, set_size
+        self.sample_sets = np.zeros(max(num_sets * set_size, 1) * 10, dtype=np.uint32)      # 40-byte records
+        self.o.orc_scene_set_sample_sets(self.h, ptr(self.sample_sets) if num_sets else None, num_sets, set_size)
+
+    def presample(self, frame_num):
+        if getattr(self, "num_sets", 0):
+            self.o.orc_presample(self.h, C.c_uint32(frame_num), C.c_uint32(self.num_sets * self.set_size), ptr(self.sample_sets))
+
     def gbuffer(self, fc, tridiff=False, nthreads=8):
         n = fc.RenderWidth * fc.RenderHeight
         core = np.zeros((n, 4), dtype=np.uint32)

@@ -6,7 +6,7 @@ import pytest
 from tests.test_rpt_gpu import _diff_report
 
 
-def _frame_loop(which, w, h, nframes, full=False, di_params=None, cam_path=None, accumulate=False):
+def _frame_loop(which, w, h, nframes, full=False, di_params=None, cam_path=None, accumulate=False, presample=None):
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, DirectLighting, IndirectLighting, Compositing, TAA, download_image
     from tests import scene_util, rpt_util
@@ -14,6 +14,9 @@ def _frame_loop(which, w, h, nframes, full=False, di_params=None, cam_path=None,
     R = rpt_util.OracleRenderer(flat, w, h)
     sc = Scene(flat)
     sc.prelighting()
+    if presample:
+        R.osc.set_presampling(*presample)
+        sc.set_presampling(*presample)
     gb = GBuffers(w, h)
     gpass, di = GBufferRT(), DirectLighting(w, h)
     if di_params:
@@ -36,6 +39,7 @@ def _frame_loop(which, w, h, nframes, full=False, di_params=None, cam_path=None,
         gb.fill_inputs(fi)
         fi.scene = sc.handle
         gpass.Render(fi)
+        sc.presample(fc.FrameNum)
         di.Render(fi)
         check(lib.zr_stream_synchronize(None))
         checks = [("di_reservoir", download_image(di.GetOutput(1), np.uint8, 32).view(rpt_util.RDI).reshape(-1), R.di_curr_reservoirs()),
@@ -99,3 +103,32 @@ def test_full_frame_pipeline_glass_moving_camera():
 def test_full_frame_pipeline_accumulate():
     problems, _ = _frame_loop("glossy", 256, 144, 4, full=True, accumulate=True)
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_presampled_sets_di_and_full_frame():
+    problems, _ = _frame_loop("glossy", 320, 180, 4, presample=(16, 64))
+    assert not problems, "\n".join(problems)
+    problems, _ = _frame_loop("cornell", 333, 187, 4, full=True, presample=(128, 512))
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_presampling_needs_the_presample_pass():
+    from zetaray_b200 import lib, _lib
+    from zetaray_b200.passes import Scene, GBuffers, GBufferRT, DirectLighting
+    from tests import scene_util, rpt_util
+    sc = Scene(scene_util.cornell())
+    sc.prelighting()
+    sc.set_presampling(4, 32)
+    gb, g, di = GBuffers(64, 64), GBufferRT(), DirectLighting(64, 64)
+    fi = _lib.FrameInputs()
+    fi.scene = sc.handle
+    fi.frame = rpt_util.FrameSequence(64, 64).next()
+    gb.flip(); gb.fill_inputs(fi)
+    g.Render(fi)
+    assert lib.zr_direct_pass_render(di.handle, C.byref(fi), None) != 0      # presample pass has not run
+    assert b"zr_presample_emissives" in lib.zr_last_error()
+    sc.presample(1)
+    di.Render(fi)
+    assert lib.zr_scene_set_presampling(sc.handle, 4, 0) != 0

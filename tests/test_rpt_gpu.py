@@ -26,7 +26,7 @@ def _diff_report(name, a, b, fields=None):
     return "%s differs at %d/%d entries; first idx %d got %s want %s" % (name, len(d), len(a), d[0], a[d[0]], b[d[0]])
 
 
-def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, cam_path=None, accumulate=False):
+def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, cam_path=None, accumulate=False, presample=None):
     import torch
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, IndirectLighting, download_image
@@ -35,6 +35,9 @@ def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, c
     R = rpt_util.OracleRenderer(flat, w, h)
     sc = Scene(flat)
     sc.prelighting()
+    if presample:
+        R.osc.set_presampling(*presample)
+        sc.set_presampling(*presample)
     gb = GBuffers(w, h)
     gpass = GBufferRT()
     ind = IndirectLighting(w, h)
@@ -56,8 +59,11 @@ def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, c
         gb.fill_inputs(fi)
         fi.scene = sc.handle
         gpass.Render(fi)
+        sc.presample(fc.FrameNum)
         ind.Render(fi)
         check(lib.zr_stream_synchronize(None))
+        if presample and fr == 0:
+            assert sc.sample_sets().tobytes() == R.osc.sample_sets[:presample[0] * presample[1] * 10].tobytes(), "presampled sets differ"
         got_res = download_image(ind.GetOutput(1), np.uint8, 64).view(rpt_util.RES).reshape(-1)
         got_final = download_image(ind.GetOutput(0), np.float32, 4)
         checks = [("reservoir", got_res, R.curr_reservoirs()), ("final", got_final.view(np.uint32), R.final.view(np.uint32))]
@@ -138,6 +144,16 @@ def test_rpt_accumulate_and_two_spatial_passes():
     problems, _ = _run("glossy", 256, 144, 4, accumulate=True)
     assert not problems, "\n".join(problems)
     problems, _ = _run("cornell", 256, 144, 4, params=dict(num_spatial_passes=2))
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+def test_rpt_presampled_sets():
+    # the *_WPS shader variants: lights come from per-group presampled sets (PresampleEmissives.hlsl); small sets so that
+    # several groups share a set and a set holds repeated lights
+    problems, _ = _run("glossy", 320, 180, 4, presample=(16, 64))
+    assert not problems, "\n".join(problems)
+    problems, _ = _run("glass", 256, 144, 3, presample=(128, 512))
     assert not problems, "\n".join(problems)
 
 

@@ -5,7 +5,7 @@
 // PreLighting.cpp:317-429, 512-585 -- now entirely on the device, alias.cu).
 // Output layout: include/zr_abi.h zr_gbuffer (one 16-byte record + 4-byte depth + 8-byte
 // motion/emissive per pixel, written with 128/64-bit stores).
-#include "zr_scene.cuh"
+#include "zr_rt.cuh"        // scene + emissive-light helpers
 
 namespace zr
 {
@@ -175,6 +175,31 @@ namespace
 
     // one thread per emissive triangle (no emissive textures in this build, so the 64 Halton taps
     // of the reference collapse to the constant 64)
+    // PresampleEmissives.hlsl:19-44: one power-proportional light sample per thread, packed to 40 bytes
+    __global__ void __launch_bounds__(64) k_presample(SceneDev sc, uint32_t frameNum, uint32_t numTotal, zr_presampled_tri* __restrict__ out)
+    {
+        const uint32_t i = blockIdx.x * 64 + threadIdx.x;
+        if (i >= numTotal) return;
+        RNG rng = RNG::InitIdx(i, frameNum);
+        const Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+        const zr_emissive_tri& tri = sc.emissives[entry.idx];
+        const Light::EmissiveTriSample ls = Light::SampleEmissiveTri(f3(0), tri, rng, false);
+        const float3 le = Light::Le_EmissiveTriangle(tri);
+        zr_presampled_tri s;
+        s.pos[0] = ls.pos.x; s.pos[1] = ls.pos.y; s.pos[2] = ls.pos.z;
+        s.normal = Math::EncodeOct32u(ls.normal);
+        s.pdf = entry.pdf * ls.pdf;
+        s.ID = tri.ID;
+        s.idx = entry.idx;
+        s.bary = Math::EncodeUNorm2(ls.bary);
+        s.le[0] = zr_f32_to_f16(le.x); s.le[1] = zr_f32_to_f16(le.y); s.le[2] = zr_f32_to_f16(le.z);
+        s.twoSided = Light::IsDoubleSided(tri) ? 1 : 0;
+        uint2 v[5];
+        memcpy(v, &s, 40);
+        uint2* q = reinterpret_cast<uint2*>(out + i);
+        for (int k = 0; k < 5; k++) q[k] = v[k];
+    }
+
     __global__ void k_emissive_power(SceneDev sc, float* __restrict__ power)
     {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,5 +318,46 @@ extern "C"
         s = zr::alias_table_build(scene->d_power, scene->dev.numEmissives, scene->d_alias, scene->d_aliasScratch, (cudaStream_t)stream);
         if (s == ZR_OK) scene->aliasBuilt = true;
         return s;
+    }
+
+    zr_status zr_scene_set_presampling(zr_scene* scene, uint32_t num_sets, uint32_t set_size)
+    {
+        if (!scene) return ZR_ERR_INVALID_ARG;
+        if ((num_sets == 0) != (set_size == 0) || (uint64_t)num_sets * set_size > (1u << 24))
+        {
+            zr::set_error("zr_scene_set_presampling: num_sets and set_size must both be 0 or both > 0 (at most 2^24 samples)");
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (scene->d_sampleSets) { cudaFree(scene->d_sampleSets); scene->d_sampleSets = nullptr; }
+        scene->dev.sampleSets = nullptr; scene->dev.numSampleSets = 0; scene->dev.sampleSetSize = 0;
+        scene->samplesValid = false;
+        if (num_sets)
+        {
+            ZR_CUDA(cudaMalloc(&scene->d_sampleSets, (size_t)num_sets * set_size * sizeof(zr_presampled_tri)));
+            scene->dev.sampleSets = scene->d_sampleSets; scene->dev.numSampleSets = num_sets; scene->dev.sampleSetSize = set_size;
+        }
+        return ZR_OK;
+    }
+    zr_status zr_presample_emissives(zr_scene* scene, uint32_t frame_num, void* stream)
+    {
+        if (!scene) return ZR_ERR_INVALID_ARG;
+        if (!scene->dev.sampleSetSize) return ZR_OK;        // presampling is off: nothing to do (like the reference's render graph)
+        if (!scene->aliasBuilt || scene->dev.numEmissives == 0)
+        {
+            zr::set_error("zr_presample_emissives: needs emissive triangles and zr_prelighting_render first");
+            return ZR_ERR_NOT_INITIALIZED;
+        }
+        const uint32_t total = scene->dev.numSampleSets * scene->dev.sampleSetSize;
+        ZR_PROF("k_presample", stream);
+        zr::k_presample<<<(total + 63) / 64, 64, 0, (cudaStream_t)stream>>>(scene->dev, frame_num, total, scene->d_sampleSets);
+        ZR_LAUNCH_CHECK();
+        scene->samplesValid = true;
+        return ZR_OK;
+    }
+    zr_status zr_scene_get_sample_sets(zr_scene* scene, void** d_sets, uint32_t* num_sets, uint32_t* set_size)
+    {
+        if (!scene || !d_sets || !num_sets || !set_size) return ZR_ERR_INVALID_ARG;
+        *d_sets = scene->d_sampleSets; *num_sets = scene->dev.numSampleSets; *set_size = scene->dev.sampleSetSize;
+        return ZR_OK;
     }
 }

@@ -157,7 +157,7 @@ struct EmissiveData
 // thread of the block walks the same 2 + 3 sample slots, `act` / the per-pixel sample counts predicate the work.
 #define ZR_PHASE() __syncthreads()
 ZR_D Reservoir RIS_InitialCandidates_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, float roughness, BSDF::ShadingData surface,
-    int numBsdfSamples, RNG& rng)
+    uint32_t sampleSetIdx, int numBsdfSamples, RNG& rng)
 {
     Reservoir r = Reservoir::Init();
     const bool specular = surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
@@ -219,7 +219,7 @@ ZR_D Reservoir RIS_InitialCandidates_Sync(bool act, const SceneDev& sc, float3 p
     for (int s_l = 0; s_l < 3; s_l++)
     {
         const bool go = act && (s_l < numLightSamples);
-        Light::EmissiveTriSample lightSample;
+        Light::LightSample lightSample;
         float3 le = f3(0), target = f3(0), wi = f3(0);
         float pdf_light = 0, t = 0, dwdA = 0;
         uint32_t emissiveIdx = 0, lightID = UINT32_MAX_;
@@ -227,14 +227,12 @@ ZR_D Reservoir RIS_InitialCandidates_Sync(bool act, const SceneDev& sc, float3 p
         ZR_PHASE();
         if (go)
         {
-            Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
-            const zr_emissive_tri& tri = sc.emissives[entry.idx];
-            lightSample = Light::SampleEmissiveTri(pos, tri, rng);
-            le = Light::Le_EmissiveTriangle(tri);
-            pdf_light = entry.pdf * lightSample.pdf;
-            emissiveIdx = entry.idx;
-            lightID = tri.ID;
-            doubleSided = Light::IsDoubleSided(tri);
+            lightSample = Light::SampleLight(sc, pos, sampleSetIdx, rng, false);
+            le = lightSample.le;
+            pdf_light = lightSample.pdf;
+            emissiveIdx = lightSample.idx;
+            lightID = lightSample.ID;
+            doubleSided = lightSample.twoSided;
             wi = lightSample.pos - pos;
             const bool isZero = dot(wi, wi) == 0;
             t = isZero ? 0 : length(wi);
@@ -564,7 +562,10 @@ struct PairwiseMIS
             rng_thread = RNG::Init(x, y, fc.FrameNum);
             numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
         }
-        Reservoir r = RIS_InitialCandidates_Sync(act, sc, p.pos, p.normal, p.roughness, p.surface, numBsdfSamples, rng_thread);
+        // group-uniform index so that every thread of an 8x8 group uses the same presampled set (ReSTIR_DI_Temporal.hlsl:368-370)
+        RNG rng_group = RNG::Init(groupFlat % dispX, groupFlat / dispX, fc.FrameNum);
+        const uint32_t sampleSetIdx = rng_group.UniformUintBounded_Faster(sc.numSampleSets);
+        Reservoir r = RIS_InitialCandidates_Sync(act, sc, p.pos, p.normal, p.roughness, p.surface, sampleSetIdx, numBsdfSamples, rng_thread);
         if (prm.temporal)
         {
             float2 motionVec = f2(0, 0);
@@ -655,7 +656,7 @@ struct PairwiseMIS
         }
         const uint32_t waveDisoccluded = __popc(__ballot_sync(0xffffffffu, active && disoccluded));
         RNG rng_group = RNG::Init(groupFlat % dispX, groupFlat / dispX, fc.FrameNum);
-        rng_group.Uniform();    // sample-set index (unused without presampled sets)
+        rng_group.UniformUintBounded_Faster(sc.numSampleSets);    // sample-set index: drawn, not used by the spatial pass (:137)
         const bool extra = !prm.stochasticSpatial || (rng_group.Uniform() < 0.6f);
         if (prm.extraDisocclusion)
             disoccluded = disoccluded && (waveDisoccluded > 3);
@@ -832,6 +833,11 @@ struct zr_direct_pass
             // PathTracer.cpp:274-284: ReSTIR DI (emissive) only runs when the scene has emissive triangles
             set_error("zr_direct_pass_render: needs emissive triangles and zr_prelighting_render first (SkyDI is not part of this build)");
             return ZR_ERR_UNSUPPORTED;
+        }
+        if (in->scene->dev.sampleSetSize && !in->scene->samplesValid)
+        {
+            set_error("zr_direct_pass_render: presampling is enabled but zr_presample_emissives has not run");
+            return ZR_ERR_NOT_INITIALIZED;
         }
         zr_status st = LoadPattern();
         if (st != ZR_OK) return st;

@@ -129,6 +129,7 @@ namespace
         int bounce = 0, maxNumBounces = 0;
         RNG rngReplay, rngThread, rngGroup;
         rngReplay.State = rngThread.State = rngGroup.State = 0;
+        uint32_t sampleSetIdx = 0;
         uint32_t seedReplay0 = 0;
 
         if (inBounds)
@@ -143,7 +144,7 @@ namespace
             bsdfSample = BSDF::SampleBSDF(p.normal, p.surface, rngReplay);
             if (dot(bsdfSample.bsdfOverPdf, bsdfSample.bsdfOverPdf) != 0)
             {
-                rngGroup.Uniform();     // sample-set index (unused without presampled sets)
+                sampleSetIdx = rngGroup.UniformUintBounded_Faster(sc.numSampleSets);    // one set per thread group (:406-408)
                 pos = p.pos; normal = p.normal; surface = p.surface;
                 throughput = bsdfSample.bsdfOverPdf;
                 prevHit.alpha_lobe = BSDF::LobeAlpha(p.surface, bsdfSample.lobe);
@@ -231,7 +232,7 @@ namespace
                 {
                     seed_nee = rngThread.State;
                     surfNee = surface;
-                    nee = NEE_Emissive_Begin(sc, pos, hitInfo.normal, surfNee, rngThread);
+                    nee = NEE_Emissive_Begin(sc, pos, hitInfo.normal, surfNee, sampleSetIdx, rngThread);
                     if (nee.facing && dot(nee.ld, nee.ld) > 0)
                         seg = SetupSegment(pos, nee.ret.wi, nee.t, hitInfo.normal, nee.ret.ID, surfNee.Transmissive());
                 }
@@ -1111,6 +1112,11 @@ struct zr_indirect_pass
             set_error("zr_indirect_pass_render: emissive integrator needs emissive triangles and zr_prelighting_render first "
                 "(the sun/sky variant is not part of this build)");
             return ZR_ERR_UNSUPPORTED;
+        }
+        if (in->scene->dev.sampleSetSize && !in->scene->samplesValid)
+        {
+            set_error("zr_indirect_pass_render: presampling is enabled but zr_presample_emissives has not run");
+            return ZR_ERR_NOT_INITIALIZED;
         }
         zr_status st = LoadPattern();
         if (st != ZR_OK) return st;

@@ -402,6 +402,7 @@ extern "C"
         if (sc->d_alias) cudaFree(sc->d_alias);
         if (sc->d_power) cudaFree(sc->d_power);
         if (sc->d_aliasScratch) cudaFree(sc->d_aliasScratch);
+        if (sc->d_sampleSets) cudaFree(sc->d_sampleSets);
         delete sc;
     }
     zr_status zr_scene_bvh_stats(const zr_scene* sc, uint32_t out[4])

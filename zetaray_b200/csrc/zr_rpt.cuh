@@ -420,17 +420,15 @@ namespace RPT
     // sampler pdf + MIS. `surface` is the caller's copy with wi set (the reference passes it by value).
     struct NeeLightState { DirectLightingEstimate ret; float3 ld; float t, lightPdf, dwdA; bool facing; };
 
-    ZR_D NeeLightState NEE_Emissive_Begin(const SceneDev& sc, float3 pos, float3 normal, ShadingData& surface, RNG& rng)
+    ZR_D NeeLightState NEE_Emissive_Begin(const SceneDev& sc, float3 pos, float3 normal, ShadingData& surface, uint32_t sampleSetIdx, RNG& rng)
     {
         NeeLightState st;
         st.ret = DirectLightingEstimate::Init();
         st.ret.lt = Light::EMISSIVE;
         st.ret.lobe = BSDF::ALL;
-        Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
-        const zr_emissive_tri& tri = sc.emissives[entry.idx];
-        Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(pos, tri, rng);
-        float3 le = Light::Le_EmissiveTriangle(tri);
-        st.lightPdf = entry.pdf * lightSample.pdf;
+        const Light::LightSample lightSample = Light::SampleLight(sc, pos, sampleSetIdx, rng, true);
+        const float3 le = lightSample.le;
+        st.lightPdf = lightSample.pdf;
         st.t = length(lightSample.pos - pos);
         const float3 wi = (lightSample.pos - pos) / st.t;
         st.facing = (dot(lightSample.normal, -wi) > 0) && (st.t > 0);
@@ -440,8 +438,8 @@ namespace RPT
             st.dwdA = saturate(dot(lightSample.normal, -wi)) / (st.t * st.t);
             surface.SetWi(wi, normal);
             st.ld = le * BSDF::Unified(surface).f * st.dwdA;
-            st.ret.le = le; st.ret.wi = wi; st.ret.ID = tri.ID;
-            st.ret.pos = lightSample.pos; st.ret.normal = lightSample.normal; st.ret.twoSided = Light::IsDoubleSided(tri);
+            st.ret.le = le; st.ret.wi = wi; st.ret.ID = lightSample.ID;
+            st.ret.pos = lightSample.pos; st.ret.normal = lightSample.normal; st.ret.twoSided = lightSample.twoSided;
         }
         return st;
     }

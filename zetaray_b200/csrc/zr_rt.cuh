@@ -226,6 +226,9 @@ namespace Light
         return ret;
     }
 
+    // One light sample for next-event estimation, from either source (ReSTIR_PT_NEE.hlsli:217-248 /
+    // ReSTIR_DI_Temporal.hlsl:119-147): a presampled set of this thread group, or alias table + uniform point on the triangle.
+    struct LightSample { float3 pos, normal, le; float2 bary; float pdf; uint32_t idx, ID; bool twoSided; };
     struct EmissiveTriSample { float3 pos, normal; float2 bary; float pdf; };
     ZR_D EmissiveTriSample SampleEmissiveTri(float3 pos, const zr_emissive_tri& tri, RNG& rng, bool reverseNormalIfTwoSided = true)
     {
@@ -243,6 +246,43 @@ namespace Light
         ret.normal = normalIs0 ? ret.normal : ret.normal / twoArea;
         ret.normal = reverseNormalIfTwoSided && IsDoubleSided(tri) && dot(pos - ret.pos, ret.normal) < 0 ? -ret.normal : ret.normal;
         return ret;
+    }
+
+    // advanceRng: the path tracer keeps the RNG stream identical with and without presampled sets (":235 Deterministic RNG
+    // state regardless of USE_PRESAMPLED_SETS"); ReSTIR DI does not.
+    ZR_D LightSample SampleLight(const SceneDev& sc, float3 pos, uint32_t sampleSetIdx, RNG& rng, bool advanceRng)
+    {
+        LightSample ls;
+        if (sc.sampleSetSize > 0)
+        {
+            const uint32_t u = rng.UniformUintBounded_Faster(sc.sampleSetSize);
+            const zr_presampled_tri* p = sc.sampleSets + (size_t)sampleSetIdx * sc.sampleSetSize + u;
+            // 40-byte records are 8-byte aligned: five 64-bit loads
+            const uint2* q = reinterpret_cast<const uint2*>(p);
+            const uint2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), c = __ldg(q + 4);
+            const uint4 a = make_uint4(q0.x, q0.y, q1.x, q1.y);                  // pos.xyz, normal
+            const uint4 b = make_uint4(q2.x, q2.y, q3.x, q3.y);                  // pdf, ID, idx, bary; c = le.xyz (half), twoSided
+            ls.pos = f3(asfloat(a.x), asfloat(a.y), asfloat(a.z));
+            ls.normal = Math::DecodeOct32(a.w);
+            ls.bary = Math::DecodeUNorm2(b.w);
+            ls.le = f3(zr_f16_to_f32((uint16_t)(c.x & 0xffff)), zr_f16_to_f32((uint16_t)(c.x >> 16)), zr_f16_to_f32((uint16_t)(c.y & 0xffff)));
+            ls.pdf = asfloat(b.x); ls.ID = b.y; ls.idx = b.z;
+            ls.twoSided = (c.y >> 16) != 0;
+            if (ls.twoSided && dot(pos - ls.pos, ls.normal) < 0)
+                ls.normal = -ls.normal;
+            if (advanceRng)
+                rng.Uniform3D();
+        }
+        else
+        {
+            AliasTableSample entry = SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+            const zr_emissive_tri& tri = sc.emissives[entry.idx];
+            const EmissiveTriSample ts = SampleEmissiveTri(pos, tri, rng);
+            ls.pos = ts.pos; ls.normal = ts.normal; ls.bary = ts.bary;
+            ls.le = Le_EmissiveTriangle(tri);
+            ls.pdf = entry.pdf * ts.pdf; ls.idx = entry.idx; ls.ID = tri.ID; ls.twoSided = IsDoubleSided(tri);
+        }
+        return ls;
     }
 }
 } // namespace zr

@@ -42,6 +42,9 @@ struct SceneDev
     uint32_t numInstances;
     uint32_t numEmissives;
     uint32_t numTris;
+    // presampled emissive sets (PresampleEmissives.hlsl); sampleSetSize == 0: lights are sampled through the alias table
+    const zr_presampled_tri* sampleSets;
+    uint32_t numSampleSets, sampleSetSize;
 };
 
 struct RayHit { bool hit; float t; float2 bary; uint32_t tri; };
@@ -240,4 +243,6 @@ struct zr_scene
     float* d_power = nullptr;
     uint32_t* d_aliasScratch = nullptr;
     bool aliasBuilt = false;
+    zr_presampled_tri* d_sampleSets = nullptr;
+    bool samplesValid = false;      // zr_presample_emissives ran since the sets were (re)configured
 };

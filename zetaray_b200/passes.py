@@ -39,6 +39,23 @@ class Scene:
     def prelighting(self, stream=None):
         check(lib.zr_prelighting_render(self.handle, stream))
 
+    def set_presampling(self, num_sets, set_size):
+        """128 x 512 is what the reference enables at >= 13107 emissive triangles; 0, 0 = alias-table sampling."""
+        check(lib.zr_scene_set_presampling(self.handle, num_sets, set_size))
+
+    def presample(self, frame_num, stream=None):
+        """PresampleEmissives: once per frame, before DirectLighting / IndirectLighting."""
+        check(lib.zr_presample_emissives(self.handle, C.c_uint32(frame_num), stream))
+
+    def sample_sets(self):
+        p, n, m = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        check(lib.zr_scene_get_sample_sets(self.handle, C.byref(p), C.byref(n), C.byref(m)))
+        out = np.zeros(n.value * m.value * 10, dtype=np.uint32)
+        if out.size:
+            check(lib.zr_memcpy_d2h(_vp(out), p, C.c_size_t(out.nbytes), None))
+            check(lib.zr_stream_synchronize(None))
+        return out
+
     def alias_table(self):
         p = C.c_void_p()
         n = C.c_uint32()
