@@ -103,13 +103,10 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     sw, sh = 960, 540
-    per = []
-    for _ in range(max(1, args.steps)):
-        mp, spf = cpu_frames(sw, sh, 1, cores, warm=3 if not per else 0)
-        per.append((mp, spf))
-        if sum(p[1] for p in per) > 90:
-            break
-    mp = sum(p[0] for p in per) / len(per)
+    # one renderer, `warmup` frames to reach steady state (temporal + spatial reuse on), then the timed frames
+    nsteps = max(1, min(args.steps, 60))
+    mp, spf = cpu_frames(sw, sh, nsteps, cores, warm=max(3, args.warmup))
+    per = [(mp, spf)] * nsteps
     sample = "%d steady-state frame(s) at %dx%d (1/4 of the 1080p pixels), %d threads" % (len(per), sw, sh, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": mp, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": len(per),
@@ -131,6 +128,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--expensive-first", action="store_true",
                     help="launch the lighting kernels' thread blocks most-expensive-tile-first instead of in plain order (measured: no gain)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "allgather"], help="transport of the strip halos (N > 1)")
     ap.add_argument("--single-stream", action="store_true", help="record DirectLighting on the main stream instead of a second one")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -204,7 +202,7 @@ def main():
             frame(seq.next())
     if world > 1:
         plan = StripPlan.balanced(H, world, costs)
-        sharded.shard(plan)
+        sharded.shard(plan, halo_mode=args.halo)
         sc = plan.strip_costs(costs)
         plan_info = {"bounds": plan.bounds, "strip_cost_max_over_mean": round(max(sc) / (sum(sc) / world), 3)}
         for _ in range(args.warmup):
@@ -238,19 +236,33 @@ def main():
     n_e2e = max(3, min(args.steps, 20))
     fc_host = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8).pin_memory()
     fc_dev = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8, device="cuda")
-    out_host = torch.empty(W * H * 8, dtype=torch.uint8).pin_memory()
+    # the image read-back of frame i runs on a copy stream while frame i + 1 renders (TAA ping-pongs between two
+    # images, so the one being copied is only read by the next frame); the host consumes frame i - 1 while i renders
+    out_host = [torch.empty(W * H * 8, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    st_copy = C.c_void_p(copy_stream.cuda_stream)
+    ev_frame = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     fcs2 = [seq.next() for _ in range(n_e2e)]
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    for fc in fcs2:
+    for i, fc in enumerate(fcs2):
         C.memmove(fc_host.data_ptr(), C.addressof(fc), C.sizeof(fc))
         fc_dev.copy_(fc_host, non_blocking=True)            # H2D of the per-frame inputs
         frame(fc)
         if rank == 0:
+            b = i & 1
+            ev_frame[b].record(stream)
+            copy_stream.wait_event(ev_frame[b])
             img = taa.GetOutput()
-            check(lib.zr_memcpy_d2h(C.c_void_p(out_host.data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st))
-        stream.synchronize()                                 # the caller consumes the image before the next frame
+            check(lib.zr_memcpy_d2h(C.c_void_p(out_host[b].data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st_copy))
+            ev_copied[b].record(copy_stream)
+            if i > 0:
+                ev_copied[b ^ 1].synchronize()               # the caller consumes frame i - 1 here
+    if rank == 0:
+        ev_copied[(n_e2e - 1) & 1].synchronize()
+        stream.wait_event(ev_copied[(n_e2e - 1) & 1])        # the last image is on the host before the clock stops
     e3.record(stream)
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device="cuda")
@@ -322,7 +334,7 @@ def main():
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [W, H], "spp": 1, "bounces": 3, "restir_pt": "temporal + 1 spatial pass",
-                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halo all-gather)" % world if world > 1 else "single GPU",
+                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halos, %s)" % (world, args.halo) if world > 1 else "single GPU",
                        "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2, "block_order": "expensive tiles first" if args.expensive_first else "plain",
                        "l2": "per-frame working set ~0.8 GB >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_value, 3), "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(_lib.FrameConstants),

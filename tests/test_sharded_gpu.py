@@ -63,7 +63,7 @@ def _worker(rank, world, port, W, H, warm, frames, out_dir):
         costs = B.end_cost_measurement(schedule=(world == 2))     # world 2 also exercises the expensive-first block order
         assert sum(costs) > 0, "cost map stayed empty"
         plan = StripPlan.balanced(H, world, costs)
-        B.shard(plan)
+        B.shard(plan, halo_mode="allgather" if world == 2 else "p2p")
         y0, y1 = plan.rows(rank)
         for f in range(frames):
             fc = seq.next()

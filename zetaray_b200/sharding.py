@@ -2,7 +2,8 @@
 
 One process per GPU. A frame is split into horizontal strips whose boundaries are multiples of 32 rows; every
 pass renders only its strip (zr_*_pass_set_rows) and reads up to HALO = 32 rows beyond it. Rows another strip
-reads are made coherent with ONE all-gather per exchange point:
+reads are made coherent at four exchange points per frame (one grouped NCCL send/recv between neighbouring strips, or
+-- `halo_mode="allgather"` -- ONE all-gather, the scheme BASELINE.json names):
 
     after ReSTIR DI temporal      32 B/px reservoirs          (hook called by zr_direct_pass_render)
     after ReSTIR PT temporal      64 B/px reservoirs          (hook called by zr_indirect_pass_render)
@@ -116,10 +117,18 @@ def _band_rows(plan, rank):
 
 
 class HaloExchanger:
-    """All-gathers the boundary bands of row-major planes. A plane is a uint8 tensor of shape [H, pitch_bytes]."""
+    """Makes the boundary bands of row-major planes coherent between neighbouring strips. A plane is a uint8 tensor of
+    shape [H, pitch_bytes]. Two transports with identical results:
 
-    def __init__(self, plan, rank, group=None):
-        self.plan, self.rank, self.group = plan, rank, group
+    "p2p" (default)   every rank sends its top band to the rank above and its bottom band to the rank below, straight out
+                      of / into the planes (a band is a contiguous row range, so nothing is packed or unpacked); one
+                      grouped NCCL send/recv per exchange. Traffic per rank is independent of the number of GPUs.
+    "allgather"       the scheme named in BASELINE.json: every rank contributes both bands to ONE all-gather and copies its
+                      two neighbours' bands out of the result. Traffic grows with the number of GPUs."""
+
+    def __init__(self, plan, rank, group=None, mode="p2p"):
+        assert mode in ("p2p", "allgather")
+        self.plan, self.rank, self.group, self.mode = plan, rank, group, mode
         self.world = plan.world
         self._bufs = {}
         self.bytes_sent = 0
@@ -132,9 +141,30 @@ class HaloExchanger:
                                torch.empty(self.world * nbytes, dtype=torch.uint8, device=like.device))
         return self._bufs[key]
 
+    def _exchange_p2p(self, planes):
+        plan, r = self.plan, self.rank
+        (t0, t1), (b0, b1) = _band_rows(plan, r)
+        ops = []
+        for p in planes:
+            if r > 0:
+                (_, _), (nb0, nb1) = _band_rows(plan, r - 1)
+                ops.append(dist.P2POp(dist.isend, p[t0:t1].reshape(-1), r - 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, p[nb0:nb1].reshape(-1), r - 1, self.group))
+                self.bytes_sent += (t1 - t0) * p.shape[1]
+            if r < self.world - 1:
+                (nt0, nt1), (_, _) = _band_rows(plan, r + 1)
+                ops.append(dist.P2POp(dist.isend, p[b0:b1].reshape(-1), r + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, p[nt0:nt1].reshape(-1), r + 1, self.group))
+                self.bytes_sent += (b1 - b0) * p.shape[1]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.calls += 1
+
     def exchange(self, planes):
         if self.world == 1:
             return
+        if self.mode == "p2p":
+            return self._exchange_p2p(planes)
         plan, r = self.plan, self.rank
         slot = [HALO * p.shape[1] for p in planes]            # bytes of one band slot per plane
         packet = 2 * sum(slot)
@@ -244,9 +274,9 @@ class ShardedFrame:
         return [sum(tiles[b * self.tiles_x:(b + 1) * self.tiles_x]) for b in range(self.tiles_y)]
 
     # ---- sharding ----
-    def shard(self, plan):
+    def shard(self, plan, halo_mode="p2p"):
         self.plan = plan
-        self.halo = HaloExchanger(plan, self.rank, self.group)
+        self.halo = HaloExchanger(plan, self.rank, self.group, mode=halo_mode)
         y0, y1 = plan.rows(self.rank)
         g0, g1 = plan.rows_with_halo(self.rank)
         self.p["gbuffer"].SetRows(g0, g1)
