@@ -180,9 +180,20 @@ def main():
     st_side = st if side is None else C.c_void_p(side.cuda_stream)
     ev_g, ev_d = torch.cuda.Event(), torch.cuda.Event()
 
+    # N == 1: the native frame driver (zr_renderer, csrc/renderer.cu) -- one C-ABI call per frame, second stream inside.
+    # N > 1: the strip-sharded frame (zetaray_b200/sharding.py) over the same passes.
+    from zetaray_b200.passes import Renderer
+    renderer = Renderer(scene, W, H, two_streams=not args.single_stream) if world == 1 else None
+
     def frame(fc):
+        if renderer is not None:
+            renderer.Render(fc, st)
+            return
         sharded.render(fi, fc, stream, st, side, st_side, ev_g, ev_d)
         sharded.gather_output(stream)
+
+    def output_image():
+        return renderer.GetOutput() if renderer is not None else taa.GetOutput()
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,14 +204,12 @@ def main():
     # ---- warm-up: unsharded frames bring temporal + spatial reuse to steady state (frame >= 3) and measure the cost
     # of every 32-row band; then the strips are cut and the same number of sharded warm-up frames follows ----
     plan_info = None
-    sharded.begin_cost_measurement()
+    if world > 1:
+        sharded.begin_cost_measurement()
     for _ in range(args.warmup):
         frame(seq.next())
-    costs = sharded.end_cost_measurement(schedule=args.expensive_first)
-    if world == 1:
-        for _ in range(args.warmup):
-            frame(seq.next())
     if world > 1:
+        costs = sharded.end_cost_measurement(schedule=args.expensive_first)
         plan = StripPlan.balanced(H, world, costs)
         sharded.shard(plan, halo_mode=args.halo)
         sc = plan.strip_costs(costs)
@@ -255,7 +264,7 @@ def main():
             b = i & 1
             ev_frame[b].record(stream)
             copy_stream.wait_event(ev_frame[b])
-            img = taa.GetOutput()
+            img = output_image()
             check(lib.zr_memcpy_d2h(C.c_void_p(out_host[b].data_ptr()), C.c_void_p(img.d_ptr), C.c_size_t(W * H * 8), st_copy))
             ev_copied[b].record(copy_stream)
             if i > 0:
@@ -274,6 +283,9 @@ def main():
     # ---- per-kernel timing (CUDA events on the launching stream around every launch) ----
     kern = {}
     nprof = 5
+    if renderer is not None:        # the stand-alone passes have not rendered yet: bring them to steady state first
+        for _ in range(3):
+            sharded.render(fi, seq.next(), stream)
     check(lib.zr_profile_enable(1))
     for _ in range(nprof):          # every rank renders (the frame holds collectives) and times its own launches;
         sharded.render(fi, seq.next(), stream)      # single stream here, so a kernel's events do not include waiting for the other stream

@@ -501,6 +501,21 @@ ZR_API zr_status zr_profile_collect(char* buf, size_t buf_size);
 /* number of kernels this library launched since load (for bench.py's gpu_launches) */
 ZR_API uint64_t zr_kernel_launch_count(void);
 
+/* ---- The frame (ZetaRenderer/Default: DefaultRenderer.cpp:304-520, PathTracer.cpp:149-563) ----
+ * Owns the double-buffered G-buffers and one object of every pass and runs a frame in the reference's order:
+ * (frame 1: emissive power + alias table) -> presampling if enabled -> GBufferRT -> DirectLighting || IndirectLighting
+ * -> Compositing + firefly filter -> TAA. DirectLighting is recorded on an internal second stream when two_streams != 0
+ * (the two lighting passes are independent render-graph nodes in the reference). Parameters are set on the pass handles. */
+typedef struct zr_renderer zr_renderer;
+typedef struct zr_renderer_desc { uint32_t width, height; int with_tridiff; int two_streams; } zr_renderer_desc;
+ZR_API zr_status zr_renderer_create(const zr_renderer_desc* desc, zr_scene* scene, zr_renderer** out);
+ZR_API zr_status zr_renderer_render(zr_renderer* r, const zr_frame_constants* frame, void* stream);
+ZR_API zr_status zr_renderer_get_output(zr_renderer* r, zr_image2d* out);      /* TAA output, RGBA16F */
+ZR_API zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** gbuffer, zr_direct_pass** direct,
+    zr_indirect_pass** indirect, zr_compositing_pass** compositing, zr_taa_pass** taa);
+ZR_API zr_status zr_renderer_get_gbuffer(zr_renderer* r, int previous, zr_gbuffer* out);
+ZR_API void zr_renderer_destroy(zr_renderer* r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,10 @@ lib.zr_last_error.restype = C.c_char_p
 lib.zr_abi_version.restype = u32
 lib.zr_kernel_launch_count.restype = u64
 
+class RendererDesc(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("with_tridiff", C.c_int), ("two_streams", C.c_int)]
+
+
 # zr_halo_exchange_fn (include/zr_abi.h "Strip-sharded frames")
 HALO_EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Image2D), C.c_int, C.c_void_p)
 

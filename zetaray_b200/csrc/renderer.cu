@@ -1,0 +1,167 @@
+// renderer.cu -- the frame: which passes run, in which order, on which stream (host code only, no kernels).
+//
+// Headless counterpart of ZetaRenderer/Default: DefaultRenderer::Update/Render (DefaultRenderer.cpp:304-520) decide what
+// a frame contains, PathTracer::Register/AddAdjacencies (PathTracer.cpp:149-563) and the GBuffer / PostProcessor
+// equivalents put the passes into the render graph, and the graph runs them in dependency order with DirectLighting and
+// IndirectLighting as independent compute nodes (both read only the G-buffer). Here that schedule is fixed:
+//
+//   frame 1 only      zr_prelighting_render        power estimate + alias table (on device, so no one-frame read-back delay)
+//   every frame       zr_presample_emissives       when presampling is on (the reference: >= 13107 emissive triangles)
+//                     GBufferRT
+//                     DirectLighting  ||  IndirectLighting      second stream, joined before Compositing
+//                     Compositing (+ firefly filter) -> TAA
+//
+// The renderer owns the double-buffered G-buffers (DefaultRendererImpl.h:111-121) and the pass objects; callers reach
+// the passes through zr_renderer_get_*_pass to set parameters, exactly like the reference's UI callbacks do.
+#include <cuda_runtime.h>
+#include "../../include/zr_abi.h"
+#include "zr_common.cuh"
+
+struct zr_renderer
+{
+    uint32_t width = 0, height = 0;
+    zr_scene* scene = nullptr;              // not owned
+    zr_gbuffer gbuffer[2]{};
+    int curr = 0;
+    uint64_t framesRendered = 0;
+    zr_gbuffer_pass* gbufferPass = nullptr;
+    zr_direct_pass* direct = nullptr;
+    zr_indirect_pass* indirect = nullptr;
+    zr_compositing_pass* compositing = nullptr;
+    zr_taa_pass* taa = nullptr;
+    cudaStream_t side = nullptr;            // DirectLighting runs here when twoStreams
+    cudaEvent_t evGBuffer = nullptr, evDirect = nullptr;
+    bool twoStreams = true;
+
+    void Release()
+    {
+        if (gbufferPass) zr_gbuffer_pass_destroy(gbufferPass);
+        if (direct) zr_direct_pass_destroy(direct);
+        if (indirect) zr_indirect_pass_destroy(indirect);
+        if (compositing) zr_compositing_pass_destroy(compositing);
+        if (taa) zr_taa_pass_destroy(taa);
+        gbufferPass = nullptr; direct = nullptr; indirect = nullptr; compositing = nullptr; taa = nullptr;
+        for (int i = 0; i < 2; i++) zr_gbuffer_free(&gbuffer[i]);
+        if (side) cudaStreamDestroy(side);
+        if (evGBuffer) cudaEventDestroy(evGBuffer);
+        if (evDirect) cudaEventDestroy(evDirect);
+        side = nullptr; evGBuffer = evDirect = nullptr;
+    }
+};
+
+extern "C"
+{
+    zr_status zr_renderer_create(const zr_renderer_desc* desc, zr_scene* scene, zr_renderer** out)
+    {
+        if (!desc || !scene || !out || !desc->width || !desc->height)
+        {
+            zr::set_error("zr_renderer_create: bad args");
+            return ZR_ERR_INVALID_ARG;
+        }
+        zr_renderer* r = new zr_renderer();
+        r->width = desc->width; r->height = desc->height; r->scene = scene; r->twoStreams = desc->two_streams != 0;
+        zr_status s = ZR_OK;
+        for (int i = 0; i < 2 && s == ZR_OK; i++) s = zr_gbuffer_alloc(desc->width, desc->height, desc->with_tridiff, &r->gbuffer[i]);
+        if (s == ZR_OK) s = zr_gbuffer_pass_create(&r->gbufferPass);
+        if (s == ZR_OK) s = zr_direct_pass_create(desc->width, desc->height, &r->direct);
+        if (s == ZR_OK) s = zr_indirect_pass_create(desc->width, desc->height, &r->indirect);
+        if (s == ZR_OK) s = zr_compositing_pass_create(desc->width, desc->height, &r->compositing);
+        if (s == ZR_OK) s = zr_taa_pass_create(desc->width, desc->height, &r->taa);
+        if (s == ZR_OK && cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking) != cudaSuccess) s = ZR_ERR_CUDA;
+        if (s == ZR_OK && cudaEventCreateWithFlags(&r->evGBuffer, cudaEventDisableTiming) != cudaSuccess) s = ZR_ERR_CUDA;
+        if (s == ZR_OK && cudaEventCreateWithFlags(&r->evDirect, cudaEventDisableTiming) != cudaSuccess) s = ZR_ERR_CUDA;
+        if (s != ZR_OK) { r->Release(); delete r; return s; }
+        *out = r;
+        return ZR_OK;
+    }
+
+    void zr_renderer_destroy(zr_renderer* r)
+    {
+        if (!r) return;
+        r->Release();
+        delete r;
+    }
+
+    // One frame == DefaultRenderer::Update + Render for the emissive-lit path-tracing configuration.
+    zr_status zr_renderer_render(zr_renderer* r, const zr_frame_constants* fc, void* stream_)
+    {
+        if (!r || !fc) return ZR_ERR_INVALID_ARG;
+        if (fc->RenderWidth != r->width || fc->RenderHeight != r->height)
+        {
+            zr::set_error("zr_renderer_render: frame is %ux%u but the renderer was sized %ux%u", fc->RenderWidth, fc->RenderHeight,
+                r->width, r->height);
+            return ZR_ERR_INVALID_ARG;
+        }
+        cudaStream_t stream = (cudaStream_t)stream_;
+        zr_status s;
+        if (r->framesRendered == 0)
+        {
+            s = zr_prelighting_render(r->scene, stream);
+            if (s != ZR_OK) return s;
+        }
+        s = zr_presample_emissives(r->scene, fc->FrameNum, stream);
+        if (s != ZR_OK) return s;
+
+        r->curr ^= 1;       // GlobalIdxForDoubleBufferedResources
+        zr_frame_inputs in;
+        in.frame = *fc;
+        in.curr = r->gbuffer[r->curr];
+        in.prev = r->gbuffer[r->curr ^ 1];
+        in.scene = r->scene;
+
+        s = zr_gbuffer_pass_render(r->gbufferPass, &in, stream);
+        if (s != ZR_OK) return s;
+        cudaStream_t directStream = stream;
+        if (r->twoStreams)
+        {
+            ZR_CUDA(cudaEventRecord(r->evGBuffer, stream));
+            ZR_CUDA(cudaStreamWaitEvent(r->side, r->evGBuffer, 0));
+            directStream = r->side;
+        }
+        s = zr_direct_pass_render(r->direct, &in, directStream);
+        if (s != ZR_OK) return s;
+        s = zr_indirect_pass_render(r->indirect, &in, stream);
+        if (s != ZR_OK) return s;
+        if (r->twoStreams)
+        {
+            ZR_CUDA(cudaEventRecord(r->evDirect, r->side));
+            ZR_CUDA(cudaStreamWaitEvent(stream, r->evDirect, 0));
+        }
+        zr_image2d di, ind, comp;
+        s = zr_direct_pass_get_output(r->direct, ZR_DIRECT_FINAL, &di);
+        if (s != ZR_OK) return s;
+        s = zr_indirect_pass_get_output(r->indirect, ZR_INDIRECT_FINAL, &ind);
+        if (s != ZR_OK) return s;
+        s = zr_compositing_pass_render(r->compositing, &in, di.d_ptr, ind.d_ptr, stream);
+        if (s != ZR_OK) return s;
+        s = zr_compositing_pass_get_output(r->compositing, &comp);
+        if (s != ZR_OK) return s;
+        s = zr_taa_pass_render(r->taa, &in, comp.d_ptr, stream);
+        if (s != ZR_OK) return s;
+        r->framesRendered++;
+        return ZR_OK;
+    }
+
+    zr_status zr_renderer_get_output(zr_renderer* r, zr_image2d* out)
+    {
+        if (!r || !out) return ZR_ERR_INVALID_ARG;
+        return zr_taa_pass_get_output(r->taa, out);
+    }
+    zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** g, zr_direct_pass** d, zr_indirect_pass** i,
+        zr_compositing_pass** c, zr_taa_pass** t)
+    {
+        if (!r) return ZR_ERR_INVALID_ARG;
+        if (g) *g = r->gbufferPass;
+        if (d) *d = r->direct;
+        if (i) *i = r->indirect;
+        if (c) *c = r->compositing;
+        if (t) *t = r->taa;
+        return ZR_OK;
+    }
+    zr_status zr_renderer_get_gbuffer(zr_renderer* r, int previous, zr_gbuffer* out)
+    {
+        if (!r || !out) return ZR_ERR_INVALID_ARG;
+        *out = r->gbuffer[previous ? r->curr ^ 1 : r->curr];
+        return ZR_OK;
+    }
+}

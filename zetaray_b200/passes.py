@@ -281,3 +281,50 @@ class TAA(_Pass):
         img = _lib.Image2D()
         check(lib.zr_taa_pass_get_output(self.handle, C.byref(img)))
         return img
+
+
+class _Borrowed:
+    """A pass handle owned by a Renderer: same verbs as the owning classes, never destroyed from here."""
+
+    def __init__(self, cls, handle):
+        self.__class__ = type("Borrowed" + cls.__name__, (cls,), {"__del__": lambda self: None})
+        self.handle = handle
+        if cls is DirectLighting:
+            self.params = _lib.DirectParams()
+            check(lib.zr_direct_pass_default_params(C.byref(self.params)))
+        if cls is IndirectLighting:
+            self.params = _lib.IndirectParams()
+            check(lib.zr_indirect_pass_default_params(C.byref(self.params)))
+
+
+class Renderer:
+    """The frame driver (zr_renderer, csrc/renderer.cu): G-buffers + all passes, one Render(frame constants) per frame."""
+
+    def __init__(self, scene, w, h, two_streams=True, with_tridiff=False):
+        self.scene = scene
+        self.handle = C.c_void_p()
+        desc = _lib.RendererDesc(w, h, int(with_tridiff), int(two_streams))
+        check(lib.zr_renderer_create(C.byref(desc), scene.handle, C.byref(self.handle)))
+        hs = [C.c_void_p() for _ in range(5)]
+        check(lib.zr_renderer_get_passes(self.handle, *[C.byref(x) for x in hs]))
+        self.gbuffer, self.direct, self.indirect, self.compositing, self.taa = (
+            _Borrowed(cls, hnd) for cls, hnd in zip((GBufferRT, DirectLighting, IndirectLighting, Compositing, TAA), hs))
+
+    def Render(self, fc, stream=None):
+        check(lib.zr_renderer_render(self.handle, C.byref(fc), stream))
+
+    def GetOutput(self):
+        img = _lib.Image2D()
+        check(lib.zr_renderer_get_output(self.handle, C.byref(img)))
+        return img
+
+    def close(self):
+        if self.handle:
+            lib.zr_renderer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
