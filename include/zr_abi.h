@@ -459,6 +459,39 @@ ZR_API zr_status zr_indirect_pass_set_cost_map(zr_indirect_pass* p, void* d_cycl
 ZR_API zr_status zr_indirect_pass_set_schedule_costs(zr_indirect_pass* p, const double* h_tile_cost, uint32_t tiles_x, uint32_t tiles_y);
 ZR_API void zr_indirect_pass_destroy(zr_indirect_pass* p);
 
+/* ---- IndirectLighting, INTEGRATOR::ReSTIR_GI (IndirectLighting.cpp:277-368; ReSTIR_GI shaders) ----
+ * One kernel per frame: a path-traced initial candidate (second path vertex + outgoing radiance), temporal reuse with one
+ * or two reprojected candidates and the reconnection Jacobian, wave-level outlier suppression. Emissive NEE only
+ * (alias table or presampled sets); the sun/sky and light-voxel-grid variants are not part of this build. */
+typedef struct zr_rgi_reservoir        /* RGI_Util::Reservoir planes A/B/C (ReSTIR_GI/Reservoir.hlsli:88-131) in one 48-byte record */
+{
+    float pos[3]; uint32_t ID;          /* A: RGBA32F {pos, asfloat(ID)} */
+    uint32_t Lo_rg, Lo_b_M;             /* B: RGBA16F {Lo, M} */
+    float w_sum, W;                     /* C.xy */
+    uint32_t normal;                    /* C.z: octahedral 2 x UNORM16 */
+    uint32_t pad[3];
+} zr_rgi_reservoir;
+typedef struct zr_gi_params            /* cb_ReSTIR_GI fields the UI drives (IndirectLighting_Common.h:79-102, IndirectLighting.h:231-244) */
+{
+    uint32_t max_non_tr_bounces;        /* 3 */
+    uint32_t max_glossy_tr_bounces;     /* 4 */
+    uint32_t russian_roulette;          /* 1 */
+    uint32_t stochastic_multi_bounce;   /* 1 */
+    uint32_t boiling_suppression;       /* 1 */
+    uint32_t M_max;                     /* 10 */
+    uint32_t temporal_resample;         /* 1 */
+} zr_gi_params;
+typedef struct zr_gi_pass zr_gi_pass;
+typedef enum zr_gi_output { ZR_GI_FINAL = 0, ZR_GI_RESERVOIR_CURR = 1, ZR_GI_RESERVOIR_PREV = 2 } zr_gi_output;
+ZR_API zr_status zr_gi_pass_create(uint32_t width, uint32_t height, zr_gi_pass** out);
+ZR_API zr_status zr_gi_pass_resize(zr_gi_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_gi_pass_reset_temporal(zr_gi_pass* p);
+ZR_API zr_status zr_gi_pass_default_params(zr_gi_params* out);
+ZR_API zr_status zr_gi_pass_set_params(zr_gi_pass* p, const zr_gi_params* params);
+ZR_API zr_status zr_gi_pass_render(zr_gi_pass* p, const zr_frame_inputs* in, void* stream);
+ZR_API zr_status zr_gi_pass_get_output(zr_gi_pass* p, zr_gi_output id, zr_image2d* out);
+ZR_API void zr_gi_pass_destroy(zr_gi_pass* p);
+
 /* ---- Compositing + FireflyFilter (Compositing/Compositing.cpp:83-145) ---- */
 typedef struct zr_compositing_pass zr_compositing_pass;
 typedef struct zr_compositing_params { uint32_t emissive_di; uint32_t indirect; uint32_t firefly_filter; } zr_compositing_params;

@@ -42,6 +42,19 @@ def default_rdi_params():
     return RdiParams(1, 1, 1, 1, 20, np.float32(0.05) * np.float32(0.05))
 
 
+RGI = np.dtype([("pos", "<f4", 3), ("ID", "<u4"), ("Lo_rg", "<u4"), ("Lo_b_M", "<u4"), ("w_sum", "<f4"), ("W", "<f4"),
+                ("normal", "<u4"), ("pad", "<u4", 3)])
+assert RGI.itemsize == 48
+GI_PARAM_NAMES = ("max_non_tr_bounces", "max_glossy_tr_bounces", "russian_roulette", "stochastic_multi_bounce", "boiling_suppression",
+                  "M_max", "temporal_resample")
+
+
+def default_gi_params():
+    # IndirectLighting.h:231-244
+    return dict(max_non_tr_bounces=3, max_glossy_tr_bounces=4, russian_roulette=1, stochastic_multi_bounce=1, boiling_suppression=1,
+                M_max=10, temporal_resample=1)
+
+
 class RptBuffers(C.Structure):
     _fields_ = [("res0", C.c_void_p), ("res1", C.c_void_p), ("target", C.c_void_p), ("final", C.c_void_p),
                 ("neighbor", C.c_void_p), ("tmCtN", C.c_void_p), ("tmNtC", C.c_void_p)]
@@ -118,6 +131,10 @@ class OracleRenderer:
         self.di_final = np.zeros((n, 4), dtype=np.float32)
         self.di_state = np.array([0, 0, 1], dtype=np.uint32)
         self.di_params = default_rdi_params()
+        self.gi_params = default_gi_params()
+        self.gi_res = [np.zeros(n, dtype=RGI), np.zeros(n, dtype=RGI)]
+        self.gi_final = np.zeros((n, 4), dtype=np.float32)
+        self.gi_state = np.array([0, 0, 1], dtype=np.uint32)
         empty = (np.zeros((n, 4), np.uint32), np.zeros(n, np.float32), np.zeros((n, 2), np.uint32), np.zeros((n, 2), np.uint32), None)
         self.gb = [empty, empty]
 
@@ -139,6 +156,16 @@ class OracleRenderer:
         self.o.orc_rdi_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]), C.byref(self.di_params),
                               ptr(self.di_res[0]), ptr(self.di_res[1]), ptr(self.di_target), ptr(self.di_final), ptr(self.di_state),
                               self.nthreads)
+
+    def rgi(self, fc):
+        """IndirectLighting with INTEGRATOR::ReSTIR_GI"""
+        c = self.gb[self.cur]; p = self.gb[self.cur ^ 1]
+        prm = np.array([self.gi_params[k] for k in GI_PARAM_NAMES], dtype=np.uint32)
+        self.o.orc_rgi_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]), ptr(prm),
+                              ptr(self.gi_res[0]), ptr(self.gi_res[1]), ptr(self.gi_final), ptr(self.gi_state), self.nthreads)
+
+    def gi_curr_reservoirs(self):
+        return self.gi_res[1 - int(self.gi_state[0])]
 
     def di_curr_reservoirs(self):
         return self.di_res[1 - int(self.di_state[0])]

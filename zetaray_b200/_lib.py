@@ -93,6 +93,11 @@ lib.zr_last_error.restype = C.c_char_p
 lib.zr_abi_version.restype = u32
 lib.zr_kernel_launch_count.restype = u64
 
+class GIParams(C.Structure):
+    _fields_ = [("max_non_tr_bounces", u32), ("max_glossy_tr_bounces", u32), ("russian_roulette", u32), ("stochastic_multi_bounce", u32),
+                ("boiling_suppression", u32), ("M_max", u32), ("temporal_resample", u32)]
+
+
 class RendererDesc(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("with_tridiff", C.c_int), ("two_streams", C.c_int)]
 

@@ -241,6 +241,36 @@ class IndirectLighting(_Pass):
         return img
 
 
+class IndirectLightingGI(_Pass):
+    """IndirectLighting with INTEGRATOR::ReSTIR_GI (zr_gi_pass, csrc/rgi.cu)."""
+    prefix = "zr_gi_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_gi_pass_create(w, h, C.byref(self.handle)))
+        self.params = _lib.GIParams()
+        check(lib.zr_gi_pass_default_params(C.byref(self.params)))
+
+    def SetParams(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        check(lib.zr_gi_pass_set_params(self.handle, C.byref(self.params)))
+
+    def OnWindowResized(self, w, h):
+        check(lib.zr_gi_pass_resize(self.handle, w, h))
+
+    def ResetTemporal(self):
+        check(lib.zr_gi_pass_reset_temporal(self.handle))
+
+    def Render(self, fi, stream=None):
+        check(lib.zr_gi_pass_render(self.handle, C.byref(fi), stream))
+
+    def GetOutput(self, which=0):
+        img = _lib.Image2D()
+        check(lib.zr_gi_pass_get_output(self.handle, which, C.byref(img)))
+        return img
+
+
 class Compositing(_Pass):
     prefix = "zr_compositing_pass"
 
