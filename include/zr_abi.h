@@ -354,6 +354,26 @@ typedef struct zr_presampled_tri       /* RT::PresampledEmissiveTriangle, ZetaCo
 ZR_API zr_status zr_scene_set_presampling(zr_scene* scene, uint32_t num_sets, uint32_t set_size);  /* 0, 0 = off (default) */
 ZR_API zr_status zr_presample_emissives(zr_scene* scene, uint32_t frame_num, void* stream);       /* once per frame, before lighting */
 ZR_API zr_status zr_scene_get_sample_sets(zr_scene* scene, void** d_sets, uint32_t* num_sets, uint32_t* set_size);
+
+/* ---- Light voxel grid (PreLighting/BuildLightVoxelGrid.hlsl:56-162, Common/LightVoxelGrid.hlsli; SURVEY a-6) ----
+ * A camera-centred grid of grid_dim voxels (half-extents `extents`, view space, y shifted by offset_y); every frame each
+ * voxel keeps 64 light samples chosen by RIS over 6 alias-table candidates with target Lum(Le) / d^2. ReSTIR GI then
+ * takes its NEE light sample after the first indirect vertex from the voxel around the shading point (ReSTIR_GI_LVG
+ * variant, ReSTIR_GI_NEE.hlsli:123-193) and falls back to the presampled set outside the grid, so it needs presampling
+ * on (DefaultRenderer.cpp:363). The reference's defaults are 32 x 8 x 40 voxels of (0.6, 0.45, 0.6). */
+typedef struct zr_voxel_sample         /* RT::VoxelSample, ZetaCore/RayTracing/RtCommon.h:324-332 (32 bytes) */
+{
+    float pos[3];
+    uint32_t normal;        /* octahedral, 2 x UNORM16 */
+    float pdf;
+    uint32_t ID;
+    uint16_t le[3];         /* half3 */
+    uint16_t twoSided;
+} zr_voxel_sample;
+#define ZR_LVG_SAMPLES_PER_VOXEL 64u
+ZR_API zr_status zr_scene_set_light_voxel_grid(zr_scene* scene, const uint32_t grid_dim[3], const float extents[3], float offset_y);
+ZR_API zr_status zr_build_light_voxel_grid(zr_scene* scene, const zr_frame_constants* frame, void* stream);   /* once per frame */
+ZR_API zr_status zr_scene_get_light_voxel_grid(zr_scene* scene, void** d_samples, uint32_t* num_samples);
 ZR_API zr_status zr_scene_get_alias_table(const zr_scene* scene, const zr_alias_entry** d_table, uint32_t* n);
 
 /* ------------------------------------------------------------------------------------------
@@ -462,7 +482,8 @@ ZR_API void zr_indirect_pass_destroy(zr_indirect_pass* p);
 /* ---- IndirectLighting, INTEGRATOR::ReSTIR_GI (IndirectLighting.cpp:277-368; ReSTIR_GI shaders) ----
  * One kernel per frame: a path-traced initial candidate (second path vertex + outgoing radiance), temporal reuse with one
  * or two reprojected candidates and the reconnection Jacobian, wave-level outlier suppression. Emissive NEE only
- * (alias table or presampled sets); the sun/sky and light-voxel-grid variants are not part of this build. */
+ * (alias table, presampled sets, or the light voxel grid when it is enabled on the scene); the sun/sky variant is not
+ * part of this build. */
 typedef struct zr_rgi_reservoir        /* RGI_Util::Reservoir planes A/B/C (ReSTIR_GI/Reservoir.hlsli:88-131) in one 48-byte record */
 {
     float pos[3]; uint32_t ID;          /* A: RGBA32F {pos, asfloat(ID)} */

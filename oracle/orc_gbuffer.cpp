@@ -280,6 +280,100 @@ extern "C"
         Scene& sc = *(Scene*)scene_;
         sc.sampleSets = sets; sc.numSampleSets = numSets; sc.sampleSetSize = setSize;
     }
+    void orc_scene_set_lvg(void* scene_, const zr_voxel_sample* lvg, const uint32_t dim[3], const float extents[3], float offset_y)
+    {
+        Scene& sc = *(Scene*)scene_;
+        sc.lvg = lvg;
+        for (int i = 0; i < 3; i++) { sc.lvgDim[i] = lvg ? dim[i] : 0; sc.lvgExtents[i] = lvg ? extents[i] : 0; }
+        sc.lvgOffsetY = offset_y;
+    }
+    // BuildLightVoxelGrid.hlsl:56-162: one group of 64 threads per voxel; the two wave sums of a group add up in any order
+    // (zeros elsewhere), each 32-lane wave sum in the xor-butterfly order
+    void orc_build_lvg(void* scene_, const zr_frame_constants* fc, zr_voxel_sample* out)
+    {
+        const Scene& sc = *(Scene*)scene_;
+        const uint32_t dx = sc.lvgDim[0], dy = sc.lvgDim[1], dz = sc.lvgDim[2];
+        const float3 extents = f3(sc.lvgExtents[0], sc.lvgExtents[1], sc.lvgExtents[2]);
+        for (uint32_t gz = 0; gz < dz; gz++) for (uint32_t gy = 0; gy < dy; gy++) for (uint32_t gx = 0; gx < dx; gx++)
+        {
+            const uint32_t gridStart = LVG::FlattenVoxelIndex(gx, gy, gz, dx, dy);
+            const float3 voxelCenter = LVG::VoxelCenter((int)gx, (int)gy, (int)gz, (int)dx, (int)dy, (int)dz, extents, fc->CurrViewInv, sc.lvgOffsetY);
+            float3 corners[8];
+            for (int i = 0; i < 8; i++)
+                corners[i] = voxelCenter + f3((i & 4) ? 1.0f : -1.0f, (i & 2) ? 1.0f : -1.0f, (i & 1) ? 1.0f : -1.0f) * extents;
+            float w_sum[64], target_z[64]; uint32_t numLights[64];
+            zr_voxel_sample r[64];
+            for (uint32_t Gidx = 0; Gidx < 64; Gidx++)
+            {
+                RNG rng = RNG::InitIdx(gridStart * 64 + Gidx, fc->FrameNum);
+                zr_voxel_sample& s = r[Gidx];
+                s.pos[0] = s.pos[1] = s.pos[2] = FLT_MAX_; s.normal = 0; s.le[0] = s.le[1] = s.le[2] = 0; s.pdf = 0; s.twoSided = 0; s.ID = 0xffffffffu;
+                w_sum[Gidx] = 0; target_z[Gidx] = 0; numLights[Gidx] = 0;
+                for (int i = 0; i < 6; i++)
+                {
+                    Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+                    const zr_emissive_tri& tri = sc.emissives[entry.idx];
+                    Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(voxelCenter, tri, rng, false);
+                    const float3 le = Light::Le_EmissiveTriangle(tri);
+                    // AdjustLightPos: snap lights inside the voxel to its boundary planes
+                    const float3 d = f3(fabsf(lightSample.pos.x - voxelCenter.x), fabsf(lightSample.pos.y - voxelCenter.y), fabsf(lightSample.pos.z - voxelCenter.z));
+                    const bool inside = d.x <= extents.x && d.y <= extents.y && d.z <= extents.z;
+                    float3 lightPos = lightSample.pos;
+                    if (inside)
+                    {
+                        const int maxIdx = d.x >= d.y ? (d.x >= d.z ? 0 : 2) : (d.y >= d.z ? 1 : 2);
+                        if (maxIdx == 0) lightPos.x = extents.x; else if (maxIdx == 1) lightPos.y = extents.y; else lightPos.z = extents.z;
+                    }
+                    if (!inside && !Light::IsDoubleSided(tri))
+                    {
+                        bool backfacing = false;
+                        for (int c = 0; c < 8; c++)
+                            if (dot(corners[c] - lightSample.pos, lightSample.normal) <= 0) { backfacing = true; break; }
+                        if (backfacing)
+                            continue;
+                    }
+                    const float t = length(lightPos - voxelCenter);
+                    const float target = Math::Luminance(le) / fmaxf(t * t, 1e-6f);
+                    const float lightPdf = entry.pdf * lightSample.pdf;
+                    const float w = target / fmaxf(lightPdf, 1e-6f);
+                    w_sum[Gidx] += w;
+                    if (rng.Uniform() < w / fmaxf(w_sum[Gidx], 1e-6f))
+                    {
+                        s.pos[0] = lightSample.pos.x; s.pos[1] = lightSample.pos.y; s.pos[2] = lightSample.pos.z;
+                        s.normal = Math::EncodeOct32u(lightSample.normal);
+                        s.le[0] = zr_f32_to_f16(le.x); s.le[1] = zr_f32_to_f16(le.y); s.le[2] = zr_f32_to_f16(le.z);
+                        s.twoSided = Light::IsDoubleSided(tri) ? 1 : 0;
+                        s.ID = tri.ID;
+                        target_z[Gidx] = target;
+                    }
+                    numLights[Gidx]++;
+                }
+            }
+            float waveSum[2]; uint32_t waveLights[2];
+            for (int wv = 0; wv < 2; wv++)
+            {
+                float a[32];
+                for (int i = 0; i < 32; i++) a[i] = w_sum[wv * 32 + i];
+                for (int off = 16; off >= 1; off >>= 1)
+                {
+                    float b[32];
+                    for (int i = 0; i < 32; i++) b[i] = a[i] + a[i ^ off];
+                    for (int i = 0; i < 32; i++) a[i] = b[i];
+                }
+                waveSum[wv] = a[0];
+                waveLights[wv] = 0;
+                for (int i = 0; i < 32; i++) waveLights[wv] += numLights[wv * 32 + i];
+            }
+            float w_sum_group = waveSum[0] + waveSum[1];
+            const uint32_t numLightsGroup = (waveLights[0] + waveLights[1]) & 0xffffu;
+            w_sum_group /= (float)numLightsGroup;
+            for (uint32_t Gidx = 0; Gidx < 64; Gidx++)
+            {
+                r[Gidx].pdf = target_z[Gidx] / fmaxf(w_sum_group, 1e-6f);
+                out[gridStart * 64 + Gidx] = r[Gidx];
+            }
+        }
+    }
     // EstimateTriEmissivePower.hlsl:30-79 without emissive textures
     void orc_estimate_power(void* scene_, float* power)
     {

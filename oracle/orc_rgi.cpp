@@ -12,8 +12,8 @@
 //   IndirectLighting/NEE.hlsli                       NEE_Emissive<1> :152-221
 //   IndirectLighting/ReSTIR_GI/Reservoir.hlsli       Reservoir, read/write :9-131
 //   host: IndirectLighting.cpp RenderReSTIR_GI :277-368 (ping-pong, flags)
-// Not restated: ray differentials (only feed texture LOD; no textures in this build), the sun/sky variant, the light
-// voxel grid variant (ReSTIR_GI_LVG), the disabled spatial pass (Resampling.hlsli:603-608 is commented out upstream).
+// Not restated: ray differentials (only feed texture LOD; no textures in this build), the sun/sky variant, the disabled
+// spatial pass (Resampling.hlsli:603-608 is commented out upstream).
 // Wave-scope ops: the Russian-roulette WaveActiveMax inside the bounce loop is evaluated over the lanes of a wave that
 // are at the same iteration (lock-step, like the ReSTIR PT restatement); SuppressOutlierReservoirs sums over the lanes
 // that reached it, in the xor-butterfly order.
@@ -171,10 +171,49 @@ namespace
         return ret;
     }
 
-    float3 NEE(const Scene& sc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
+    // ReSTIR_GI_NEE.hlsli:123-193 with numSamples = 1 (the ReSTIR_GI_LVG variant); extents / offset arrive as halves (ReSTIR_GI.hlsl:52-55)
+    float3 NEE_Emissive_LVG(const Scene& sc, const zr_frame_constants& fc, float3 pos, float3 normal, BSDF::ShadingData surface, uint32_t sampleSetIdx, RNG& rng)
+    {
+        float3 ret = f3(0);
+        const float3 extents = f3(to_half(sc.lvgExtents[0]), to_half(sc.lvgExtents[1]), to_half(sc.lvgExtents[2]));
+        const float offset_y = to_half(sc.lvgOffsetY);
+        zr_voxel_sample s;
+        float3 lightPos, lightNormal, le; float lightPdf; uint32_t lightID;
+        if (LVG::Sample(sc, pos, extents, offset_y, fc.CurrView, s, rng))
+        {
+            lightPos = f3(s.pos[0], s.pos[1], s.pos[2]);
+            lightNormal = Math::DecodeOct32(s.normal);
+            le = f3(zr_f16_to_f32(s.le[0]), zr_f16_to_f32(s.le[1]), zr_f16_to_f32(s.le[2]));
+            lightPdf = s.pdf; lightID = s.ID;
+            if (s.twoSided && dot(lightNormal, pos - lightPos) < 0)
+                lightNormal = -lightNormal;
+        }
+        else
+        {
+            const Light::LightSample ls = Light::SampleLight(sc, pos, sampleSetIdx, rng, false);
+            lightPos = ls.pos; lightNormal = ls.normal; le = ls.le; lightPdf = ls.pdf; lightID = ls.ID;
+        }
+        const float t = length(lightPos - pos);
+        const float3 wi = (lightPos - pos) / t;
+        if (lightID != UINT32_MAX_ && dot(lightNormal, -wi) > 0)
+        {
+            const float dwdA = saturate(dot(lightNormal, -wi)) / (t * t);
+            surface.SetWi(wi, normal);
+            le *= BSDF::Unified(surface).f * dwdA;
+            if (Math::Luminance(le) > 1e-6f)
+                le *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
+            ret += le / fmaxf(lightPdf, 1e-6f);
+        }
+        ret = ret / 1.0f;
+        return ret;
+    }
+
+    float3 NEE(const Scene& sc, const zr_frame_constants& fc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
     {
         if (bounce == 0)
             return NEE_Emissive_MIS(sc, pos, normal, surface, sampleSetIdx, rng);
+        if (sc.lvg && sc.sampleSetSize)
+            return NEE_Emissive_LVG(sc, fc, pos, normal, surface, sampleSetIdx, rng);
         return NEE_Emissive_1(sc, pos, normal, surface, sampleSetIdx, rng);
     }
 
@@ -196,12 +235,12 @@ namespace
     };
 
     // loop top .. Russian-roulette point; false = left the loop
-    bool PT_PhaseA(const Scene& sc, GILane& s)
+    bool PT_PhaseA(const Scene& sc, const zr_frame_constants& fc, GILane& s)
     {
         const float3 hitPos = mad(s.hitInfo.t, s.bsdfSample.wi, s.pos);
         if (!GetMaterialData(sc, -s.bsdfSample.wi, s.eta_curr, s.hitInfo, s.surface, s.eta_next))
             return false;
-        s.li += s.throughput * NEE(sc, hitPos, s.hitInfo.normal, s.surface, s.sampleSetIdx, s.bounce, s.rngThread);
+        s.li += s.throughput * NEE(sc, fc, hitPos, s.hitInfo.normal, s.surface, s.sampleSetIdx, s.bounce, s.rngThread);
         if (s.bounce >= (s.maxNumBounces - 1))
             return false;
         s.pos = hitPos;
@@ -563,7 +602,7 @@ namespace
                         atRR[l] = false;
                         GILane& s = lanes[l];
                         if (!s.tracing) continue;
-                        if (!PT_PhaseA(sc, s)) { s.tracing = false; continue; }
+                        if (!PT_PhaseA(sc, fc, s)) { s.tracing = false; continue; }
                         atRR[l] = true; any = true;
                     }
                     if (!any) break;

@@ -140,6 +140,7 @@ class OracleRenderer:
 
     def gbuffer(self, fc):
         self.osc.presample(fc.FrameNum)       # PreLighting runs before the lighting passes; no-op unless presampling is on
+        self.osc.build_light_voxel_grid(fc)   # no-op unless the light voxel grid is on
         self.cur ^= 1
         self.gb[self.cur] = self.osc.gbuffer(fc, tridiff=False, nthreads=self.nthreads)
         return self.gb[self.cur]

@@ -77,6 +77,18 @@ class OracleScene:
         if getattr(self, "num_sets", 0):
             self.o.orc_presample(self.h, C.c_uint32(frame_num), C.c_uint32(self.num_sets * self.set_size), ptr(self.sample_sets))
 
+    def set_light_voxel_grid(self, grid_dim, extents, offset_y=0.0):
+        self.lvg_dim = tuple(grid_dim)
+        n = grid_dim[0] * grid_dim[1] * grid_dim[2]
+        self.lvg = np.zeros(max(n, 1) * 64 * 8, dtype=np.uint32)            # 32-byte records
+        d = (C.c_uint32 * 3)(*grid_dim)
+        e = (C.c_float * 3)(*extents)
+        self.o.orc_scene_set_lvg(self.h, ptr(self.lvg) if n else None, d, e, C.c_float(offset_y))
+
+    def build_light_voxel_grid(self, fc):
+        if getattr(self, "lvg_dim", None) and self.lvg_dim[0]:
+            self.o.orc_build_lvg(self.h, C.byref(fc), ptr(self.lvg))
+
     def gbuffer(self, fc, tridiff=False, nthreads=8):
         n = fc.RenderWidth * fc.RenderHeight
         core = np.zeros((n, 4), dtype=np.uint32)

@@ -10,7 +10,7 @@ from tests.test_rpt_gpu import _diff_report
 pytestmark = pytest.mark.gpu
 
 
-def _run(which, w, h, nframes, params=None, cam_path=None, presample=None, dof=False, accumulate=False):
+def _run(which, w, h, nframes, params=None, cam_path=None, presample=None, dof=False, accumulate=False, lvg=None):
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, IndirectLightingGI, download_image
     from tests import scene_util, rpt_util
@@ -21,6 +21,9 @@ def _run(which, w, h, nframes, params=None, cam_path=None, presample=None, dof=F
     if presample:
         R.osc.set_presampling(*presample)
         sc.set_presampling(*presample)
+    if lvg:
+        R.osc.set_light_voxel_grid(*lvg)
+        sc.set_light_voxel_grid(*lvg)
     gb, gpass, gi = GBuffers(w, h), GBufferRT(), IndirectLightingGI(w, h)
     if params:
         R.gi_params.update(params)
@@ -40,8 +43,14 @@ def _run(which, w, h, nframes, params=None, cam_path=None, presample=None, dof=F
         fi.scene = sc.handle
         gpass.Render(fi)
         sc.presample(fc.FrameNum)
+        sc.build_light_voxel_grid(fc)
         gi.Render(fi)
         check(lib.zr_stream_synchronize(None))
+        if lvg and fr == 0:
+            n = lvg[0][0] * lvg[0][1] * lvg[0][2] * 64 * 8
+            msg = _diff_report("light voxel grid", sc.light_voxel_grid().reshape(-1, 8), R.osc.lvg[:n].reshape(-1, 8))
+            if msg:
+                problems.append(msg)
         got_res = download_image(gi.GetOutput(1), np.uint8, 48).view(rpt_util.RGI).reshape(-1)
         got_final = download_image(gi.GetOutput(0), np.float32, 4)
         for name, a, b in (("gi reservoir", got_res, R.gi_curr_reservoirs()), ("gi final", got_final.view(np.uint32), R.gi_final.view(np.uint32))):
@@ -80,6 +89,17 @@ def test_rgi_presampled_sets_dof_accumulate():
     problems, _ = _run("glossy", 256, 144, 3, dof=True)
     assert not problems, "\n".join(problems)
     problems, _ = _run("cornell", 256, 144, 3, accumulate=True)
+    assert not problems, "\n".join(problems)
+
+
+def test_rgi_light_voxel_grid():
+    # ReSTIR_GI_LVG: the NEE light sample after the first indirect vertex comes from the camera-centred voxel grid, with the
+    # presampled set as fallback outside it. A small grid so that both branches run; then the reference's own dimensions.
+    path = lambda f: (0.03 * f, 1.2, -4.043 + 0.04 * f)
+    problems, _ = _run("glossy", 320, 180, 4, presample=(32, 128), lvg=((8, 4, 8), (0.6, 0.45, 0.6), 0.1), cam_path=path,
+                       params=dict(stochastic_multi_bounce=0))
+    assert not problems, "\n".join(problems)
+    problems, _ = _run("glass", 256, 144, 3, presample=(128, 512), lvg=((32, 8, 40), (0.6, 0.45, 0.6), 0.0))
     assert not problems, "\n".join(problems)
 
 

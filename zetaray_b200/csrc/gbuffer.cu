@@ -200,6 +200,78 @@ namespace
         for (int k = 0; k < 5; k++) q[k] = v[k];
     }
 
+    // BuildLightVoxelGrid.hlsl:56-162: one 64-thread group per voxel, RIS over 6 alias-table candidates per thread
+    __global__ void __launch_bounds__(64) k_build_lvg(SceneDev sc, zr_frame_constants fc, zr_voxel_sample* __restrict__ out)
+    {
+        __shared__ float s_waveSum[2];
+        __shared__ uint32_t s_waveLights[2];
+        const uint32_t dx = sc.lvgDim[0], dy = sc.lvgDim[1], dz = sc.lvgDim[2];
+        const uint32_t Gidx = threadIdx.x;
+        const uint32_t gridStart = LVG::FlattenVoxelIndex(blockIdx.x, blockIdx.y, blockIdx.z, dx, dy);
+        const float3 extents = f3(sc.lvgExtents[0], sc.lvgExtents[1], sc.lvgExtents[2]);
+        RNG rng = RNG::InitIdx(gridStart * 64 + Gidx, fc.FrameNum);
+        const float3 voxelCenter = LVG::VoxelCenter((int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)dx, (int)dy, (int)dz, extents, fc.CurrViewInv,
+            sc.lvgOffsetY);
+        zr_voxel_sample r;
+        r.pos[0] = r.pos[1] = r.pos[2] = FLT_MAX_; r.normal = 0; r.le[0] = r.le[1] = r.le[2] = 0; r.pdf = 0; r.twoSided = 0; r.ID = 0xffffffffu;
+        float w_sum = 0, target_z = 0;
+        uint32_t numLights = 0;
+        for (int i = 0; i < 6; i++)
+        {
+            const Light::AliasTableSample entry = Light::SampleAlias(sc.aliasTable, sc.numEmissives, rng);
+            const zr_emissive_tri& tri = sc.emissives[entry.idx];
+            const Light::EmissiveTriSample lightSample = Light::SampleEmissiveTri(voxelCenter, tri, rng, false);
+            const float3 le = Light::Le_EmissiveTriangle(tri);
+            const float3 d = f3(fabsf(lightSample.pos.x - voxelCenter.x), fabsf(lightSample.pos.y - voxelCenter.y), fabsf(lightSample.pos.z - voxelCenter.z));
+            const bool inside = d.x <= extents.x && d.y <= extents.y && d.z <= extents.z;
+            float3 lightPos = lightSample.pos;
+            if (inside)
+            {
+                const int maxIdx = d.x >= d.y ? (d.x >= d.z ? 0 : 2) : (d.y >= d.z ? 1 : 2);
+                if (maxIdx == 0) lightPos.x = extents.x; else if (maxIdx == 1) lightPos.y = extents.y; else lightPos.z = extents.z;
+            }
+            if (!inside && !Light::IsDoubleSided(tri))
+            {
+                bool backfacing = false;
+                for (int c = 0; c < 8; c++)
+                {
+                    const float3 corner = voxelCenter + f3((c & 4) ? 1.0f : -1.0f, (c & 2) ? 1.0f : -1.0f, (c & 1) ? 1.0f : -1.0f) * extents;
+                    if (dot(corner - lightSample.pos, lightSample.normal) <= 0) backfacing = true;
+                }
+                if (backfacing)
+                    continue;
+            }
+            const float t = length(lightPos - voxelCenter);
+            const float target = Math::Luminance(le) / fmaxf(t * t, 1e-6f);
+            const float lightPdf = entry.pdf * lightSample.pdf;
+            const float w = target / fmaxf(lightPdf, 1e-6f);
+            w_sum += w;
+            if (rng.Uniform() < w / fmaxf(w_sum, 1e-6f))
+            {
+                r.pos[0] = lightSample.pos.x; r.pos[1] = lightSample.pos.y; r.pos[2] = lightSample.pos.z;
+                r.normal = Math::EncodeOct32u(lightSample.normal);
+                r.le[0] = zr_f32_to_f16(le.x); r.le[1] = zr_f32_to_f16(le.y); r.le[2] = zr_f32_to_f16(le.z);
+                r.twoSided = Light::IsDoubleSided(tri) ? 1 : 0;
+                r.ID = tri.ID;
+                target_z = target;
+            }
+            numLights++;
+        }
+        const float waveSum = WaveSum32(w_sum);
+        uint32_t waveLights = numLights;
+        for (int off = 16; off >= 1; off >>= 1) waveLights += __shfl_xor_sync(0xffffffffu, waveLights, off);
+        if ((Gidx & 31) == 0) { s_waveSum[Gidx >> 5] = waveSum; s_waveLights[Gidx >> 5] = waveLights; }
+        __syncthreads();
+        float w_sum_group = s_waveSum[0] + s_waveSum[1];
+        const uint32_t numLightsGroup = (s_waveLights[0] + s_waveLights[1]) & 0xffffu;
+        w_sum_group /= (float)numLightsGroup;
+        r.pdf = target_z / fmaxf(w_sum_group, 1e-6f);
+        uint4 v[2];
+        memcpy(v, &r, 32);
+        uint4* q = reinterpret_cast<uint4*>(out + gridStart * 64 + Gidx);
+        q[0] = v[0]; q[1] = v[1];
+    }
+
     __global__ void k_emissive_power(SceneDev sc, float* __restrict__ power)
     {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,6 +424,50 @@ extern "C"
         zr::k_presample<<<(total + 63) / 64, 64, 0, (cudaStream_t)stream>>>(scene->dev, frame_num, total, scene->d_sampleSets);
         ZR_LAUNCH_CHECK();
         scene->samplesValid = true;
+        return ZR_OK;
+    }
+    zr_status zr_scene_set_light_voxel_grid(zr_scene* scene, const uint32_t grid_dim[3], const float extents[3], float offset_y)
+    {
+        if (!scene) return ZR_ERR_INVALID_ARG;
+        if (scene->d_lvg) { cudaFree(scene->d_lvg); scene->d_lvg = nullptr; }
+        scene->dev.lvg = nullptr; scene->lvgValid = false;
+        for (int i = 0; i < 3; i++) { scene->dev.lvgDim[i] = 0; scene->dev.lvgExtents[i] = 0; }
+        scene->dev.lvgOffsetY = 0;
+        if (!grid_dim || (grid_dim[0] | grid_dim[1] | grid_dim[2]) == 0)
+            return ZR_OK;       // off
+        const uint64_t voxels = (uint64_t)grid_dim[0] * grid_dim[1] * grid_dim[2];
+        if (!extents || !grid_dim[0] || !grid_dim[1] || !grid_dim[2] || voxels > (1u << 20) || !(extents[0] > 0 && extents[1] > 0 && extents[2] > 0))
+        {
+            zr::set_error("zr_scene_set_light_voxel_grid: need positive dims (<= 2^20 voxels) and extents");
+            return ZR_ERR_INVALID_ARG;
+        }
+        ZR_CUDA(cudaMalloc(&scene->d_lvg, voxels * 64 * sizeof(zr_voxel_sample)));
+        scene->dev.lvg = scene->d_lvg;
+        for (int i = 0; i < 3; i++) { scene->dev.lvgDim[i] = grid_dim[i]; scene->dev.lvgExtents[i] = extents[i]; }
+        scene->dev.lvgOffsetY = offset_y;
+        return ZR_OK;
+    }
+    zr_status zr_build_light_voxel_grid(zr_scene* scene, const zr_frame_constants* frame, void* stream)
+    {
+        if (!scene || !frame) return ZR_ERR_INVALID_ARG;
+        if (!scene->dev.lvg) return ZR_OK;
+        if (!scene->aliasBuilt || scene->dev.numEmissives == 0)
+        {
+            zr::set_error("zr_build_light_voxel_grid: needs emissive triangles and zr_prelighting_render first");
+            return ZR_ERR_NOT_INITIALIZED;
+        }
+        ZR_PROF("k_build_lvg", stream);
+        zr::k_build_lvg<<<dim3(scene->dev.lvgDim[0], scene->dev.lvgDim[1], scene->dev.lvgDim[2]), 64, 0, (cudaStream_t)stream>>>(scene->dev, *frame,
+            scene->d_lvg);
+        ZR_LAUNCH_CHECK();
+        scene->lvgValid = true;
+        return ZR_OK;
+    }
+    zr_status zr_scene_get_light_voxel_grid(zr_scene* scene, void** d_samples, uint32_t* num_samples)
+    {
+        if (!scene || !d_samples || !num_samples) return ZR_ERR_INVALID_ARG;
+        *d_samples = scene->d_lvg;
+        *num_samples = scene->dev.lvgDim[0] * scene->dev.lvgDim[1] * scene->dev.lvgDim[2] * 64u;
         return ZR_OK;
     }
     zr_status zr_scene_get_sample_sets(zr_scene* scene, void** d_sets, uint32_t* num_sets, uint32_t* set_size)

@@ -101,6 +101,8 @@ extern "C"
         }
         s = zr_presample_emissives(r->scene, fc->FrameNum, stream);
         if (s != ZR_OK) return s;
+        s = zr_build_light_voxel_grid(r->scene, fc, stream);        // no-op unless the grid is enabled (ReSTIR GI's LVG variant)
+        if (s != ZR_OK) return s;
 
         r->curr ^= 1;       // GlobalIdxForDoubleBufferedResources
         zr_frame_inputs in;

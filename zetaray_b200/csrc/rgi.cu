@@ -3,8 +3,8 @@
 // Replaces IndirectLighting/ReSTIR_GI/ReSTIR_GI.hlsl (+ Resampling.hlsli, PathTracing.hlsli, ReSTIR_GI_NEE.hlsli,
 // Reservoir.hlsli, ../NEE.hlsli) and the host sequencing of IndirectLighting.cpp:277-368 for the ReSTIR_GI_WoPS / _WPS
 // variants: a path-traced initial candidate (second path vertex + its outgoing radiance), temporal reuse with one or two
-// reprojected candidates weighted by the reconnection Jacobian, wave-level outlier suppression. Not built: sun/sky NEE,
-// the light-voxel-grid variant, ray differentials (they only feed texture LOD; no textures in this build), the spatial
+// reprojected candidates weighted by the reconnection Jacobian, wave-level outlier suppression; NEE after the first indirect
+// vertex optionally from the light voxel grid (ReSTIR_GI_LVG). Not built: sun/sky NEE, ray differentials (they only feed texture LOD; no textures in this build), the spatial
 // pass (commented out upstream, Resampling.hlsli:603-608).
 // A block is 16 consecutive 8x8 groups of the reference's swizzled dispatch, one warp per reference wave, so the
 // Russian-roulette WaveActiveMax (PathTracing.hlsli:64-67, evaluated over the lanes at the same loop iteration) is a warp max
@@ -169,10 +169,46 @@ namespace
         return ret;
     }
 
-    ZR_D float3 NEE(const SceneDev& sc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
+    // ReSTIR_GI_NEE.hlsli:123-193 with numSamples = 1 (the ReSTIR_GI_LVG variant); extents / offset arrive as halves (ReSTIR_GI.hlsl:52-55)
+    ZR_D float3 NEE_Emissive_LVG(const SceneDev& sc, const zr_frame_constants& fc, float3 pos, float3 normal, BSDF::ShadingData surface, uint32_t sampleSetIdx, RNG& rng)
+    {
+        float3 ret = f3(0);
+        const float3 extents = f3(to_half(sc.lvgExtents[0]), to_half(sc.lvgExtents[1]), to_half(sc.lvgExtents[2]));
+        const float offset_y = to_half(sc.lvgOffsetY);
+        LVG::VoxelLight s;
+        float3 lightPos, lightNormal, le; float lightPdf; uint32_t lightID;
+        if (LVG::Sample(sc, pos, extents, offset_y, fc.CurrView, s, rng))
+        {
+            lightPos = s.pos; lightNormal = s.normal; le = s.le; lightPdf = s.pdf; lightID = s.ID;
+            if (s.twoSided && dot(lightNormal, pos - lightPos) < 0)
+                lightNormal = -lightNormal;
+        }
+        else
+        {
+            const Light::LightSample ls = Light::SampleLight(sc, pos, sampleSetIdx, rng, false);
+            lightPos = ls.pos; lightNormal = ls.normal; le = ls.le; lightPdf = ls.pdf; lightID = ls.ID;
+        }
+        const float t = length(lightPos - pos);
+        const float3 wi = (lightPos - pos) / t;
+        if (lightID != UINT32_MAX_ && dot(lightNormal, -wi) > 0)
+        {
+            const float dwdA = saturate(dot(lightNormal, -wi)) / (t * t);
+            surface.SetWi(wi, normal);
+            le *= BSDF::Unified(surface).f * dwdA;
+            if (Math::Luminance(le) > 1e-6f)
+                le *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
+            ret += le / fmaxf(lightPdf, 1e-6f);
+        }
+        ret = ret / 1.0f;
+        return ret;
+    }
+
+    ZR_D float3 NEE(const SceneDev& sc, const zr_frame_constants& fc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
     {
         if (bounce == 0)
             return NEE_Emissive_MIS(sc, pos, normal, surface, sampleSetIdx, rng);
+        if (sc.lvg && sc.sampleSetSize)
+            return NEE_Emissive_LVG(sc, fc, pos, normal, surface, sampleSetIdx, rng);
         return NEE_Emissive_1(sc, pos, normal, surface, sampleSetIdx, rng);
     }
 
@@ -518,7 +554,7 @@ namespace
                     tracing = false;
                 else
                 {
-                    li += throughput * NEE(sc, hitPos, hitInfo.normal, surface, sampleSetIdx, bounce, rngThread);
+                    li += throughput * NEE(sc, fc, hitPos, hitInfo.normal, surface, sampleSetIdx, bounce, rngThread);
                     if (bounce >= (maxNumBounces - 1))
                         tracing = false;
                     else
@@ -710,6 +746,11 @@ struct zr_gi_pass
         if (in->scene->dev.sampleSetSize && !in->scene->samplesValid)
         {
             set_error("zr_gi_pass_render: presampling is enabled but zr_presample_emissives has not run");
+            return ZR_ERR_NOT_INITIALIZED;
+        }
+        if (in->scene->dev.lvg && in->scene->dev.sampleSetSize && !in->scene->lvgValid)
+        {
+            set_error("zr_gi_pass_render: the light voxel grid is enabled but zr_build_light_voxel_grid has not run");
             return ZR_ERR_NOT_INITIALIZED;
         }
         const bool doTemporal = params.temporal_resample && isTemporalReservoirValid;

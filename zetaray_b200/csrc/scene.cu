@@ -403,6 +403,7 @@ extern "C"
         if (sc->d_power) cudaFree(sc->d_power);
         if (sc->d_aliasScratch) cudaFree(sc->d_aliasScratch);
         if (sc->d_sampleSets) cudaFree(sc->d_sampleSets);
+        if (sc->d_lvg) cudaFree(sc->d_lvg);
         delete sc;
     }
     zr_status zr_scene_bvh_stats(const zr_scene* sc, uint32_t out[4])

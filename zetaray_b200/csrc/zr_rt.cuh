@@ -285,4 +285,62 @@ namespace Light
         return ls;
     }
 }
+// Common/LightVoxelGrid.hlsli:8-69
+namespace LVG
+{
+    ZR_D uint32_t FlattenVoxelIndex(uint32_t x, uint32_t y, uint32_t z, uint32_t dx, uint32_t dy) { return z * dx * dy + y * dx + x; }
+
+    ZR_D float3 VoxelCenter(int vx, int vy, int vz, int dx, int dy, int dz, float3 voxelExtents, const float viewInv[3][4], float offset_y)
+    {
+        const int hx = dx >> 1, hy = dy >> 1, hz = dz >> 1;
+        int cx = vx - hx, cy = vy - hy, cz = vz - hz;
+        cx += vx < hx ? 1 : 0; cy += vy < hy ? 1 : 0; cz += vz < hz ? 1 : 0;
+        cy *= -1;       // voxel space Y points in the opposite direction of camera space Y
+        const float3 corner = f3((float)(cx * 2), (float)(cy * 2), (float)(cz * 2)) * voxelExtents;
+        const float3 s = f3(Math::SignNotZero((float)cx), Math::SignNotZero((float)cy), Math::SignNotZero((float)cz));
+        float3 centerV = corner + voxelExtents * s;
+        centerV.y += offset_y;
+        return Math::mul3x4(viewInv, centerV);
+    }
+
+    ZR_D bool MapPosToVoxel(float3 pos, int dx, int dy, int dz, float3 voxelExtents, const float view[3][4], int& ox, int& oy, int& oz, float offset_y)
+    {
+        float3 posV = Math::mul3x4(view, pos);
+        posV.y -= offset_y;
+        const int hx = dx >> 1, hy = dy >> 1, hz = dz >> 1;
+        float3 voxel = f3(floorf(fabsf(posV.x) / (2 * voxelExtents.x)), floorf(fabsf(posV.y) / (2 * voxelExtents.y)), floorf(fabsf(posV.z) / (2 * voxelExtents.z)));
+        if (voxel.x >= (float)hx || voxel.y >= (float)hy || voxel.z >= (float)hz)
+            return false;
+        voxel = voxel * f3(Math::SignNotZero(posV.x), Math::SignNotZero(posV.y), Math::SignNotZero(posV.z));
+        voxel.y *= -1;
+        ox = (int)voxel.x + hx - (posV.x < 0 ? 1 : 0);
+        oy = (int)voxel.y + hy - (posV.y >= 0 ? 1 : 0);
+        oz = (int)voxel.z + hz - (posV.z < 0 ? 1 : 0);
+        return true;
+    }
+}
+
+namespace LVG
+{
+    // LightVoxelGrid.hlsli:54-68 (32-byte records, 16-byte aligned: two 128-bit loads)
+    struct VoxelLight { float3 pos, normal, le; float pdf; uint32_t ID; bool twoSided; };
+    ZR_D bool Sample(const SceneDev& sc, float3 pos, float3 voxelExtents, float offset_y, const float view[3][4], VoxelLight& out, RNG& rng)
+    {
+        const float3 u = rng.Uniform3D();
+        const float3 posJittered = pos + (u * 2.0f - 1.0f) * voxelExtents;
+        int vx, vy, vz;
+        if (!MapPosToVoxel(posJittered, (int)sc.lvgDim[0], (int)sc.lvgDim[1], (int)sc.lvgDim[2], voxelExtents, view, vx, vy, vz, offset_y))
+            return false;
+        const uint32_t start = FlattenVoxelIndex((uint32_t)vx, (uint32_t)vy, (uint32_t)vz, sc.lvgDim[0], sc.lvgDim[1]) * 64u;
+        const uint32_t k = rng.UniformUintBounded_Faster(64u);
+        const uint4* q = reinterpret_cast<const uint4*>(sc.lvg + start + k);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        out.pos = f3(asfloat(a.x), asfloat(a.y), asfloat(a.z));
+        out.normal = Math::DecodeOct32(a.w);
+        out.pdf = asfloat(b.x); out.ID = b.y;
+        out.le = f3(zr_f16_to_f32((uint16_t)(b.z & 0xffff)), zr_f16_to_f32((uint16_t)(b.z >> 16)), zr_f16_to_f32((uint16_t)(b.w & 0xffff)));
+        out.twoSided = (b.w >> 16) != 0;
+        return true;
+    }
+}
 } // namespace zr

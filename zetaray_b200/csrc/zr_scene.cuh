@@ -45,6 +45,11 @@ struct SceneDev
     // presampled emissive sets (PresampleEmissives.hlsl); sampleSetSize == 0: lights are sampled through the alias table
     const zr_presampled_tri* sampleSets;
     uint32_t numSampleSets, sampleSetSize;
+    // light voxel grid (BuildLightVoxelGrid.hlsl); lvg == nullptr: off
+    const zr_voxel_sample* lvg;
+    uint32_t lvgDim[3];
+    float lvgExtents[3];
+    float lvgOffsetY;
 };
 
 struct RayHit { bool hit; float t; float2 bary; uint32_t tri; };
@@ -245,4 +250,6 @@ struct zr_scene
     bool aliasBuilt = false;
     zr_presampled_tri* d_sampleSets = nullptr;
     bool samplesValid = false;      // zr_presample_emissives ran since the sets were (re)configured
+    zr_voxel_sample* d_lvg = nullptr;
+    bool lvgValid = false;          // zr_build_light_voxel_grid ran since the grid was (re)configured
 };

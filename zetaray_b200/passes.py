@@ -56,6 +56,25 @@ class Scene:
             check(lib.zr_stream_synchronize(None))
         return out
 
+    def set_light_voxel_grid(self, grid_dim, extents, offset_y=0.0):
+        """Reference defaults: (32, 8, 40) voxels of half-extents (0.6, 0.45, 0.6); (0, 0, 0) switches the grid off."""
+        d = (C.c_uint32 * 3)(*grid_dim)
+        e = (C.c_float * 3)(*extents)
+        check(lib.zr_scene_set_light_voxel_grid(self.handle, d, e, C.c_float(offset_y)))
+
+    def build_light_voxel_grid(self, fc, stream=None):
+        """BuildLightVoxelGrid: once per frame (the grid follows the camera), after presample()."""
+        check(lib.zr_build_light_voxel_grid(self.handle, C.byref(fc), stream))
+
+    def light_voxel_grid(self):
+        p, n = C.c_void_p(), C.c_uint32()
+        check(lib.zr_scene_get_light_voxel_grid(self.handle, C.byref(p), C.byref(n)))
+        out = np.zeros(n.value * 8, dtype=np.uint32)
+        if out.size:
+            check(lib.zr_memcpy_d2h(_vp(out), p, C.c_size_t(out.nbytes), None))
+            check(lib.zr_stream_synchronize(None))
+        return out
+
     def alias_table(self):
         p = C.c_void_p()
         n = C.c_uint32()
