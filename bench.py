@@ -141,7 +141,8 @@ def main():
     import torch.distributed as dist
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, DirectLighting, IndirectLighting, Compositing, TAA
-    from tests import scene_util, rpt_util     # scene fixture + frame-constant generator (no oracle code on this path)
+    from zetaray_b200.camera import FrameSequence
+    from zetaray_b200.scene import FlatScene
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,14 +163,14 @@ def main():
     # halos move with one NCCL all-gather per exchange point (zetaray_b200/sharding.py); the finished strips are
     # all-gathered every frame so the image is complete on every rank before the next frame starts.
     from zetaray_b200.sharding import ShardedFrame, StripPlan
-    flat = scene_util.cornell()
+    flat = FlatScene.load(os.path.join(ROOT, "tests", "golden", "cornell_emissive.npz"))     # the reference's cornell_emissive.gltf, flattened
     scene = Scene(flat)
     scene.prelighting(st)
     gb = GBuffers(W, H)
     passes = dict(gbuffer=GBufferRT(), direct=DirectLighting(W, H), indirect=IndirectLighting(W, H),
                   compositing=Compositing(W, H), taa=TAA(W, H))
     taa = passes["taa"]
-    seq = rpt_util.FrameSequence(W, H)
+    seq = FrameSequence(W, H)
     fi = _lib.FrameInputs()
     fi.scene = scene.handle
     sharded = ShardedFrame(passes, gb, W, H, rank, world)

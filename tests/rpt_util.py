@@ -60,47 +60,7 @@ class RptBuffers(C.Structure):
                 ("neighbor", C.c_void_p), ("tmCtN", C.c_void_p), ("tmNtC", C.c_void_p)]
 
 
-def halton(i, b):
-    f = np.float32(1.0); r = np.float32(0.0); bf = np.float32(b)
-    while i > 0:
-        f = np.float32(f / bf)
-        r = np.float32(r + f * np.float32(i % b))
-        i = int(np.float32(i) / bf)
-    return r
-
-
-class FrameSequence:
-    """cbFrameConstants for consecutive frames of a static camera: jitter = Halton(2,3) - 0.5
-    over an 8-phase cycle, prev* = last frame's curr*."""
-
-    def __init__(self, w, h, jitter=True, first_frame=1, cam_path=None, accumulate=False):
-        """cam_path(frame) -> camera position (a translating camera); None = the static default camera.
-        accumulate: Accumulate + CameraStatic with NumFramesCameraStatic counting up (the reference's accumulation mode)."""
-        self.w, self.h, self.jitter = w, h, jitter
-        self.frame = first_frame - 1
-        self.prev_jitter = (0.0, 0.0)
-        self.cam_path, self.accumulate = cam_path, accumulate
-        self.prev_cam = None
-        self.static_frames = 0
-
-    def next(self):
-        self.frame += 1
-        j = (0.0, 0.0)
-        if self.jitter:
-            ph = self.frame % 8
-            j = (float(halton(ph + 1, 2) - np.float32(0.5)), float(halton(ph + 1, 3) - np.float32(0.5)))
-        if self.cam_path is None:
-            fc = synth.look_at_frame_constants(self.w, self.h, frame=self.frame, jitter=j, prev_jitter=self.prev_jitter)
-        else:
-            cam = tuple(float(np.float32(c)) for c in self.cam_path(self.frame))
-            fc = synth.look_at_frame_constants(self.w, self.h, frame=self.frame, jitter=j, prev_jitter=self.prev_jitter, cam=cam,
-                                               prev_cam=self.prev_cam or cam)
-            self.prev_cam = cam
-        if self.accumulate:
-            self.static_frames += 1
-            fc.Accumulate, fc.CameraStatic, fc.NumFramesCameraStatic = 1, 1, self.static_frames
-        self.prev_jitter = j
-        return fc
+from zetaray_b200.camera import halton, FrameSequence  # noqa: E402,F401  (moved into the package)
 
 
 class OracleRenderer:

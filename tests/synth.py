@@ -7,33 +7,7 @@ from zetaray_b200._lib import FrameConstants
 FLT_MAX = np.float32(3.402823466e+38)
 
 
-def look_at_frame_constants(w, h, frame=1, jitter=(0.0, 0.0), prev_jitter=(0.0, 0.0), cam=(0.0, 1.2, -4.043), prev_cam=None):
-    """cbFrameConstants for the default camera: left-handed, +Z forward, vfov 60 deg.
-    prev_cam: last frame's camera position (a translating camera); defaults to cam (static)."""
-    fc = FrameConstants()
-    pc = cam if prev_cam is None else prev_cam
-    view = np.array([[1, 0, 0, -cam[0]], [0, 1, 0, -cam[1]], [0, 0, 1, -cam[2]]], dtype=np.float32)
-    inv = np.array([[1, 0, 0, cam[0]], [0, 1, 0, cam[1]], [0, 0, 1, cam[2]]], dtype=np.float32)
-    pview = np.array([[1, 0, 0, -pc[0]], [0, 1, 0, -pc[1]], [0, 0, 1, -pc[2]]], dtype=np.float32)
-    pinv = np.array([[1, 0, 0, pc[0]], [0, 1, 0, pc[1]], [0, 0, 1, pc[2]]], dtype=np.float32)
-    for name, m in (("CurrView", view), ("PrevView", pview), ("CurrViewInv", inv), ("PrevViewInv", pinv)):
-        arr = getattr(fc, name)
-        for i, v in enumerate(m.reshape(-1)):
-            arr[i] = float(v)
-    fc.CameraPos[0], fc.CameraPos[1], fc.CameraPos[2] = cam
-    fc.CameraNear = 0.2
-    fc.AspectRatio = np.float32(w) / np.float32(h)
-    fc.TanHalfFOV = float(np.tan(np.float32(0.5) * np.float32(np.pi / 3)).astype(np.float32))
-    fc.PixelSpreadAngle = float(np.arctan(np.float32(2 * fc.TanHalfFOV / h)))
-    fc.FrameNum = frame
-    fc.RenderWidth, fc.RenderHeight, fc.DisplayWidth, fc.DisplayHeight = w, h, w, h
-    fc.CurrCameraJitter[0], fc.CurrCameraJitter[1] = jitter
-    fc.PrevCameraJitter[0], fc.PrevCameraJitter[1] = prev_jitter
-    fc.CameraRayUVGradsScale = 1.0
-    fc.NumFramesCameraStatic = 0
-    fc.CameraStatic = 0
-    fc.Accumulate = 0
-    return fc
+from zetaray_b200.camera import look_at_frame_constants  # noqa: E402,F401  (moved into the package)
 
 
 def synth_gbuffer(w, h, seed, miss_frac=0.1, emissive_frac=0.03):
