@@ -143,3 +143,33 @@ def test_restir_pt_mean_matches_plain_path_tracing():
     pt = run(0, 0)
     rs = run(1, 1)
     assert np.all(np.abs(rs - pt) / pt < 0.12), (pt, rs)
+
+
+def test_oracle_outputs_are_frozen():
+    """The lighting oracle has no external pin; tests/golden/oracle_hashes.json freezes its outputs (tools/make_oracle_hashes.py)
+    so that a change to the oracle is a deliberate, visible act."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_oracle_hashes", os.path.join(root, "tools", "make_oracle_hashes.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    want = json.load(open(os.path.join(root, "tests", "golden", "oracle_hashes.json")))
+    for name, kw in m.CASES.items():
+        got = m.run(**kw)
+        assert got == want[name], "oracle output changed for case %s: %s" % (name, [k for k in got if got[k] != want[name].get(k)])
+
+
+def test_presampled_sets_follow_the_alias_distribution():
+    """PresampleEmissives draws lights in proportion to their power: over many sets the light indices of the oracle's presampled
+    records match the alias table's probabilities."""
+    import numpy as np
+    from tests import scene_util
+    osc = scene_util.OracleScene(scene_util.cornell())
+    osc.set_presampling(64, 512)
+    osc.presample(7)
+    idx = osc.sample_sets.reshape(-1, 10)[:64 * 512, 6]
+    p = osc.power / osc.power.sum()
+    freq = np.bincount(idx, minlength=len(p)) / idx.size
+    assert np.abs(freq - p).max() < 0.01, (freq, p)
