@@ -303,6 +303,12 @@ ZR_API void zr_scene_destroy(zr_scene* scene);
 /* BVH statistics for tests: {num_nodes, num_tris, max_depth, bytes}. */
 ZR_API zr_status zr_scene_bvh_stats(const zr_scene* scene, uint32_t out[4]);
 
+/* The BVH builder alone, on host memory (no GPU needed): world-space triangles as 9 floats {v0, e1, e2} in, 80-byte
+ * nodes and the leaf-order permutation out (either may be NULL to query sizes). out_info = {num_nodes, num_tris,
+ * max_depth, max_traversal_stack}; zr_scene_create refuses a tree whose max_traversal_stack exceeds the kernels' stack. */
+ZR_API zr_status zr_bvh_build_host(const float* h_world_tris, uint32_t num_tris, void* h_nodes, uint32_t node_capacity,
+    uint32_t* h_leaf_order, uint32_t out_info[4]);
+
 /* Ray queries through the product traversal kernel, for parity tests against the oracle's brute
  * force (mirrors RtRayQuery::Hit::FindClosest / Visibility_Segment, Common/RayQuery.hlsli:15-144,
  * 337-406). rays: n x {origin xyz, tmin, dir xyz, tmax}; hits: n x {t, bary.x, bary.y, triGlobal(u32)}. */
@@ -568,6 +574,16 @@ ZR_API zr_status zr_renderer_get_output(zr_renderer* r, zr_image2d* out);      /
 ZR_API zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** gbuffer, zr_direct_pass** direct,
     zr_indirect_pass** indirect, zr_compositing_pass** compositing, zr_taa_pass** taa);
 ZR_API zr_status zr_renderer_get_gbuffer(zr_renderer* r, int previous, zr_gbuffer* out);
+/* IndirectLighting::SetMethod(INTEGRATOR) as DefaultRenderer.cpp:243 calls it; values follow IndirectLighting.h's enum
+ * (PATH_TRACING 0 is not part of this build). The ReSTIR GI pass object is created on first use. */
+typedef enum zr_integrator { ZR_INTEGRATOR_PATH_TRACING = 0, ZR_INTEGRATOR_RESTIR_GI = 1, ZR_INTEGRATOR_RESTIR_PT = 2 } zr_integrator;
+ZR_API zr_status zr_renderer_set_integrator(zr_renderer* r, zr_integrator method);
+ZR_API zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi);
+/* RenderSettings::LightPresampling / UseLVG as DefaultRenderer::Update derives them from the scene
+ * (DefaultRenderer.cpp:361-363, 439-478; DefaultRendererImpl.h:37-43): presampled sets 128 x 512 iff the scene has
+ * >= 13107 emissive triangles, the 32 x 8 x 40 light voxel grid only if requested AND presampling is on.
+ * out_applied (may be NULL) = {presampling, lvg} as decided. */
+ZR_API zr_status zr_renderer_apply_scene_settings(zr_renderer* r, int use_lvg, uint32_t out_applied[2]);
 ZR_API void zr_renderer_destroy(zr_renderer* r);
 
 #ifdef __cplusplus

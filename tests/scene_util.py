@@ -44,7 +44,29 @@ def glass_cornell():
     return s
 
 
-SCENES = {"cornell": cornell, "glossy": glossy_cornell, "glass": glass_cornell}
+def atrium_small():
+    """"Sponza-class" procedural atrium (config C4 stand-in) at a size the brute-force oracle traces in seconds."""
+    from zetaray_b200 import procedural
+    return procedural.atrium(0.12)
+
+
+def atrium_many_lights():
+    """Same hall, coarser, but with finely tessellated lanterns: >= 13107 emissive triangles, the reference's threshold
+    for presampled sets (DefaultRendererImpl.h:37-41)."""
+    from zetaray_b200 import procedural
+    return procedural.atrium(0.08, lamp_tris=224)
+
+
+def tunnel_small():
+    """"Subway-class" procedural station tunnel (config C5 stand-in): glass screens, glossy metal, emissive tubes."""
+    from zetaray_b200 import procedural
+    return procedural.tunnel(0.1)
+
+
+SCENES = {"cornell": cornell, "glossy": glossy_cornell, "glass": glass_cornell, "atrium": atrium_small,
+          "atrium_lights": atrium_many_lights, "tunnel": tunnel_small}
+# static camera per scene (looks down +Z); the Cornell variants use the reference's default camera
+CAMERAS = {"atrium": (0.0, 1.7, -13.0), "atrium_lights": (0.0, 1.7, -13.0), "tunnel": (-1.6, 1.7, -4.0)}
 
 
 class OracleScene:

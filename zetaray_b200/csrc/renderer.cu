@@ -27,6 +27,8 @@ struct zr_renderer
     zr_gbuffer_pass* gbufferPass = nullptr;
     zr_direct_pass* direct = nullptr;
     zr_indirect_pass* indirect = nullptr;
+    zr_gi_pass* gi = nullptr;                       // created on the first SetMethod(ReSTIR_GI)
+    zr_integrator integrator = ZR_INTEGRATOR_RESTIR_PT;     // RenderSettings::Indirect default, DefaultRendererImpl.h:64
     zr_compositing_pass* compositing = nullptr;
     zr_taa_pass* taa = nullptr;
     cudaStream_t side = nullptr;            // DirectLighting runs here when twoStreams
@@ -38,6 +40,8 @@ struct zr_renderer
         if (gbufferPass) zr_gbuffer_pass_destroy(gbufferPass);
         if (direct) zr_direct_pass_destroy(direct);
         if (indirect) zr_indirect_pass_destroy(indirect);
+        if (gi) zr_gi_pass_destroy(gi);
+        gi = nullptr;
         if (compositing) zr_compositing_pass_destroy(compositing);
         if (taa) zr_taa_pass_destroy(taa);
         gbufferPass = nullptr; direct = nullptr; indirect = nullptr; compositing = nullptr; taa = nullptr;
@@ -122,7 +126,7 @@ extern "C"
         }
         s = zr_direct_pass_render(r->direct, &in, directStream);
         if (s != ZR_OK) return s;
-        s = zr_indirect_pass_render(r->indirect, &in, stream);
+        s = r->integrator == ZR_INTEGRATOR_RESTIR_GI ? zr_gi_pass_render(r->gi, &in, stream) : zr_indirect_pass_render(r->indirect, &in, stream);
         if (s != ZR_OK) return s;
         if (r->twoStreams)
         {
@@ -132,7 +136,8 @@ extern "C"
         zr_image2d di, ind, comp;
         s = zr_direct_pass_get_output(r->direct, ZR_DIRECT_FINAL, &di);
         if (s != ZR_OK) return s;
-        s = zr_indirect_pass_get_output(r->indirect, ZR_INDIRECT_FINAL, &ind);
+        s = r->integrator == ZR_INTEGRATOR_RESTIR_GI ? zr_gi_pass_get_output(r->gi, ZR_GI_FINAL, &ind)
+                                                     : zr_indirect_pass_get_output(r->indirect, ZR_INDIRECT_FINAL, &ind);
         if (s != ZR_OK) return s;
         s = zr_compositing_pass_render(r->compositing, &in, di.d_ptr, ind.d_ptr, stream);
         if (s != ZR_OK) return s;
@@ -141,6 +146,59 @@ extern "C"
         s = zr_taa_pass_render(r->taa, &in, comp.d_ptr, stream);
         if (s != ZR_OK) return s;
         r->framesRendered++;
+        return ZR_OK;
+    }
+
+    // IndirectLighting::SetMethod (IndirectLighting.cpp:203-235, called from DefaultRenderer.cpp:243): switching the
+    // integrator drops the temporal history of the one switched to.
+    zr_status zr_renderer_set_integrator(zr_renderer* r, zr_integrator method)
+    {
+        if (!r) return ZR_ERR_INVALID_ARG;
+        if (method != ZR_INTEGRATOR_RESTIR_GI && method != ZR_INTEGRATOR_RESTIR_PT)
+        {
+            zr::set_error("zr_renderer_set_integrator: integrator %d is not part of this build (ReSTIR GI = 1, ReSTIR PT = 2)", (int)method);
+            return ZR_ERR_INVALID_ARG;
+        }
+        if (method == r->integrator) return ZR_OK;
+        zr_status s = ZR_OK;
+        if (method == ZR_INTEGRATOR_RESTIR_GI)
+        {
+            if (!r->gi) s = zr_gi_pass_create(r->width, r->height, &r->gi);
+            else s = zr_gi_pass_reset_temporal(r->gi);
+        }
+        else
+            s = zr_indirect_pass_reset_temporal(r->indirect);
+        if (s != ZR_OK) return s;
+        r->integrator = method;
+        return ZR_OK;
+    }
+    zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi)
+    {
+        if (!r || !gi) return ZR_ERR_INVALID_ARG;
+        *gi = r->gi;        // NULL until ReSTIR GI has been selected once
+        return ZR_OK;
+    }
+    // The host decisions of DefaultRenderer::Update for an emissive-lit scene (DefaultRenderer.cpp:361-363, 439-478 with
+    // the constants of DefaultRendererImpl.h:37-43): presampled sets 128 x 512 iff the scene has at least
+    // 0.5 MB / sizeof(PresampledEmissiveTriangle) = 13107 emissive triangles; the light voxel grid (32 x 8 x 40 voxels of
+    // half-extents 0.6 x 0.45 x 0.6, y offset 0.1) only together with presampling.
+    zr_status zr_renderer_apply_scene_settings(zr_renderer* r, int use_lvg, uint32_t out_applied[2])
+    {
+        if (!r) return ZR_ERR_INVALID_ARG;
+        const zr_alias_entry* table = nullptr; uint32_t numEmissive = 0;
+        zr_status s = zr_scene_get_alias_table(r->scene, &table, &numEmissive);
+        if (s != ZR_OK) return s;
+        constexpr uint32_t MIN_NUM_LIGHTS_PRESAMPLING = (uint32_t)((0.5 * 1024 * 1024) / sizeof(zr_presampled_tri));
+        static_assert(MIN_NUM_LIGHTS_PRESAMPLING == 13107, "sizeof(PresampledEmissiveTriangle) must be 40");
+        const bool presampling = numEmissive >= MIN_NUM_LIGHTS_PRESAMPLING;
+        const bool lvg = use_lvg && presampling;
+        s = presampling ? zr_scene_set_presampling(r->scene, 128, 512) : zr_scene_set_presampling(r->scene, 0, 0);
+        if (s != ZR_OK) return s;
+        const uint32_t dim[3] = { 32, 8, 40 }, none[3] = { 0, 0, 0 };
+        const float ext[3] = { 0.6f, 0.45f, 0.6f };
+        s = zr_scene_set_light_voxel_grid(r->scene, lvg ? dim : none, ext, 0.1f);
+        if (s != ZR_OK) return s;
+        if (out_applied) { out_applied[0] = presampling; out_applied[1] = lvg; }
         return ZR_OK;
     }
 

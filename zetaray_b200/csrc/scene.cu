@@ -62,188 +62,6 @@ namespace
         flags[i] = TraceAnyExcept(sc, f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7], 0xffffffffu) ? 1u : 0u;
     }
 
-    // ------------------------------------------------------------------------------------------
-    // host BVH builder
-    // ------------------------------------------------------------------------------------------
-    struct AABB
-    {
-        float lo[3], hi[3];
-        void reset() { for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; } }
-        void grow(const AABB& b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
-        void grow(const float p[3]) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
-        float area() const
-        {
-            float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-            if (dx < 0) return 0;
-            return 2.0f * (dx * dy + dy * dz + dz * dx);
-        }
-    };
-
-    struct BNode { AABB box; int left = -1, right = -1; uint32_t first = 0, count = 0; };
-
-    struct Builder
-    {
-        std::vector<AABB> triBox;
-        std::vector<float> centroid;    // 3 per tri
-        std::vector<uint32_t> order;
-        std::vector<BNode> nodes;
-
-        int build(uint32_t first, uint32_t count)
-        {
-            BNode n;
-            n.box.reset();
-            AABB cb; cb.reset();
-            for (uint32_t i = first; i < first + count; i++)
-            {
-                n.box.grow(triBox[order[i]]);
-                cb.grow(&centroid[order[i] * 3]);
-            }
-            n.first = first; n.count = count;
-            const int idx = (int)nodes.size();
-            nodes.push_back(n);
-            if (count <= 3)
-                return idx;
-            // binned SAH over the widest centroid axis (try all 3)
-            const int NB = 16;
-            float bestCost = INFINITY; int bestAxis = -1; int bestSplit = -1;
-            for (int a = 0; a < 3; a++)
-            {
-                const float ext = cb.hi[a] - cb.lo[a];
-                if (!(ext > 0)) continue;
-                AABB bb[NB]; uint32_t bc[NB];
-                for (int b = 0; b < NB; b++) { bb[b].reset(); bc[b] = 0; }
-                for (uint32_t i = first; i < first + count; i++)
-                {
-                    int b = (int)((centroid[order[i] * 3 + a] - cb.lo[a]) / ext * NB);
-                    b = std::min(std::max(b, 0), NB - 1);
-                    bb[b].grow(triBox[order[i]]); bc[b]++;
-                }
-                AABB r; r.reset();
-                float rArea[NB]; uint32_t rCnt[NB]; uint32_t c = 0;
-                for (int b = NB - 1; b > 0; b--) { r.grow(bb[b]); c += bc[b]; rArea[b] = r.area(); rCnt[b] = c; }
-                AABB l; l.reset(); c = 0;
-                for (int b = 0; b < NB - 1; b++)
-                {
-                    l.grow(bb[b]); c += bc[b];
-                    if (c == 0 || rCnt[b + 1] == 0) continue;
-                    const float cost = l.area() * (float)c + rArea[b + 1] * (float)rCnt[b + 1];
-                    if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
-                }
-            }
-            uint32_t mid;
-            if (bestAxis < 0)
-                mid = first + count / 2;        // all centroids coincide: split by index
-            else
-            {
-                const float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
-                auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t t) {
-                    int b = (int)((centroid[t * 3 + bestAxis] - cb.lo[bestAxis]) / ext * NB);
-                    b = std::min(std::max(b, 0), NB - 1);
-                    return b <= bestSplit;
-                });
-                mid = (uint32_t)(it - order.begin());
-                if (mid == first || mid == first + count)
-                    mid = first + count / 2;
-            }
-            const int l = build(first, mid - first);
-            const int r = build(mid, first + count - mid);
-            nodes[idx].left = l; nodes[idx].right = r;
-            return idx;
-        }
-    };
-
-    struct WideOut
-    {
-        std::vector<BVH8Node> nodes;
-        std::vector<uint32_t> leafOrder;     // global tri index per slot in leaf order
-        uint32_t maxDepth = 0;
-    };
-
-    void emit_wide(const Builder& b, int binIdx, uint32_t outIdx, WideOut& out, uint32_t depth)
-    {
-        out.maxDepth = std::max(out.maxDepth, depth);
-        // gather up to 8 children by repeatedly opening the child with the largest area
-        std::vector<int> kids;
-        const BNode& root = b.nodes[binIdx];
-        if (root.left < 0) kids.push_back(binIdx);
-        else { kids.push_back(root.left); kids.push_back(root.right); }
-        while (kids.size() < 8)
-        {
-            int bestK = -1; float bestA = -1;
-            for (size_t k = 0; k < kids.size(); k++)
-            {
-                const BNode& c = b.nodes[kids[k]];
-                if (c.left < 0) continue;
-                const float a = c.box.area();
-                if (a > bestA) { bestA = a; bestK = (int)k; }
-            }
-            if (bestK < 0) break;
-            const BNode c = b.nodes[kids[bestK]];
-            kids[bestK] = c.left;
-            kids.push_back(c.right);
-        }
-        BVH8Node n;
-        memset(&n, 0, sizeof(n));
-        const AABB& box = root.box;
-        n.px = box.lo[0]; n.py = box.lo[1]; n.pz = box.lo[2];
-        uint8_t* ex[3] = { &n.ex, &n.ey, &n.ez };
-        float scale[3];
-        for (int a = 0; a < 3; a++)
-        {
-            const float ext = std::max(box.hi[a] - box.lo[a], 1e-30f);
-            int e = (int)std::ceil(std::log2(ext / 255.0f));
-            // make sure 255 * 2^e covers the extent even after rounding
-            while (std::ldexp(255.0f, e) < ext) e++;
-            e = std::min(std::max(e, -126), 127);
-            *ex[a] = (uint8_t)(e + 127);
-            scale[a] = std::ldexp(1.0f, e);
-        }
-        // internal children first get contiguous node slots
-        std::vector<int> internalKids, leafKids;
-        for (int k : kids) (b.nodes[k].left < 0 ? leafKids : internalKids).push_back(k);
-        n.childBase = (uint32_t)out.nodes.size();
-        n.triBase = (uint32_t)out.leafOrder.size();
-        const uint32_t childBase = n.childBase;
-        out.nodes.resize(out.nodes.size() + internalKids.size());
-        int slot = 0;
-        uint32_t triOff = 0, intOff = 0;
-        std::vector<std::pair<int, uint32_t>> recurse;
-        auto quant = [&](const AABB& cb, int c) {
-            const float org[3] = { n.px, n.py, n.pz };
-            for (int a = 0; a < 3; a++)
-            {
-                float lo = std::floor((cb.lo[a] - org[a]) / scale[a]);
-                float hi = std::ceil((cb.hi[a] - org[a]) / scale[a]);
-                // guard against rounding of the division itself
-                while (lo > 0 && org[a] + lo * scale[a] > cb.lo[a]) lo -= 1;
-                while (hi < 255 && org[a] + hi * scale[a] < cb.hi[a]) hi += 1;
-                lo = std::min(std::max(lo, 0.0f), 255.0f);
-                hi = std::min(std::max(hi, 0.0f), 255.0f);
-                n.qlo[a][c] = (uint8_t)lo;
-                n.qhi[a][c] = (uint8_t)hi;
-            }
-        };
-        for (int k : internalKids)
-        {
-            n.meta[slot] = (uint8_t)(0x20u | intOff);
-            quant(b.nodes[k].box, slot);
-            recurse.push_back({ k, childBase + intOff });
-            intOff++; slot++;
-        }
-        for (int k : leafKids)
-        {
-            const BNode& c = b.nodes[k];
-            n.meta[slot] = (uint8_t)((c.count << 6) | triOff);
-            quant(c.box, slot);
-            for (uint32_t i = 0; i < c.count; i++)
-                out.leafOrder.push_back(b.order[c.first + i]);
-            triOff += c.count; slot++;
-        }
-        out.nodes[outIdx] = n;
-        for (auto& r : recurse)
-            emit_wide(b, r.first, r.second, out, depth + 1);
-    }
-
     std::string asset_path(const char* name)
     {
         Dl_info info;
@@ -334,29 +152,14 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
     cudaFree(d_wt);
     if (e != cudaSuccess) { zr_scene_destroy(sc); return cuda_fail(e, "world triangles"); }
 
-    Builder b;
-    b.triBox.resize(total); b.centroid.resize((size_t)total * 3); b.order.resize(total);
-    for (uint32_t i = 0; i < total; i++)
+    BvhBuild w;
+    build_bvh8(wt.data(), total, w);
+    if (w.maxStack > (uint32_t)BVH_STACK_ENTRIES)
     {
-        const float* t = &wt[(size_t)i * 9];
-        float p[3][3];
-        for (int a = 0; a < 3; a++) { p[0][a] = t[a]; p[1][a] = t[a] + t[3 + a]; p[2][a] = t[a] + t[6 + a]; }
-        AABB bx; bx.reset();
-        for (int k = 0; k < 3; k++) bx.grow(p[k]);
-        for (int a = 0; a < 3; a++)
-        {
-            const float pad = 4e-7f * std::max(std::max(std::fabs(bx.lo[a]), std::fabs(bx.hi[a])), 1.0f);
-            bx.lo[a] -= pad; bx.hi[a] += pad;
-            b.centroid[(size_t)i * 3 + a] = 0.5f * (bx.lo[a] + bx.hi[a]);
-        }
-        b.triBox[i] = bx;
-        b.order[i] = i;
+        set_error("zr_scene_create: the BVH needs a traversal stack of %u entries, the kernels hold %d", w.maxStack, BVH_STACK_ENTRIES);
+        zr_scene_destroy(sc);
+        return ZR_ERR_INVALID_ARG;
     }
-    b.nodes.reserve((size_t)total * 2);
-    b.build(0, total);
-    WideOut w;
-    w.nodes.resize(1);
-    emit_wide(b, 0, 0, w, 1);
     std::vector<float4> tris((size_t)total * 3);
     for (uint32_t s = 0; s < total; s++)
     {
@@ -377,6 +180,7 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
     sc->info.numNodes = (uint32_t)w.nodes.size();
     sc->info.numTris = total;
     sc->info.maxDepth = w.maxDepth;
+    sc->info.maxStack = w.maxStack;
     sc->info.bytes = (uint32_t)(w.nodes.size() * sizeof(BVH8Node) + tris.size() * sizeof(float4));
 
     // alias table storage (built by zr_prelighting_render)
@@ -405,6 +209,21 @@ extern "C"
         if (sc->d_sampleSets) cudaFree(sc->d_sampleSets);
         if (sc->d_lvg) cudaFree(sc->d_lvg);
         delete sc;
+    }
+    zr_status zr_bvh_build_host(const float* h_world_tris, uint32_t num_tris, void* h_nodes, uint32_t node_capacity,
+        uint32_t* h_leaf_order, uint32_t out_info[4])
+    {
+        if (!h_world_tris || !out_info || num_tris == 0) { zr::set_error("zr_bvh_build_host: null argument"); return ZR_ERR_INVALID_ARG; }
+        zr::BvhBuild w;
+        zr::build_bvh8(h_world_tris, num_tris, w);
+        out_info[0] = (uint32_t)w.nodes.size(); out_info[1] = num_tris; out_info[2] = w.maxDepth; out_info[3] = w.maxStack;
+        if (h_nodes)
+        {
+            if (node_capacity < w.nodes.size()) { zr::set_error("zr_bvh_build_host: %zu nodes, capacity %u", w.nodes.size(), node_capacity); return ZR_ERR_INVALID_ARG; }
+            memcpy(h_nodes, w.nodes.data(), w.nodes.size() * sizeof(zr::BVH8Node));
+        }
+        if (h_leaf_order) memcpy(h_leaf_order, w.leafOrder.data(), (size_t)num_tris * sizeof(uint32_t));
+        return ZR_OK;
     }
     zr_status zr_scene_bvh_stats(const zr_scene* sc, uint32_t out[4])
     {

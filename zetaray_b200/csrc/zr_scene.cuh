@@ -11,21 +11,10 @@
 // independent of traversal order.
 #pragma once
 #include "zr_common.cuh"
+#include "zr_bvh.h"
 
 namespace zr
 {
-struct BVH8Node
-{
-    float px, py, pz;
-    uint8_t ex, ey, ez, pad;
-    uint32_t childBase;
-    uint32_t triBase;
-    uint8_t meta[8];        // bits 7..6: #tris of a leaf child (0 = not a leaf), bit 5: internal child, bits 4..0: offset
-    uint8_t qlo[3][8];
-    uint8_t qhi[3][8];
-};
-static_assert(sizeof(BVH8Node) == 80, "BVH8Node must be 80 bytes");
-
 struct SceneDev
 {
     const zr_vertex* vertices;
@@ -84,7 +73,7 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
     RayHit best;
     best.hit = false; best.t = tmax; best.bary = f2(0, 0); best.tri = 0xffffffffu;
     const float3 invd = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    uint32_t stack[48];
+    uint32_t stack[BVH_STACK_ENTRIES];
     int sp = 0;
     stack[sp++] = 0;
     while (sp > 0)
@@ -167,7 +156,7 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
             childT[j + 1] = kt; childNode[j + 1] = kn;
         }
         for (int i = 0; i < nPush; i++)
-            if (sp < 48) stack[sp++] = childNode[i];
+            if (sp < BVH_STACK_ENTRIES) stack[sp++] = childNode[i];      // never drops: scene creation checked BvhBuild::maxStack
     }
     return best;
 }
@@ -235,7 +224,7 @@ ZR_D VertexD LoadVertex(const SceneDev& sc, uint32_t idx)
 }
 
 // host side (scene.cu)
-struct SceneHostInfo { uint32_t numNodes, numTris, maxDepth, bytes; };
+struct SceneHostInfo { uint32_t numNodes, numTris, maxDepth, bytes, maxStack; };
 } // namespace zr
 
 struct zr_scene

@@ -362,6 +362,22 @@ class Renderer:
     def Render(self, fc, stream=None):
         check(lib.zr_renderer_render(self.handle, C.byref(fc), stream))
 
+    RESTIR_GI, RESTIR_PT = 1, 2
+
+    def SetMethod(self, integrator):
+        """IndirectLighting::SetMethod as the renderer calls it (DefaultRenderer.cpp:243)."""
+        check(lib.zr_renderer_set_integrator(self.handle, int(integrator)))
+        if integrator == self.RESTIR_GI:
+            h = C.c_void_p()
+            check(lib.zr_renderer_get_gi_pass(self.handle, C.byref(h)))
+            self.gi = _Borrowed(IndirectLightingGI, h)
+
+    def ApplySceneSettings(self, use_lvg=False):
+        """The reference's host decision: presampled sets iff >= 13107 emissive triangles, LVG only with them."""
+        out = (C.c_uint32 * 2)()
+        check(lib.zr_renderer_apply_scene_settings(self.handle, int(use_lvg), out))
+        return bool(out[0]), bool(out[1])
+
     def GetOutput(self):
         img = _lib.Image2D()
         check(lib.zr_renderer_get_output(self.handle, C.byref(img)))

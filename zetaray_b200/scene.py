@@ -103,7 +103,7 @@ def emissive_triangle(v0, v1, v2, uv0, uv1, uv2, factor_rgb8, strength_half_bits
     v0 = np.asarray(v0, dtype=np.float32); v1 = np.asarray(v1, dtype=np.float32); v2 = np.asarray(v2, dtype=np.float32)
     e["Vtx0"] = v0
     e0 = (v1 - v0).astype(np.float32); e1 = (v2 - v0).astype(np.float32)
-    l0 = np.sqrt(np.float32(np.dot(e0, e0))); l1 = np.sqrt(np.float32(np.dot(e1, e1)))
+    l0 = np.sqrt((e0[0] * e0[0] + e0[1] * e0[1]) + e0[2] * e0[2]); l1 = np.sqrt((e1[0] * e1[0] + e1[1] * e1[1]) + e1[2] * e1[2])
     e["V0V1"] = oct_encode_unorm16(e0 / l0)[0]
     e["V0V2"] = oct_encode_unorm16(e1 / l1)[0]
     e["EdgeLengths"] = half_bits([l0, l1])
@@ -112,6 +112,43 @@ def emissive_triangle(v0, v1, v2, uv0, uv1, uv2, factor_rgb8, strength_half_bits
     e["PackedB"] = INVALID_ID | (int(strength_half_bits) << 16)
     e["UV0"] = half_bits(uv0); e["UV1"] = half_bits(uv1); e["UV2"] = half_bits(uv2)
     return e
+
+
+def emissive_triangles(v0, v1, v2, uv0, uv1, uv2, factor_rgb8, strength_half_bits, tri_ids, double_sided):
+    """Batch form of emissive_triangle (same arithmetic, n triangles at once)."""
+    v0 = np.asarray(v0, dtype=np.float32).reshape(-1, 3); v1 = np.asarray(v1, dtype=np.float32).reshape(-1, 3)
+    v2 = np.asarray(v2, dtype=np.float32).reshape(-1, 3)
+    n = len(v0)
+    e = np.zeros(n, dtype=EMISSIVE_TRI)
+    e["Vtx0"] = v0
+    e0 = (v1 - v0).astype(np.float32); e1 = (v2 - v0).astype(np.float32)
+    l0 = np.sqrt((e0[:, 0] * e0[:, 0] + e0[:, 1] * e0[:, 1]) + e0[:, 2] * e0[:, 2])
+    l1 = np.sqrt((e1[:, 0] * e1[:, 0] + e1[:, 1] * e1[:, 1]) + e1[:, 2] * e1[:, 2])
+    e["V0V1"] = oct_encode_unorm16(e0 / l0[:, None])
+    e["V0V2"] = oct_encode_unorm16(e1 / l1[:, None])
+    e["EdgeLengths"] = np.stack([half_bits(l0), half_bits(l1)], axis=1)
+    e["ID"] = np.asarray(tri_ids, dtype=np.uint32)
+    e["PackedA"] = (factor_rgb8 & 0xffffff) | (1 << 24) | ((1 << 25) if double_sided else 0) | ((int(strength_half_bits) & 0xf) << 28)
+    e["PackedB"] = INVALID_ID | (int(strength_half_bits) << 16)
+    e["UV0"] = half_bits(uv0).reshape(-1, 2); e["UV1"] = half_bits(uv1).reshape(-1, 2); e["UV2"] = half_bits(uv2).reshape(-1, 2)
+    return e
+
+
+def pcg3d_np(x, y, z):
+    """pcg3d over uint32 arrays."""
+    x = np.asarray(x, dtype=np.uint64); y = np.asarray(y, dtype=np.uint64); z = np.asarray(z, dtype=np.uint64)
+    m = np.uint64(0xffffffff); a = np.uint64(1664525); c = np.uint64(1013904223); s16 = np.uint64(16)
+    x = (x * a + c) & m; y = (y * a + c) & m; z = (z * a + c) & m
+    x = (x + y * z) & m; y = (y + z * x) & m; z = (z + x * y) & m
+    x ^= x >> s16; y ^= y >> s16; z ^= z >> s16
+    x = (x + y * z) & m; y = (y + z * x) & m; z = (z + x * y) & m
+    return x.astype(np.uint32), y.astype(np.uint32), z.astype(np.uint32)
+
+
+def quat_rotate_np(q, v):
+    q = np.asarray(q, dtype=np.float64); v = np.asarray(v, dtype=np.float64)
+    t = np.cross(2.0 * q[:3], v)
+    return v + q[3] * t + np.cross(q[:3], t)
 
 
 class FlatScene:
@@ -154,6 +191,7 @@ class SceneBuilder:
         self.nv = 0
         self.ni = 0
         self.nem = 0
+        self.geo = {}
 
     def add_material(self, mat):
         self.mats.append(mat)
@@ -172,9 +210,30 @@ class SceneBuilder:
         vb["uv"] = uvs
         vb["normal"] = oct_encode_unorm16(normals)
         vb["tangent"] = oct_encode_unorm16(tangents if tangents is not None else np.tile([1.0, 0, 0], (n, 1)))
+        inst = self._instance(self.nv, self.ni, mat_idx, translation, rotation, scale)
+        ntri = len(indices) // 3
+        geo_idx = len(self.inst)
+        self._emit_emissives(inst, mat_idx, positions, uvs, indices, geo_idx)
+        self.v.append(vb); self.i.append(indices); self.inst.append(inst); self.ntris.append(ntri)
+        self.geo[geo_idx] = (int(inst["BaseVtxOffset"]), int(inst["BaseIdxOffset"]), positions, uvs, indices)
+        self.nv += n
+        self.ni += len(indices)
+        return geo_idx
+
+    def add_instance_of(self, geo_idx, mat_idx, translation=(0, 0, 0), rotation=(0, 0, 0, 1), scale=(1, 1, 1)):
+        """Another instance of an already added mesh: same vertex / index range, its own transform and material
+        (RT::MeshInstance only stores offsets into the shared buffers, RtCommon.h:47-64)."""
+        bv, bi, positions, uvs, indices = self.geo[geo_idx]
+        inst = self._instance(bv, bi, mat_idx, translation, rotation, scale)
+        new_idx = len(self.inst)
+        self._emit_emissives(inst, mat_idx, positions, uvs, indices, new_idx)
+        self.inst.append(inst); self.ntris.append(len(indices) // 3)
+        return new_idx
+
+    def _instance(self, base_vtx, base_idx, mat_idx, translation, rotation, scale):
         inst = np.zeros(1, dtype=MESH_INSTANCE)[0]
-        inst["BaseVtxOffset"] = self.nv
-        inst["BaseIdxOffset"] = self.ni
+        inst["BaseVtxOffset"] = base_vtx
+        inst["BaseIdxOffset"] = base_idx
         q = np.asarray(rotation, dtype=np.float64)
         q = q / np.linalg.norm(q)
         inst["Rotation"] = _unorm(q * 0.5 + 0.5, 16).astype(np.uint16)
@@ -186,33 +245,29 @@ class SceneBuilder:
         inst["dTranslation"] = half_bits([0, 0, 0])
         inst["BaseColorTex"] = 0xffff
         inst["AlphaFactor_Cutoff"] = 0xffff       # cutoff = 1.0 -> opaque (GBufferRT_Inline.hlsl:41-43)
+        return inst
+
+    def _emit_emissives(self, inst, mat_idx, positions, uvs, indices, geo_idx):
         mat = self.mats[mat_idx]
         ef = int(mat["EmissiveFactor_NormalScale"]) & 0xffffff
-        emissive = ef != 0
-        ntri = len(indices) // 3
-        geo_idx = len(self.inst)
-        if emissive:
-            inst["BaseEmissiveTriOffset"] = self.nem
-            strength = int(mat["EmissiveStrength_IOR"]) & 0xffff
-            ds = bool(int(mat["CoatColor_Flags"]) & (1 << 25))
-            # same arithmetic the shaders use for world positions: quantised rotation/scale
-            qd = (inst["Rotation"].astype(np.float64) / 65535.0) * 2.0 - 1.0
-            qd = qd / np.linalg.norm(qd)
-            sd = inst["Scale"].view(np.float16).astype(np.float64)
-            td = inst["Translation"].astype(np.float64)
-            for t in range(ntri):
-                ids = indices[3 * t:3 * t + 3]
-                pw = [quat_rotate(qd, positions[k].astype(np.float64) * sd) + td for k in ids]
-                tri_id = pcg3d(geo_idx, 0, t)[0]
-                self.em.append(emissive_triangle(pw[0], pw[1], pw[2], uvs[ids[0]], uvs[ids[1]], uvs[ids[2]], ef,
-                                                 strength, tri_id, ds))
-            self.nem += ntri
-        else:
+        if ef == 0:
             inst["BaseEmissiveTriOffset"] = 0xffffffff
-        self.v.append(vb); self.i.append(indices); self.inst.append(inst); self.ntris.append(ntri)
-        self.nv += n
-        self.ni += len(indices)
-        return geo_idx
+            return
+        ntri = len(indices) // 3
+        inst["BaseEmissiveTriOffset"] = self.nem
+        strength = int(mat["EmissiveStrength_IOR"]) & 0xffff
+        ds = bool(int(mat["CoatColor_Flags"]) & (1 << 25))
+        # same arithmetic the shaders use for world positions: quantised rotation/scale
+        qd = (inst["Rotation"].astype(np.float64) / 65535.0) * 2.0 - 1.0
+        qd = qd / np.linalg.norm(qd)
+        sd = inst["Scale"].view(np.float16).astype(np.float64)
+        td = inst["Translation"].astype(np.float64)
+        pw = quat_rotate_np(qd, positions.astype(np.float64) * sd) + td
+        tri = indices.reshape(-1, 3)
+        ids = pcg3d_np(np.full(ntri, geo_idx), np.zeros(ntri), np.arange(ntri))[0]
+        self.em.append(emissive_triangles(pw[tri[:, 0]], pw[tri[:, 1]], pw[tri[:, 2]], uvs[tri[:, 0]], uvs[tri[:, 1]],
+                                          uvs[tri[:, 2]], ef, strength, ids, ds))
+        self.nem += ntri
 
     def finish(self):
         s = FlatScene()
@@ -221,7 +276,7 @@ class SceneBuilder:
         s.instances = np.array(self.inst, dtype=MESH_INSTANCE)
         s.instance_num_tris = np.array(self.ntris, dtype=np.uint32)
         s.materials = np.array(self.mats, dtype=MATERIAL)
-        s.emissives = np.array(self.em, dtype=EMISSIVE_TRI) if self.em else np.zeros(0, dtype=EMISSIVE_TRI)
+        s.emissives = np.concatenate(self.em) if self.em else np.zeros(0, dtype=EMISSIVE_TRI)
         return s
 
 
