@@ -81,7 +81,7 @@ def _frames(which, w, h, nframes, rpt_params=None, cam_path=None, with_di=True):
 
 
 def test_atrium_whole_frame():
-    problems, R = _frames("atrium", 160, 90, 3)
+    problems, R = _frames("atrium", 240, 135, 3)
     assert not problems, "\n".join(problems)
     res = R.curr_reservoirs()
     k = res["meta"] & 0xf
@@ -94,7 +94,7 @@ def test_tunnel_five_bounces_two_spatial_passes_moving_camera():
     """Config C5's parameters: 5 non-transmissive bounces (the wave-wide Russian roulette runs), 2 spatial passes; the
     camera walks down the platform so temporal reprojection and the TAA history taps move."""
     path = lambda f: (-1.6 + 0.01 * f, 1.7, -4.0 + 0.05 * f)
-    problems, R = _frames("tunnel", 144, 80, 4, rpt_params=dict(max_non_tr_bounces=5, max_glossy_tr_bounces=5, num_spatial_passes=2),
+    problems, R = _frames("tunnel", 192, 108, 4, rpt_params=dict(max_non_tr_bounces=5, max_glossy_tr_bounces=5, num_spatial_passes=2),
                           cam_path=path)
     assert not problems, "\n".join(problems)
 

@@ -31,8 +31,11 @@ def _orient(pos, nrm, idx):
     return np.ascontiguousarray(t).reshape(-1).astype(np.uint32)
 
 
-def patch(f, nu, nv, flip=False, uv_scale=(1.0, 1.0)):
-    """Parametric surface f(U, V) -> (..., 3) over [0,1]^2 with nu x nv quads; normals from central differences."""
+def patch(f, nu, nv, flip=False, uv_scale=(1.0, 1.0), toward=None, away=None):
+    """Parametric surface f(U, V) -> (..., 3) over [0,1]^2 with nu x nv quads; normals from central differences.
+    toward / away: a point (or an array of points shaped like the surface) the front faces must look at / away from --
+    single-sided materials are invisible from behind (GetMaterialData, RayQuery.hlsli:452-470), so every mesh states
+    which way it faces instead of relying on the parametrisation's handedness."""
     nu = max(int(nu), 1); nv = max(int(nv), 1)
     u = np.linspace(0.0, 1.0, nu + 1); v = np.linspace(0.0, 1.0, nv + 1)
     U, V = np.meshgrid(u, v, indexing="ij")
@@ -46,6 +49,11 @@ def patch(f, nu, nv, flip=False, uv_scale=(1.0, 1.0)):
     N = N / ln
     if flip:
         N = -N
+    if toward is not None or away is not None:
+        ref = np.asarray(toward if toward is not None else away, dtype=np.float64)
+        d = np.einsum("...k,...k->...", N, ref - P).mean()
+        if (d < 0) == (toward is not None):
+            N = -N
     i = (np.arange(nu)[:, None] * (nv + 1) + np.arange(nv)[None, :]).reshape(-1)
     quads = np.stack([i, i + nv + 1, i + nv + 2, i, i + nv + 2, i + 1], axis=1).reshape(-1)
     pos = P.reshape(-1, 3).astype(F32); nrm = N.reshape(-1, 3).astype(F32)
@@ -160,9 +168,9 @@ def atrium(detail=1.0, lamp_tris=None):
     d = detail
     # floor: gently uneven flagstones
     b.add_mesh(*patch(lambda U, V: np.stack([(U * 2 - 1) * X, 0.012 * np.sin(37 * U) * np.sin(53 * V), (V * 2 - 1) * Z], -1),
-                      _n(d, 90), _n(d, 160), uv_scale=(9, 16)), M["floor"])
+                      _n(d, 90), _n(d, 160), uv_scale=(9, 16), toward=(0.0, 1000.0, 0.0)), M["floor"])
     # ceiling
-    b.add_mesh(*patch(lambda U, V: np.stack([(U * 2 - 1) * X, Y + 0 * U, (V * 2 - 1) * Z], -1), _n(d, 24), _n(d, 40), flip=True), M["ceiling"])
+    b.add_mesh(*patch(lambda U, V: np.stack([(U * 2 - 1) * X, Y + 0 * U, (V * 2 - 1) * Z], -1), _n(d, 24), _n(d, 40), toward=(0.0, -1000.0, 0.0)), M["ceiling"])
     # walls with a brick-like relief; normals face inwards
     def wall_x(sx):
         return lambda U, V: np.stack([sx * (X + 0.03 * np.cos(60 * np.pi * U) * np.cos(25 * np.pi * V)) , V * Y, (U * 2 - 1) * Z], -1)
@@ -223,7 +231,11 @@ def atrium(detail=1.0, lamp_tris=None):
         c = 2.0 * np.pi * V
         R = 1.75
         return np.stack([r * np.cos(c), R * np.sin(a) + r * np.sin(c) * np.sin(a), -R * np.cos(a) - r * np.sin(c) * np.cos(a)], -1)
-    am = patch(arch, _n(d, 40, 4), _n(d, 12, 3))
+    def arch_axis(U, V):
+        a = np.pi * U
+        return np.stack([0 * a, 1.75 * np.sin(a), -1.75 * np.cos(a)], -1)
+    _u, _v = np.meshgrid(np.linspace(0, 1, _n(d, 40, 4) + 1), np.linspace(0, 1, _n(d, 12, 3) + 1), indexing="ij")
+    am = patch(arch, _n(d, 40, 4), _n(d, 12, 3), away=arch_axis(_u, _v))
     g_arch = None
     for side in (-1.0, 1.0):
         for k in range(ncol - 1):
@@ -282,7 +294,7 @@ def atrium(detail=1.0, lamp_tris=None):
             b.add_instance_of(g_l[c], M["lamp%d" % c], (x, y, z), _quat_y(0.4 * k))
     # two emissive ceiling panels (large area lights)
     for z in (-7.0, 7.0):
-        p, n, uv, i = patch(lambda U, V, z=z: np.stack([(U * 2 - 1) * 2.0, Y - 0.05 + 0 * U, z + (V * 2 - 1) * 3.0], -1), _n(d, 6), _n(d, 8), flip=True)
+        p, n, uv, i = patch(lambda U, V, z=z: np.stack([(U * 2 - 1) * 2.0, Y - 0.05 + 0 * U, z + (V * 2 - 1) * 3.0], -1), _n(d, 6), _n(d, 8), toward=(0.0, -1000.0, z))
         b.add_mesh(p, n, uv, i, M["panel"])
     return b.finish()
 
@@ -344,14 +356,14 @@ def tunnel(detail=1.0):
         b.add_mesh(p, n, uv, i, M["concrete"])
     # platform (x < 0.4) and track bed (x > 0.4), both tessellated
     b.add_mesh(*patch(lambda U, V: np.stack([-W + (W + 0.4) * U, 1.05 + 0.004 * np.cos(2 * np.pi * 10 * U) * np.cos(2 * np.pi * (Z0 + L * V) / 0.6),
-                                             Z0 + L * V], -1), _n(d, 64), _n(d, 900)), M["platform"])
+                                             Z0 + L * V], -1), _n(d, 64), _n(d, 900), toward=(0.0, 1000.0, 50.0)), M["platform"])
     b.add_mesh(*box((0.35, 0.02, L), (0.1, 1.065, 0.5 * (Z0 + Z1))), M["yellow"])
     b.add_mesh(*box((0.1, 1.05, L), (0.45, 0.525, 0.5 * (Z0 + Z1))), M["concrete"])
     def bed(U, V):
         z = Z0 + L * V
         h = 0.5 + 0.25 * np.sin(41.0 * U + 3.1 * z) * np.cos(17.3 * z) + 0.25 * np.sin(23.0 * U - 7.7 * z)
         return np.stack([0.5 + (W - 0.5) * U, 0.02 + 0.05 * h, z], -1)
-    b.add_mesh(*patch(bed, _n(d, 70), _n(d, 1400)), M["ballast"])
+    b.add_mesh(*patch(bed, _n(d, 70), _n(d, 1400), toward=(3.0, 1000.0, 50.0)), M["ballast"])
     # rails and sleepers
     for x in (2.3, 3.8):
         b.add_mesh(*box((0.08, 0.16, L), (x, 0.26, 0.5 * (Z0 + Z1))), M["rail"])
