@@ -108,6 +108,82 @@ namespace
         out[idx] = f4(ret.x, ret.y, ret.z, 0.0f);
     }
 
+    // Shared-memory-tiled form of the fused compositing + firefly stencil (the product path; k_firefly above stays as the
+    // reference-shaped two-dispatch sequence the tests compare it with). A block owns a 32 x 16 pixel tile: every pixel
+    // of the 34 x 18 halo'd tile is composited ONCE (1.2 composites per output pixel instead of 9 -- the untiled kernel
+    // re-composites each tap, 27 IEEE divisions per pixel, and is issue-bound, not bandwidth-bound), its luminance and
+    // "has geometry" flag are staged next to it, and the 3 x 3 min / max search then runs out of shared memory in the
+    // same tap order, so the result is bit-identical. Rows are read as contiguous 34-pixel segments (coalesced 128-bit loads).
+    constexpr int FF_TW = 32, FF_TH = 16, FF_SW = FF_TW + 2, FF_SH = FF_TH + 2;
+    template<bool Fused>
+    __global__ void __launch_bounds__(FF_TW * FF_TH) k_firefly_tiled(const uint4* __restrict__ core, const float* __restrict__ depth,
+        const float4* __restrict__ inOrDirect, const float4* __restrict__ indirect, float4* __restrict__ out, PostParams p)
+    {
+        __shared__ float4 tile[FF_SH][FF_SW];           // xyz = (composited) colour, w = its luminance
+        __shared__ uint8_t geom[FF_SH][FF_SW];          // 1 = inside the image and depth != FLT_MAX
+        const int W = (int)p.W, H = (int)p.H;
+        const int x0 = blockIdx.x * FF_TW;
+        const int y0 = (int)p.rowBegin + blockIdx.y * FF_TH;
+        for (int e = threadIdx.x; e < FF_SW * FF_SH; e += FF_TW * FF_TH)
+        {
+            const int ty = e / FF_SW, tx = e - ty * FF_SW;
+            const int gx = x0 - 1 + tx, gy = y0 - 1 + ty;
+            float4 v = f4(0.0f, 0.0f, 0.0f, 0.0f);
+            uint8_t g = 0;
+            if ((uint32_t)gx < (uint32_t)W && (uint32_t)gy < (uint32_t)H)
+            {
+                const size_t i = (size_t)gy * W + gx;
+                float3 c;
+                if (Fused)
+                    c = composite_px(core, inOrDirect, indirect, i, p);
+                else
+                {
+                    const float4 c4 = __ldg(&inOrDirect[i]);
+                    c = f3(c4.x, c4.y, c4.z);
+                }
+                v = f4(c.x, c.y, c.z, Math::Luminance(c));
+                g = __ldg(&depth[i]) != FLT_MAX_ ? 1 : 0;
+            }
+            tile[ty][tx] = v;
+            geom[ty][tx] = g;
+        }
+        __syncthreads();
+        const int lx = threadIdx.x & (FF_TW - 1), ly = threadIdx.x / FF_TW;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x >= W || y >= (int)p.rowEnd) return;
+        const size_t idx = (size_t)y * W + x;
+        const float4 c4 = tile[ly + 1][lx + 1];
+        const float3 currColor = f3(c4.x, c4.y, c4.z);
+        if (!geom[ly + 1][lx + 1])
+        {
+            out[idx] = f4(currColor.x, currColor.y, currColor.z, 0.0f);
+            return;
+        }
+        float minLum = FLT_MAX_;
+        float maxLum = 0.0f;
+        float3 minColor = currColor;
+        float3 maxColor = f3(0);
+        const float currLum = c4.w;
+#pragma unroll
+        for (int i = -1; i <= 1; i++)
+        {
+#pragma unroll
+            for (int j = -1; j <= 1; j++)
+            {
+                if (i == 0 && j == 0) continue;
+                if (!geom[ly + 1 + i][lx + 1 + j]) continue;
+                const float4 n4 = tile[ly + 1 + i][lx + 1 + j];
+                const float3 neighborColor = f3(n4.x, n4.y, n4.z);
+                const float neighborLum = n4.w;
+                if (neighborLum < minLum) { minLum = neighborLum; minColor = neighborColor; }
+                else if (neighborLum > maxLum) { maxLum = neighborLum; maxColor = neighborColor; }
+            }
+        }
+        float3 ret = currLum < minLum ? minColor : (currLum > maxLum ? maxColor : currColor);
+        ret = minLum <= maxLum ? ret : currColor;
+        out[idx] = f4(ret.x, ret.y, ret.z, 0.0f);
+    }
+
     ZR_D float Mitchell1D(float x, float B, float C)
     {
         x = fabsf(2.0f * x);
@@ -322,8 +398,9 @@ struct zr_compositing_pass
         SetRows(p, grid);
         if (params.firefly_filter)
         {
+            const dim3 tgrid((width + FF_TW - 1) / FF_TW, (p.rowEnd - p.rowBegin + FF_TH - 1) / FF_TH);
             ZR_PROF("k_firefly", stream);
-            k_firefly<true><<<grid, 256, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
+            k_firefly_tiled<true><<<tgrid, FF_TW * FF_TH, 0, stream>>>((const uint4*)in->curr.d_core, (const float*)in->curr.d_depth,
                 direct, indirect, d_composited, p);
             ZR_LAUNCH_CHECK();
         }
