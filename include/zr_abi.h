@@ -515,6 +515,11 @@ ZR_API zr_status zr_gi_pass_resize(zr_gi_pass* p, uint32_t width, uint32_t heigh
 ZR_API zr_status zr_gi_pass_reset_temporal(zr_gi_pass* p);
 ZR_API zr_status zr_gi_pass_default_params(zr_gi_params* out);
 ZR_API zr_status zr_gi_pass_set_params(zr_gi_pass* p, const zr_gi_params* params);
+/* The integrators of IndirectLighting.h's INTEGRATOR enum. PATH_TRACING (IndirectLighting/PathTracer/PathTracer.hlsl: MIS next-event
+ * estimation at every bounce, exact shadow rays, Beer's law in translucent media, no reuse -- the in-repo ground truth) and
+ * ReSTIR GI run on this pass object (both read cb_ReSTIR_GI in the reference); ReSTIR PT is zr_indirect_pass. */
+typedef enum zr_integrator { ZR_INTEGRATOR_PATH_TRACING = 0, ZR_INTEGRATOR_RESTIR_GI = 1, ZR_INTEGRATOR_RESTIR_PT = 2 } zr_integrator;
+ZR_API zr_status zr_gi_pass_set_method(zr_gi_pass* p, zr_integrator method);     /* default RESTIR_GI; a change drops the history */
 ZR_API zr_status zr_gi_pass_render(zr_gi_pass* p, const zr_frame_inputs* in, void* stream);
 ZR_API zr_status zr_gi_pass_get_output(zr_gi_pass* p, zr_gi_output id, zr_image2d* out);
 ZR_API void zr_gi_pass_destroy(zr_gi_pass* p);
@@ -575,8 +580,7 @@ ZR_API zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** gbuffe
     zr_indirect_pass** indirect, zr_compositing_pass** compositing, zr_taa_pass** taa);
 ZR_API zr_status zr_renderer_get_gbuffer(zr_renderer* r, int previous, zr_gbuffer* out);
 /* IndirectLighting::SetMethod(INTEGRATOR) as DefaultRenderer.cpp:243 calls it; values follow IndirectLighting.h's enum
- * (PATH_TRACING 0 is not part of this build). The ReSTIR GI pass object is created on first use. */
-typedef enum zr_integrator { ZR_INTEGRATOR_PATH_TRACING = 0, ZR_INTEGRATOR_RESTIR_GI = 1, ZR_INTEGRATOR_RESTIR_PT = 2 } zr_integrator;
+ * (zr_integrator, declared with the GI pass above). PATH_TRACING and ReSTIR GI share one pass object, created on first use. */
 ZR_API zr_status zr_renderer_set_integrator(zr_renderer* r, zr_integrator method);
 ZR_API zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi);
 /* RenderSettings::LightPresampling / UseLVG as DefaultRenderer::Update derives them from the scene

@@ -94,14 +94,17 @@ namespace
         return surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
     }
 
-    // ReSTIR_GI_NEE.hlsli:8-121 with NumLightSamples = 1, skipDiffuse = true
-    float3 NEE_Emissive_MIS(const Scene& sc, float3 pos, float3 normal, BSDF::ShadingData surface, uint32_t sampleSetIdx, RNG& rng)
+    // ReSTIR_GI_NEE.hlsli:8-121 with NumLightSamples = 1. ReSTIR GI compiles it with skipDiffuse = true
+    // (MIS_NON_DIFFUSE_BSDF_SAMPLING 1) and approximate shadow rays; the plain path tracer with skipDiffuse = false and
+    // APPROXIMATE_EMISSIVE_SHADOW_RAY 0 (PathTracer/Params.hlsli:19-27).
+    float3 NEE_Emissive_MIS(const Scene& sc, float3 pos, float3 normal, BSDF::ShadingData surface, uint32_t sampleSetIdx, RNG& rng,
+        bool skipDiffuse = true, bool preciseShadow = false)
     {
         float3 ld = f3(0);
         const bool specular = IsSpecular(surface);
         const int numLightSamples = specular ? 0 : 1;
         {
-            BSDF::BSDFSample bsdfSample = BSDF::SampleBSDF_NoDiffuse(normal, surface, rng);
+            BSDF::BSDFSample bsdfSample = skipDiffuse ? BSDF::SampleBSDF_NoDiffuse(normal, surface, rng) : BSDF::SampleBSDF(normal, surface, rng);
             float3 wi = bsdfSample.wi;
             float3 f = bsdfSample.f;
             float wiPdf = bsdfSample.pdf;
@@ -140,8 +143,9 @@ namespace
                 surface.SetWi(wi, normal);
                 le *= BSDF::Unified(surface).f * dwdA;
                 if (dot(le, le) > 0)
-                    le *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
-                float bsdfPdf = BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi);
+                    le *= (preciseShadow ? Visibility_Segment_Precise(sc, pos, wi, t, normal, lightID, surface.Transmissive())
+                                         : Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive())) ? 1.0f : 0.0f;
+                float bsdfPdf = skipDiffuse ? BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi) : BSDF::BSDFSamplerPdf(normal, surface, wi, rng);
                 bsdfPdf *= dwdA;
                 ld += RT::PowerHeuristic(lightPdf, bsdfPdf, le, (float)numLightSamples);
             }
@@ -208,8 +212,13 @@ namespace
         return ret;
     }
 
-    float3 NEE(const Scene& sc, const zr_frame_constants& fc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
+    // plainPT: the macro set of IndirectLighting/PathTracer/Params.hlsli -- MIS_ALL_BOUNCES 1, MIS_NON_DIFFUSE_BSDF_SAMPLING 0,
+    // APPROXIMATE_EMISSIVE_SHADOW_RAY 0 (ReSTIR_GI_NEE.hlsli:225-238)
+    float3 NEE(const Scene& sc, const zr_frame_constants& fc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng,
+        bool plainPT = false)
     {
+        if (plainPT)
+            return NEE_Emissive_MIS(sc, pos, normal, surface, sampleSetIdx, rng, false, true);
         if (bounce == 0)
             return NEE_Emissive_MIS(sc, pos, normal, surface, sampleSetIdx, rng);
         if (sc.lvg && sc.sampleSetSize)
@@ -235,12 +244,19 @@ namespace
     };
 
     // loop top .. Russian-roulette point; false = left the loop
-    bool PT_PhaseA(const Scene& sc, const zr_frame_constants& fc, GILane& s)
+    bool PT_PhaseA(const Scene& sc, const zr_frame_constants& fc, GILane& s, bool plainPT = false)
     {
         const float3 hitPos = mad(s.hitInfo.t, s.bsdfSample.wi, s.pos);
         if (!GetMaterialData(sc, -s.bsdfSample.wi, s.eta_curr, s.hitInfo, s.surface, s.eta_next))
             return false;
-        s.li += s.throughput * NEE(sc, fc, hitPos, s.hitInfo.normal, s.surface, s.sampleSetIdx, s.bounce, s.rngThread);
+        s.li += s.throughput * NEE(sc, fc, hitPos, s.hitInfo.normal, s.surface, s.sampleSetIdx, s.bounce, s.rngThread, plainPT);
+        // ACCOUNT_FOR_TRANSMITTANCE == 1 (PathTracing.hlsli:41-48): Beer's law inside a translucent medium
+        if (plainPT && s.inTranslucentMedium && (s.surface.trDepth > 0))
+        {
+            const float3 c = s.surface.baseColor_Fr0_TrCol;
+            const float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / s.surface.trDepth;
+            s.throughput *= f3(zr_expf(-s.hitInfo.t * extCoeff.x), zr_expf(-s.hitInfo.t * extCoeff.y), zr_expf(-s.hitInfo.t * extCoeff.z));
+        }
         if (s.bounce >= (s.maxNumBounces - 1))
             return false;
         s.pos = hitPos;
@@ -529,8 +545,10 @@ namespace
         return a[0];
     }
 
+    // plainPT: IndirectLighting/PathTracer/PathTracer.hlsl (INTEGRATOR::PATH_TRACING): same dispatch shape, RNG seeds and
+    // PathTrace loop, no reservoirs / reuse; main :98-212, EstimateIndirectLighting :58-104
     void RenderPass(const Frame& f, const GIParams& prm, bool doTemporal, bool resetTemporal, zr_rgi_reservoir* resCurr,
-        const zr_rgi_reservoir* resPrev, float4* finalImg, int nthreads)
+        const zr_rgi_reservoir* resPrev, float4* finalImg, int nthreads, bool plainPT = false)
     {
         const zr_frame_constants& fc = *f.fc;
         const Scene& sc = *f.sc;
@@ -565,13 +583,17 @@ namespace
                     s.p = LoadPixel(f, f.core, f.coat, sx, sy, false, sx, sy);
                     const GCore g = LoadCore(f.core, idx);
                     const float3 wo = normalize(s.p.origin - s.p.pos);
+                    if (plainPT)        // PathTracer.hlsl:184-185 also passes flags.trDepthGt0 as the transmission depth
+                        s.surface0 = BSDF::ShadingData::Init(s.p.normal, wo, flags.metallic, g.roughness, f3(g.baseColor.x, g.baseColor.y, g.baseColor.z),
+                            BSDF::ETA_AIR, s.p.eta_next, flags.transmissive, flags.trDepthGt0 ? 1.0f : 0.0f);
+                    else
                     s.surface0 = BSDF::ShadingData::Init(s.p.normal, wo, flags.metallic, g.roughness, f3(g.baseColor.x, g.baseColor.y, g.baseColor.z),
                         BSDF::ETA_AIR, s.p.eta_next, flags.transmissive);
                     s.rngGroup = RNG::Init(sgx ^ 61u, sgy ^ 61u, fc.FrameNum);
                     s.rngThread = RNG::Init(sx ^ 511u, sy ^ 31u, fc.FrameNum);
                     s.maxNumBounces = (int)(flags.transmissive ? prm.maxGlossyTrBounces : prm.maxNonTrBounces);
                     // EstimateIndirectLighting
-                    if (prm.stochasticMultiBounce && (g.roughness >= 0.1f || fc.CameraStatic))
+                    if (!plainPT && prm.stochasticMultiBounce && (g.roughness >= 0.1f || fc.CameraStatic))
                         s.maxNumBounces = s.rngGroup.Uniform() < 0.5f ? 1 : s.maxNumBounces;
                     s.sampleSetIdx = s.rngGroup.UniformUintBounded_Faster(sc.numSampleSets);
                     // RIS_InitialCandidates up to the path-tracing loop
@@ -602,7 +624,7 @@ namespace
                         atRR[l] = false;
                         GILane& s = lanes[l];
                         if (!s.tracing) continue;
-                        if (!PT_PhaseA(sc, fc, s)) { s.tracing = false; continue; }
+                        if (!PT_PhaseA(sc, fc, s, plainPT)) { s.tracing = false; continue; }
                         atRR[l] = true; any = true;
                     }
                     if (!any) break;
@@ -617,6 +639,32 @@ namespace
                     for (int l = 0; l < 32; l++)
                         if (atRR[l] && !PT_PhaseB(sc, lanes[l], doRR, waveMax))
                             lanes[l].tracing = false;
+                }
+                if (plainPT)
+                {
+                    // EstimateIndirectLighting :97-103, main :199-211
+                    for (int l = 0; l < 32; l++)
+                    {
+                        GILane& s = lanes[l];
+                        if (!s.active) continue;
+                        float3 li = f3(0);
+                        if (s.bsdfSample0.pdf != 0 && s.hit0.hit)
+                        {
+                            li = s.li;
+                            if (dot(li, li) > 0)
+                                li *= s.bsdfSample0.bsdfOverPdf;
+                        }
+                        li = isnan3(li) ? f3(0) : li;       // any(isnan(li)) ? 0 : li
+                        const size_t idx = (size_t)s.py * f.W + s.px;
+                        if (fc.Accumulate && fc.CameraStatic)
+                        {
+                            const float4 prev = finalImg[idx];
+                            finalImg[idx] = f4(prev.x + li.x, prev.y + li.y, prev.z + li.z, prev.w);
+                        }
+                        else
+                            finalImg[idx] = f4(li.x, li.y, li.z, finalImg[idx].w);
+                    }
+                    continue;
                 }
                 // rest of RIS_InitialCandidates, temporal reuse
                 float wsum[32];
@@ -692,6 +740,20 @@ namespace
 
 extern "C"
 {
+    // IndirectLighting with INTEGRATOR::PATH_TRACING (IndirectLighting.cpp: RenderPathTracer; PathTracer/PathTracer.hlsl), emissive NEE.
+    // params: the same GIParams words (only the bounce budgets and the Russian-roulette flag are read).
+    void orc_pt_render(void* scene, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* me, const orc::uint2* coat,
+        const uint32_t* params, orc::float4* finalImg, int nthreads)
+    {
+        using namespace orc;
+        Frame f;
+        f.sc = (const Scene*)scene; f.fc = fc; f.core = core; f.me = me; f.coat = coat; f.pcore = core; f.pcoat = coat;
+        f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+        GIParams prm;
+        memcpy(&prm, params, sizeof(prm));
+        RenderPass(f, prm, false, false, nullptr, nullptr, finalImg, nthreads, true);
+    }
+
     // state[0] = currTemporalIdx, state[1] = isTemporalReservoirValid, state[2] = reset flag (IndirectLighting.cpp:277-368, :1021-1024)
     void orc_rgi_render(void* scene, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* me, const orc::uint2* coat,
         const orc::uint4* pcore, const orc::uint2* pcoat, const uint32_t* params /* GIParams */, zr_rgi_reservoir* res0, zr_rgi_reservoir* res1,

@@ -291,6 +291,29 @@ inline bool Visibility_Segment(const Scene& sc, float3 origin, float3 wi, float 
     return !sc.AnyHitExcept(adjustedOrigin, wi, tMin, tMax, triID);
 }
 
+// RayQuery.hlsli:337-406 with APPROXIMATE_EMISSIVE_SHADOW_RAY == 0 (the plain path tracer's setting,
+// IndirectLighting/PathTracer/Params.hlsli:27): tMax = rayT, the committed hit is the closest one, and the light is visible
+// iff nothing is hit or the closest hit is the light itself.
+inline bool Visibility_Segment_Precise(const Scene& sc, float3 origin, float3 wi, float rayT, float3 normal, uint32_t triID,
+    bool transmissive)
+{
+    if (triID == UINT32_MAX_) return false;
+    if (rayT < 1e-6f) return false;
+    float ndotwi = dot(normal, wi);
+    if (ndotwi == 0) return false;
+    bool wiBackface = ndotwi < 0;
+    if (wiBackface)
+    {
+        if (transmissive) normal = -normal;
+        else return false;
+    }
+    const float3 adjustedOrigin = RTU::OffsetRayRTG(origin, normal);
+    const RayHit h = sc.Closest(adjustedOrigin, wi, 3e-6f, rayT);
+    if (h.hit)
+        return triID == sc.TriID(h.tri);
+    return true;
+}
+
 // GetMaterialData (RayQuery.hlsli:452-510), textures unsupported (factors only)
 inline bool GetMaterialData(const Scene& sc, float3 wo, float eta_curr, Hit& hitInfo, BSDF::ShadingData& surface, float& eta)
 {

@@ -125,6 +125,12 @@ class OracleRenderer:
         self.o.orc_rgi_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(p[0]), ptr(p[3]), ptr(prm),
                               ptr(self.gi_res[0]), ptr(self.gi_res[1]), ptr(self.gi_final), ptr(self.gi_state), self.nthreads)
 
+    def pt(self, fc):
+        """IndirectLighting with INTEGRATOR::PATH_TRACING (the plain path tracer); writes gi_final like rgi()."""
+        c = self.gb[self.cur]
+        prm = np.array([self.gi_params[k] for k in GI_PARAM_NAMES], dtype=np.uint32)
+        self.o.orc_pt_render(self.osc.h, C.byref(fc), ptr(c[0]), ptr(c[2]), ptr(c[3]), ptr(prm), ptr(self.gi_final), self.nthreads)
+
     def gi_curr_reservoirs(self):
         return self.gi_res[1 - int(self.gi_state[0])]
 

@@ -145,6 +145,35 @@ def test_restir_pt_mean_matches_plain_path_tracing():
     assert np.all(np.abs(rs - pt) / pt < 0.12), (pt, rs)
 
 
+def test_plain_path_tracer_is_the_ground_truth_for_both_restir_integrators():
+    """the reference's plain path tracer (MIS at every bounce, no reuse) is the in-repo ground truth. ReSTIR PT and
+    ReSTIR GI with all their reuse switched on converge to the same image mean. The comparison uses the median of per-frame
+    means: ReSTIR GI's light-only NEE after the first bounce (MIS_ALL_BOUNCES 0) has a 1 / t^2 tail, so single fireflies
+    move a plain mean by factors."""
+    from tests import scene_util, rpt_util
+    w, h = 128, 72
+
+    def run(mode, nframes=36):
+        R = rpt_util.OracleRenderer(scene_util.cornell(), w, h)
+        R.gi_params.update(stochastic_multi_bounce=0)
+        seq = rpt_util.FrameSequence(w, h)
+        means = []
+        for fr in range(nframes):
+            fc = seq.next(); R.gbuffer(fc)
+            if mode == "pt":
+                R.pt(fc); img = R.gi_final
+            elif mode == "gi":
+                R.rgi(fc); img = R.gi_final
+            else:
+                R.rpt(fc); img = R.final
+            if fr >= 6:
+                means.append(img[:, :3].astype(np.float64).mean(axis=0))
+        return np.median(np.array(means), axis=0)
+    pt, gi, rs = run("pt"), run("gi"), run("rpt")
+    assert np.all(np.abs(rs - pt) / pt < 0.12), (pt, rs)
+    assert np.all(np.abs(gi - pt) / pt < 0.2), (pt, gi)
+
+
 def test_oracle_outputs_are_frozen():
     """The lighting oracle has no external pin; tests/golden/oracle_hashes.json freezes its outputs (tools/make_oracle_hashes.py)
     so that a change to the oracle is a deliberate, visible act."""

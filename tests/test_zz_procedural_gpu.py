@@ -148,7 +148,7 @@ def test_atrium_many_lights_gi_lvg_through_the_renderer():
     flat2, _, sc2, _ = _setup("atrium", 64, 36)
     rd2 = Renderer(sc2, 64, 36)
     assert rd2.ApplySceneSettings(use_lvg=True) == (False, False)
-    assert lib.zr_renderer_set_integrator(rd2.handle, 0) != 0           # the plain path tracer is not part of this build
+    assert lib.zr_renderer_set_integrator(rd2.handle, 7) != 0
     assert b"integrator" in lib.zr_last_error()
 
 

@@ -14,7 +14,8 @@ def run(which, w=96, h=54, nframes=3, presample=None, lvg=None):
         R.osc.set_presampling(*presample)
     if lvg:
         R.osc.set_light_voxel_grid(*lvg)
-    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: (0.02 * f, 1.2, -4.043))
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: (cam[0] + 0.02 * f, cam[1], cam[2]))
     taa_prev = np.zeros((w * h, 2), dtype=np.uint32)
     out = {}
     for i in range(nframes):
@@ -26,6 +27,8 @@ def run(which, w=96, h=54, nframes=3, presample=None, lvg=None):
                                                                  R.curr_reservoirs()["W"].view(np.uint32)])), ("pt_final", R.final),
                       ("gi_reservoirs", R.gi_curr_reservoirs()), ("gi_final", R.gi_final), ("taa", taa_prev)):
         out[name] = hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+    R.pt(fc)        # the plain path tracer on the last frame's G-buffer (overwrites gi_final, hashed above)
+    out["path_tracer_final"] = hashlib.sha256(np.ascontiguousarray(R.gi_final).tobytes()).hexdigest()
     if presample:
         out["sample_sets"] = hashlib.sha256(R.osc.sample_sets[:presample[0] * presample[1] * 10].tobytes()).hexdigest()
     if lvg:
@@ -37,6 +40,9 @@ CASES = {
     "cornell": dict(which="cornell"),
     "glossy": dict(which="glossy"),
     "glass_presampled_lvg": dict(which="glass", presample=(16, 64), lvg=((8, 4, 8), (0.6, 0.45, 0.6), 0.1)),
+    # the procedural C4 / C5 stand-ins (also freezes the scene generators)
+    "atrium": dict(which="atrium", w=80, h=45),
+    "tunnel": dict(which="tunnel", w=80, h=45),
 }
 
 if __name__ == "__main__":

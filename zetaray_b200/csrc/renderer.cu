@@ -27,7 +27,7 @@ struct zr_renderer
     zr_gbuffer_pass* gbufferPass = nullptr;
     zr_direct_pass* direct = nullptr;
     zr_indirect_pass* indirect = nullptr;
-    zr_gi_pass* gi = nullptr;                       // created on the first SetMethod(ReSTIR_GI)
+    zr_gi_pass* gi = nullptr;                       // created on the first SetMethod(ReSTIR_GI / PATH_TRACING)
     zr_integrator integrator = ZR_INTEGRATOR_RESTIR_PT;     // RenderSettings::Indirect default, DefaultRendererImpl.h:64
     zr_compositing_pass* compositing = nullptr;
     zr_taa_pass* taa = nullptr;
@@ -126,7 +126,7 @@ extern "C"
         }
         s = zr_direct_pass_render(r->direct, &in, directStream);
         if (s != ZR_OK) return s;
-        s = r->integrator == ZR_INTEGRATOR_RESTIR_GI ? zr_gi_pass_render(r->gi, &in, stream) : zr_indirect_pass_render(r->indirect, &in, stream);
+        s = r->integrator != ZR_INTEGRATOR_RESTIR_PT ? zr_gi_pass_render(r->gi, &in, stream) : zr_indirect_pass_render(r->indirect, &in, stream);
         if (s != ZR_OK) return s;
         if (r->twoStreams)
         {
@@ -136,7 +136,7 @@ extern "C"
         zr_image2d di, ind, comp;
         s = zr_direct_pass_get_output(r->direct, ZR_DIRECT_FINAL, &di);
         if (s != ZR_OK) return s;
-        s = r->integrator == ZR_INTEGRATOR_RESTIR_GI ? zr_gi_pass_get_output(r->gi, ZR_GI_FINAL, &ind)
+        s = r->integrator != ZR_INTEGRATOR_RESTIR_PT ? zr_gi_pass_get_output(r->gi, ZR_GI_FINAL, &ind)
                                                      : zr_indirect_pass_get_output(r->indirect, ZR_INDIRECT_FINAL, &ind);
         if (s != ZR_OK) return s;
         s = zr_compositing_pass_render(r->compositing, &in, di.d_ptr, ind.d_ptr, stream);
@@ -154,17 +154,19 @@ extern "C"
     zr_status zr_renderer_set_integrator(zr_renderer* r, zr_integrator method)
     {
         if (!r) return ZR_ERR_INVALID_ARG;
-        if (method != ZR_INTEGRATOR_RESTIR_GI && method != ZR_INTEGRATOR_RESTIR_PT)
+        if (method != ZR_INTEGRATOR_PATH_TRACING && method != ZR_INTEGRATOR_RESTIR_GI && method != ZR_INTEGRATOR_RESTIR_PT)
         {
-            zr::set_error("zr_renderer_set_integrator: integrator %d is not part of this build (ReSTIR GI = 1, ReSTIR PT = 2)", (int)method);
+            zr::set_error("zr_renderer_set_integrator: unknown integrator %d (path tracing = 0, ReSTIR GI = 1, ReSTIR PT = 2)", (int)method);
             return ZR_ERR_INVALID_ARG;
         }
         if (method == r->integrator) return ZR_OK;
         zr_status s = ZR_OK;
-        if (method == ZR_INTEGRATOR_RESTIR_GI)
+        if (method != ZR_INTEGRATOR_RESTIR_PT)
         {
+            // the plain path tracer and ReSTIR GI share one pass object (both read cb_ReSTIR_GI in the reference)
             if (!r->gi) s = zr_gi_pass_create(r->width, r->height, &r->gi);
             else s = zr_gi_pass_reset_temporal(r->gi);
+            if (s == ZR_OK) s = zr_gi_pass_set_method(r->gi, method);
         }
         else
             s = zr_indirect_pass_reset_temporal(r->indirect);

@@ -92,14 +92,17 @@ namespace
         return surface.GlossSpecular() && (surface.metallic || surface.specTr) && (!surface.Coated() || surface.CoatSpecular());
     }
 
-    // ReSTIR_GI_NEE.hlsli:8-121 with NumLightSamples = 1, skipDiffuse = true
+    // ReSTIR_GI_NEE.hlsli:8-121 with NumLightSamples = 1. ReSTIR GI: skipDiffuse = true (MIS_NON_DIFFUSE_BSDF_SAMPLING 1),
+    // approximate shadow rays; the plain path tracer: skipDiffuse = false, APPROXIMATE_EMISSIVE_SHADOW_RAY 0
+    // (PathTracer/Params.hlsli:19-27).
+    template<bool SkipDiffuse, bool PreciseShadow>
     ZR_D float3 NEE_Emissive_MIS(const SceneDev& sc, float3 pos, float3 normal, BSDF::ShadingData surface, uint32_t sampleSetIdx, RNG& rng)
     {
         float3 ld = f3(0);
         const bool specular = IsSpecular(surface);
         const int numLightSamples = specular ? 0 : 1;
         {
-            BSDF::BSDFSample bsdfSample = BSDF::SampleBSDF_NoDiffuse(normal, surface, rng);
+            BSDF::BSDFSample bsdfSample = SkipDiffuse ? BSDF::SampleBSDF_NoDiffuse(normal, surface, rng) : BSDF::SampleBSDF(normal, surface, rng);
             float3 wi = bsdfSample.wi;
             float3 f = bsdfSample.f;
             float wiPdf = bsdfSample.pdf;
@@ -138,8 +141,9 @@ namespace
                 surface.SetWi(wi, normal);
                 le *= BSDF::Unified(surface).f * dwdA;
                 if (dot(le, le) > 0)
-                    le *= Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive()) ? 1.0f : 0.0f;
-                float bsdfPdf = BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi);
+                    le *= (PreciseShadow ? Visibility_Segment_Precise(sc, pos, wi, t, normal, lightID, surface.Transmissive())
+                                         : Visibility_Segment(sc, pos, wi, t, normal, lightID, surface.Transmissive())) ? 1.0f : 0.0f;
+                float bsdfPdf = SkipDiffuse ? BSDF::BSDFSamplerPdf_NoDiffuse(normal, surface, wi) : BSDF::BSDFSamplerPdf(normal, surface, wi, rng);
                 bsdfPdf *= dwdA;
                 ld += RT::PowerHeuristic(lightPdf, bsdfPdf, le, (float)numLightSamples);
             }
@@ -203,10 +207,15 @@ namespace
         return ret;
     }
 
+    // PlainPT: the macro set of IndirectLighting/PathTracer/Params.hlsli -- MIS_ALL_BOUNCES 1, MIS_NON_DIFFUSE_BSDF_SAMPLING 0,
+    // APPROXIMATE_EMISSIVE_SHADOW_RAY 0 (ReSTIR_GI_NEE.hlsli:225-238)
+    template<bool PlainPT>
     ZR_D float3 NEE(const SceneDev& sc, const zr_frame_constants& fc, float3 pos, float3 normal, const BSDF::ShadingData& surface, uint32_t sampleSetIdx, int bounce, RNG& rng)
     {
+        if (PlainPT)
+            return NEE_Emissive_MIS<false, true>(sc, pos, normal, surface, sampleSetIdx, rng);
         if (bounce == 0)
-            return NEE_Emissive_MIS(sc, pos, normal, surface, sampleSetIdx, rng);
+            return NEE_Emissive_MIS<true, false>(sc, pos, normal, surface, sampleSetIdx, rng);
         if (sc.lvg && sc.sampleSetSize)
             return NEE_Emissive_LVG(sc, fc, pos, normal, surface, sampleSetIdx, rng);
         return NEE_Emissive_1(sc, pos, normal, surface, sampleSetIdx, rng);
@@ -461,6 +470,9 @@ namespace
 #ifndef ZR_RGI_THREADS
 #define ZR_RGI_THREADS 1024
 #endif
+    // PlainPT = true: IndirectLighting/PathTracer/PathTracer.hlsl (INTEGRATOR::PATH_TRACING) -- the same dispatch shape, RNG
+    // seeds and PathTrace loop without reservoirs or reuse (main :98-212, EstimateIndirectLighting :58-104).
+    template<bool PlainPT>
     __global__ void ZR_LB(ZR_RGI_THREADS) k_rgi(SceneDev sc, FrameView f, GIParams prm, zr_rgi_reservoir* __restrict__ resCurr,
         const zr_rgi_reservoir* __restrict__ resPrev, float4* __restrict__ finalImg, uint32_t dispX, uint32_t dispY,
         const uint32_t* __restrict__ order)
@@ -506,12 +518,13 @@ namespace
         {
             p = LoadPixel(f, sc, f.core, f.coat, (int)px.x, (int)px.y, false, (int)px.x, (int)px.y);
             const float3 wo = normalize(p.origin - p.pos);
+            // PathTracer.hlsl:184-185 also passes flags.trDepthGt0 as the transmission depth
             surface0 = BSDF::ShadingData::Init(p.normal, wo, flags.metallic, roughness, baseColor, BSDF::ETA_AIR, p.eta_next, flags.transmissive,
-                0.0f, 0.0f, 0.0f, f3(0.0f), 0.0f, BSDF::DEFAULT_ETA_COAT, sc.rho);
+                (PlainPT && flags.trDepthGt0) ? 1.0f : 0.0f, 0.0f, 0.0f, f3(0.0f), 0.0f, BSDF::DEFAULT_ETA_COAT, sc.rho);
             rngGroup = RNG::Init(sg.x ^ 61u, sg.y ^ 61u, fc.FrameNum);
             rngThread = RNG::Init(px.x ^ 511u, px.y ^ 31u, fc.FrameNum);
             maxNumBounces = (int)(flags.transmissive ? prm.maxGlossyTrBounces : prm.maxNonTrBounces);
-            if (prm.stochasticMultiBounce && (roughness >= 0.1f || fc.CameraStatic))
+            if (!PlainPT && prm.stochasticMultiBounce && (roughness >= 0.1f || fc.CameraStatic))
                 maxNumBounces = rngGroup.Uniform() < 0.5f ? 1 : maxNumBounces;
             sampleSetIdx = rngGroup.UniformUintBounded_Faster(sc.numSampleSets);
         }
@@ -554,7 +567,14 @@ namespace
                     tracing = false;
                 else
                 {
-                    li += throughput * NEE(sc, fc, hitPos, hitInfo.normal, surface, sampleSetIdx, bounce, rngThread);
+                    li += throughput * NEE<PlainPT>(sc, fc, hitPos, hitInfo.normal, surface, sampleSetIdx, bounce, rngThread);
+                    // ACCOUNT_FOR_TRANSMITTANCE == 1 (PathTracing.hlsli:41-48): Beer's law inside a translucent medium
+                    if (PlainPT && inTranslucentMedium && (surface.trDepth > 0))
+                    {
+                        const float3 c = surface.baseColor_Fr0_TrCol;
+                        const float3 extCoeff = f3(-zr_logf(c.x), -zr_logf(c.y), -zr_logf(c.z)) / surface.trDepth;
+                        throughput *= f3(zr_expf(-hitInfo.t * extCoeff.x), zr_expf(-hitInfo.t * extCoeff.y), zr_expf(-hitInfo.t * extCoeff.z));
+                    }
                     if (bounce >= (maxNumBounces - 1))
                         tracing = false;
                     else
@@ -612,6 +632,26 @@ namespace
                 }
                 tracing = go;
             }
+        }
+        if (PlainPT)
+        {
+            // EstimateIndirectLighting :97-103, main :199-211
+            if (!active)
+                return;
+            float3 liOut = f3(0);
+            if (traced)
+            {
+                liOut = li;
+                if (dot(liOut, liOut) > 0)
+                    liOut *= bsdfSample0.bsdfOverPdf;
+            }
+            liOut = isnan3(liOut) ? f3(0) : liOut;
+            const float4 prev = finalImg[idx];
+            if (fc.Accumulate && fc.CameraStatic)
+                finalImg[idx] = f4(prev.x + liOut.x, prev.y + liOut.y, prev.z + liOut.z, prev.w);
+            else
+                finalImg[idx] = f4(liOut.x, liOut.y, liOut.z, prev.w);
+            return;
         }
         // ---- rest of RIS_InitialCandidates :83-113 ----
         if (traced)
@@ -690,6 +730,7 @@ struct zr_gi_pass
     bool isTemporalReservoirValid = false;
     bool resetTemporalTextures = true;
     zr_gi_params params{};
+    bool plainPathTracer = false;       // INTEGRATOR::PATH_TRACING instead of ReSTIR_GI (both read cb_ReSTIR_GI in the reference)
     uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
     zr::TileCosts tileCosts;
     zr::BlockSchedule sched;
@@ -753,7 +794,7 @@ struct zr_gi_pass
             set_error("zr_gi_pass_render: the light voxel grid is enabled but zr_build_light_voxel_grid has not run");
             return ZR_ERR_NOT_INITIALIZED;
         }
-        const bool doTemporal = params.temporal_resample && isTemporalReservoirValid;
+        const bool doTemporal = !plainPathTracer && params.temporal_resample && isTemporalReservoirValid;
         if (doTemporal && !in->prev.d_core)
         {
             set_error("zr_gi_pass_render: temporal reuse needs the previous G-buffer");
@@ -773,8 +814,15 @@ struct zr_gi_pass
             ZR_CUDA(sched.Upload(ScheduleSwizzled(dispX, dispY, 8, 8, ZR_RGI_THREADS / 64, prm.rowBegin, prm.rowEnd, tileCosts), prm.rowBegin, prm.rowEnd,
                 tileCosts.version));
         const int cur = currTemporalIdx;
+        if (plainPathTracer)
+        {
+            ZR_PROF("k_pathtracer", stream);
+            k_rgi<true><<<sched.count, ZR_RGI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_final, dispX, dispY, sched.d_order);
+            ZR_LAUNCH_CHECK();
+            return ZR_OK;       // no reservoirs: the ReSTIR GI history is left as it is (and is dropped by SetMethod)
+        }
         ZR_PROF("k_rgi", stream);
-        k_rgi<<<sched.count, ZR_RGI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_final, dispX, dispY, sched.d_order);
+        k_rgi<false><<<sched.count, ZR_RGI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_final, dispX, dispY, sched.d_order);
         ZR_LAUNCH_CHECK();
         isTemporalReservoirValid = true;
         currTemporalIdx = 1 - cur;
@@ -818,6 +866,20 @@ extern "C"
         }
         p->params = *params;
         return ZR_OK;
+    }
+    // IndirectLighting::SetMethod for the two integrators that share this pass object (IndirectLighting.cpp:203-235):
+    // ZR_INTEGRATOR_PATH_TRACING or ZR_INTEGRATOR_RESTIR_GI; a change drops the temporal history.
+    zr_status zr_gi_pass_set_method(zr_gi_pass* p, zr_integrator method)
+    {
+        if (!p || (method != ZR_INTEGRATOR_PATH_TRACING && method != ZR_INTEGRATOR_RESTIR_GI))
+        {
+            zr::set_error("zr_gi_pass_set_method: PATH_TRACING (0) or RESTIR_GI (1); ReSTIR PT is zr_indirect_pass");
+            return ZR_ERR_INVALID_ARG;
+        }
+        const bool plain = method == ZR_INTEGRATOR_PATH_TRACING;
+        if (plain == p->plainPathTracer) return ZR_OK;
+        p->plainPathTracer = plain;
+        return p->ResetTemporal();
     }
     zr_status zr_gi_pass_render(zr_gi_pass* p, const zr_frame_inputs* in, void* stream)
     {

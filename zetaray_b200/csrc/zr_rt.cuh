@@ -155,6 +155,28 @@ ZR_D bool Visibility_Segment(const SceneDev& sc, float3 origin, float3 wi, float
     return !TraceAnyExcept(sc, adjustedOrigin, wi, tMin, tMax, triID);
 }
 
+// RayQuery.hlsli:337-406 with APPROXIMATE_EMISSIVE_SHADOW_RAY == 0 (the plain path tracer, PathTracer/Params.hlsli:27):
+// tMax = rayT, the committed hit is the closest one; visible iff nothing is hit or the closest hit is the light itself.
+ZR_D bool Visibility_Segment_Precise(const SceneDev& sc, float3 origin, float3 wi, float rayT, float3 normal, uint32_t triID,
+    bool transmissive)
+{
+    if (triID == UINT32_MAX_) return false;
+    if (rayT < 1e-6f) return false;
+    float ndotwi = dot(normal, wi);
+    if (ndotwi == 0) return false;
+    bool wiBackface = ndotwi < 0;
+    if (wiBackface)
+    {
+        if (transmissive) normal = -normal;
+        else return false;
+    }
+    const float3 adjustedOrigin = RTU::OffsetRayRTG(origin, normal);
+    const RayHit h = TraceClosest(sc, adjustedOrigin, wi, 3e-6f, rayT);
+    if (h.hit)
+        return triID == TriID(sc, h.tri);
+    return true;
+}
+
 // GetMaterialData (RayQuery.hlsli:452-510), textures unsupported (factors only)
 ZR_F2 bool GetMaterialData(const SceneDev& sc, float3 wo, float eta_curr, Hit& hitInfo, BSDF::ShadingData& surface, float& eta)
 {

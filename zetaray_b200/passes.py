@@ -275,6 +275,13 @@ class IndirectLightingGI(_Pass):
             setattr(self.params, k, v)
         check(lib.zr_gi_pass_set_params(self.handle, C.byref(self.params)))
 
+    PATH_TRACING, RESTIR_GI = 0, 1
+
+    def SetMethod(self, integrator):
+        """IndirectLighting::SetMethod for the two integrators this pass object runs: the plain path tracer
+        (PathTracer.hlsl) or ReSTIR GI."""
+        check(lib.zr_gi_pass_set_method(self.handle, int(integrator)))
+
     def OnWindowResized(self, w, h):
         check(lib.zr_gi_pass_resize(self.handle, w, h))
 
@@ -362,12 +369,12 @@ class Renderer:
     def Render(self, fc, stream=None):
         check(lib.zr_renderer_render(self.handle, C.byref(fc), stream))
 
-    RESTIR_GI, RESTIR_PT = 1, 2
+    PATH_TRACING, RESTIR_GI, RESTIR_PT = 0, 1, 2
 
     def SetMethod(self, integrator):
         """IndirectLighting::SetMethod as the renderer calls it (DefaultRenderer.cpp:243)."""
         check(lib.zr_renderer_set_integrator(self.handle, int(integrator)))
-        if integrator == self.RESTIR_GI:
+        if integrator != self.RESTIR_PT:
             h = C.c_void_p()
             check(lib.zr_renderer_get_gi_pass(self.handle, C.byref(h)))
             self.gi = _Borrowed(IndirectLightingGI, h)
