@@ -65,6 +65,12 @@ def make_rays(wt, n, seed, cam):
         ax = j % 3
         v = np.zeros(3); v[ax] = 1.0 if j % 2 else -1.0
         rays[h + j, 4:7] = v; rays[h + j, 7] = 3.0e38
+    # degenerate rays: zero direction, NaN direction, NaN origin -- no hit under the hit rule, and the traversal must say so
+    # without sweeping the tree (zr_scene.cuh::Traverse's early-out)
+    if n - h > k + 3:
+        rays[h + k, 4:7] = 0.0; rays[h + k, 7] = 3.0e38
+        rays[h + k + 1, 4] = np.nan; rays[h + k + 1, 7] = 3.0e38
+        rays[h + k + 2, 0] = np.nan; rays[h + k + 2, 7] = 3.0e38
     return rays
 
 
@@ -103,6 +109,8 @@ def test_builder_and_traversal_against_brute_force(name, make, cam, nrays):
     assert got.tobytes() == ref.tobytes(), (name, int((got.view(np.uint32) != ref.view(np.uint32)).any(axis=1).sum()))
     hit = ref[:, 0] < 3.0e38
     assert np.array_equal(anyf != 0, hit), name
+    deg = nrays // 2 + 16
+    assert not hit[deg:deg + 3].any()           # the three degenerate rays
     assert hit.mean() > 0.2       # not a degenerate comparison: a good share of the rays hit something
 
 

@@ -72,6 +72,13 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
 {
     RayHit best;
     best.hit = false; best.t = tmax; best.bary = f2(0, 0); best.tri = 0xffffffffu;
+    // Degenerate rays hit nothing under the hit rule (a zero direction makes every determinant 0, a NaN direction or origin makes
+    // every barycentric NaN), but they pass every slab test below (0 * inf and NaN drop out of fminf / fmaxf), i.e. they would
+    // sweep the whole tree: one such ray per ~1500 pixels comes out of the path tracer's BSDF-sampled emissive-hit query on
+    // transmissive surfaces (wi = 0 when the sampler returns pdf 0), and on a 195 k-node tree it stalled its whole 1024-thread block
+    // for tens of milliseconds (3.5 s per 4K frame of the 10^6-triangle tunnel before this test).
+    if ((d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) || d.x != d.x || d.y != d.y || d.z != d.z || o.x != o.x || o.y != o.y || o.z != o.z)
+        return best;
     const float3 invd = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     uint32_t stack[BVH_STACK_ENTRIES];
     int sp = 0;
