@@ -16,6 +16,9 @@ static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); re
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 template<typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 
+struct ZrTraverseStats { unsigned long long nodes, tris; };
+static thread_local ZrTraverseStats g_stats;
+#define ZR_TRAVERSE_STATS g_stats
 #include "../../zetaray_b200/csrc/zr_scene.cuh"
 
 namespace zr
@@ -159,4 +162,22 @@ extern "C" uint64_t hostsim_validate(const void* nodes_, uint32_t numNodes, cons
     }
     for (uint32_t i = 0; i < numTris; i++) if (seen[i] != 1) bad++;
     return bad;
+}
+
+// node visits and triangle tests of every ray (closest hit, or any hit when anyhit != 0), single-threaded
+extern "C" int hostsim_trace_stats(const void* nodes, const float* leafTris, const uint32_t* triMesh, const uint32_t* meshFirstTri,
+    const float* rays, uint32_t n, uint32_t* outNodes, uint32_t* outTris, int anyhit)
+{
+    zr::SceneDev sc{};
+    sc.nodes = reinterpret_cast<const uint4*>(nodes); sc.tris = reinterpret_cast<const float4*>(leafTris);
+    sc.triMesh = triMesh; sc.meshFirstTri = meshFirstTri;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const float* r = rays + (size_t)i * 8;
+        const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[4], r[5], r[6]);
+        g_stats.nodes = g_stats.tris = 0;
+        if (anyhit) zr::TraceAnyExcept(sc, o, d, r[3], r[7], 0xffffffffu); else zr::TraceClosest(sc, o, d, r[3], r[7]);
+        outNodes[i] = (uint32_t)g_stats.nodes; outTris[i] = (uint32_t)g_stats.tris;
+    }
+    return 0;
 }

@@ -94,6 +94,9 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
     while (sp > 0)
     {
         const uint32_t nodeIdx = stack[--sp];
+#ifdef ZR_TRAVERSE_STATS        /* host test builds only (tests/hostsim): node visits / triangle tests per ray */
+        ZR_TRAVERSE_STATS.nodes++;
+#endif
         const uint4* np = sc.nodes + (size_t)nodeIdx * 5;
         const uint4 n0 = __ldg(np + 0);
         const uint4 n1 = __ldg(np + 1);
@@ -143,6 +146,9 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
                     const float4* tp = sc.tris + (size_t)(first + k) * 3;
                     const float4 a = __ldg(tp), b = __ldg(tp + 1), cc = __ldg(tp + 2);
                     float t, u, v;
+#ifdef ZR_TRAVERSE_STATS
+                    ZR_TRAVERSE_STATS.tris++;
+#endif
                     if (TriHit(o, d, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(cc.x, cc.y, cc.z), tmin, tmax, t, u, v))
                     {
                         const uint32_t triGlobal = asuint(a.w);
