@@ -41,21 +41,40 @@ def pcg3d(x, y, z):
 
 
 def _unorm(v, bits):
-    v = np.clip(np.asarray(v, dtype=np.float64), 0.0, 1.0)
-    return np.floor(v * ((1 << bits) - 1) + 0.5).astype(np.uint32)
+    """Math::FloatToUNorm8 / FloatToUNorm16 (ZetaCore/Math/Common.h:158-166): (uintN) fmaf(value, 2^N - 1, 0.5f) -- one float32
+    rounding of the exact product-sum, then truncation. Pinned against the reference's own code (tests/test_scene_pinning.py)."""
+    v = np.asarray(v, dtype=np.float32).astype(np.float64)
+    t = (v * float((1 << bits) - 1) + 0.5).astype(np.float32)      # the float64 sum is exact to well below float32 resolution
+    return np.clip(t, 0.0, float((1 << bits) - 1)).astype(np.uint32)
+
+
+def _unorm_rne(v01, bits):
+    """The SIMD packers (unorm2 / unorm4::FromNormalized, Vector.h:626-647, 745-769; Float3ToRGB8, Color.h:21-33):
+    float32 multiply by 2^N - 1, then _mm_cvtps_epi32 = round to nearest EVEN."""
+    t = np.asarray(v01, dtype=np.float32) * np.float32((1 << bits) - 1)
+    return np.clip(np.rint(t), 0, (1 << bits) - 1).astype(np.uint32)
+
+
+def snorm_to_unorm16(v):
+    """[-1, 1] -> UNORM16 as unorm2 / unorm4::FromNormalized do it: fmadd(v, 0.5, 0.5) in float32 (v * 0.5 is exact, so one
+    rounding), times 65535, round to nearest even."""
+    v = np.asarray(v, dtype=np.float32)
+    return _unorm_rne(v * np.float32(0.5) + np.float32(0.5), 16)
 
 
 def oct_encode_unorm16(n):
-    """Math::oct32 (ZetaCore/Math/OctahedralVector.h:8-39): octahedral map, 2 x UNORM16."""
-    n = np.asarray(n, dtype=np.float64).reshape(-1, 3)
-    s = np.abs(n).sum(axis=1, keepdims=True)
-    s[s == 0] = 1.0
-    p = n[:, :2] / s
-    neg = n[:, 2] <= 0
-    sgn = np.where(p >= 0, 1.0, -1.0)
-    folded = (1.0 - np.abs(p[:, ::-1])) * sgn
-    p = np.where(neg[:, None], folded, p)
-    return _unorm(p * 0.5 + 0.5, 16).astype(np.uint16)
+    """Math::oct32 (ZetaCore/Math/OctahedralVector.h:8-39 over VectorFuncs.h:123-153 encode_octahedral): float32 throughout,
+    the abs-sum in hadd_float3's order (|x| + |z|) + |y|, sign(v) = v >= 0 ? 1 : -1 of the INPUT vector, 2 x UNORM16 (RNE).
+    Bit-exact with the reference's own code (tests/test_scene_pinning.py)."""
+    n = np.asarray(n, dtype=np.float32).reshape(-1, 3)
+    a = np.abs(n)
+    s = (a[:, 0] + a[:, 2]) + a[:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = n[:, :2] / s[:, None]
+    sgn = np.where(n[:, :2] >= 0, np.float32(1.0), np.float32(-1.0))
+    folded = (np.float32(1.0) - np.abs(p[:, ::-1])) * sgn
+    enc = np.where((n[:, 2] <= 0)[:, None], folded, p).astype(np.float32)
+    return snorm_to_unorm16(enc).astype(np.uint16)
 
 
 def half_bits(v):
@@ -63,8 +82,15 @@ def half_bits(v):
 
 
 def rgb8(c):
-    u = _unorm(np.asarray(c)[:3], 8)
+    """Math::Float3ToRGB8 (ZetaCore/Math/Color.h:21-33): float32 * 255, round to nearest even, saturate."""
+    u = _unorm_rne(np.asarray(c, dtype=np.float32)[:3], 8)
     return int(u[0]) | (int(u[1]) << 8) | (int(u[2]) << 16)
+
+
+def rgba8(c):
+    """Math::Float4ToRGBA8 (Color.h:35-46)."""
+    u = _unorm_rne(np.asarray(c, dtype=np.float32)[:4], 8)
+    return int(u[0]) | (int(u[1]) << 8) | (int(u[2]) << 16) | (int(u[3]) << 24)
 
 
 def make_material(base_color=(1, 1, 1, 1), metallic=0.0, roughness=0.3, ior=1.5, transmission=0.0,
@@ -74,14 +100,16 @@ def make_material(base_color=(1, 1, 1, 1), metallic=0.0, roughness=0.3, ior=1.5,
     """ZetaCore/Core/Material.h setters (defaults from the constructor, Material.h:69-93)."""
     m = np.zeros(1, dtype=MATERIAL)[0]
     bc = list(base_color) + [1.0] * (4 - len(base_color))
-    a = int(_unorm(bc[3], 8))
-    m["BaseColorFactor"] = rgb8(bc) | (a << 24)
+    m["BaseColorFactor"] = rgba8(bc)
     m["BaseColorTex_Subsurf_CoatWeight"] = INVALID_ID | (int(_unorm(subsurface, 8)) << 16) | (int(_unorm(coat_weight, 8)) << 24)
     m["NormalTex_TrDepth"] = INVALID_ID | (int(half_bits(transmission_depth)) << 16)
     m["MRTex_SpecRoughness_CoatRoughness"] = INVALID_ID | (int(_unorm(roughness, 8)) << 16) | (int(_unorm(coat_roughness, 8)) << 24)
     m["EmissiveFactor_NormalScale"] = rgb8(emissive_factor) | (int(_unorm(1.0, 8)) << 24)
-    m["EmissiveStrength_IOR"] = int(half_bits(emissive_strength)) | (int(_unorm((ior - 1.0) / 1.5, 16)) << 16)
-    m["EmissiveTex_AlphaCutoff_CoatIOR"] = INVALID_ID | (int(_unorm(0.5, 8)) << 16) | (int(_unorm((coat_ior - 1.0) / 1.5, 8)) << 24)
+    # (ior - MIN_IOR) / (MAX_IOR - MIN_IOR) in float32 (Material.h:160-163, 184-190)
+    nior = (np.float32(ior) - np.float32(1.0)) / (np.float32(2.5) - np.float32(1.0))
+    ncoat = (np.float32(coat_ior) - np.float32(1.0)) / (np.float32(2.5) - np.float32(1.0))
+    m["EmissiveStrength_IOR"] = int(half_bits(emissive_strength)) | (int(_unorm(nior, 16)) << 16)
+    m["EmissiveTex_AlphaCutoff_CoatIOR"] = INVALID_ID | (int(_unorm(0.5, 8)) << 16) | (int(_unorm(ncoat, 8)) << 24)
     flags = 0
     if metallic >= 0.9: flags |= 1 << 24
     if double_sided: flags |= 1 << 25
@@ -236,7 +264,7 @@ class SceneBuilder:
         inst["BaseIdxOffset"] = base_idx
         q = np.asarray(rotation, dtype=np.float64)
         q = q / np.linalg.norm(q)
-        inst["Rotation"] = _unorm(q * 0.5 + 0.5, 16).astype(np.uint16)
+        inst["Rotation"] = snorm_to_unorm16(q.astype(np.float32)).astype(np.uint16)       # unorm4::FromNormalized, RtAccelerationStructure.cpp:345
         inst["Scale"] = half_bits(scale)
         inst["MatIdx"] = mat_idx
         inst["Translation"] = np.asarray(translation, dtype=np.float32)
