@@ -56,6 +56,20 @@ extern "C"
         RNG rng = RNG::InitSeed(seed);
         return BSDF::BSDFSamplerPdf(f3(d->normal[0], d->normal[1], d->normal[2]), s, f3(wi[0], wi[1], wi[2]), rng);
     }
+    void orc_bsdf_sample_nodiffuse(const orc_surface_desc* d, uint32_t seed, float* out)
+    {
+        BSDF::ShadingData s = mk(d);
+        RNG rng = RNG::InitSeed(seed);
+        BSDF::BSDFSample b = BSDF::SampleBSDF_NoDiffuse(f3(d->normal[0], d->normal[1], d->normal[2]), s, rng);
+        out[0] = b.wi.x; out[1] = b.wi.y; out[2] = b.wi.z; out[3] = (float)b.lobe; out[4] = b.pdf;
+        out[5] = b.bsdfOverPdf.x; out[6] = b.bsdfOverPdf.y; out[7] = b.bsdfOverPdf.z; out[8] = b.f.x; out[9] = b.f.y; out[10] = b.f.z;
+        out[11] = asfloat(rng.State);
+    }
+    float orc_bsdf_sampler_pdf_nodiffuse(const orc_surface_desc* d, const float* wi)
+    {
+        BSDF::ShadingData s = mk(d);
+        return BSDF::BSDFSamplerPdf_NoDiffuse(f3(d->normal[0], d->normal[1], d->normal[2]), s, f3(wi[0], wi[1], wi[2]));
+    }
     // f(wi) * |cos| as BSDF::Unified returns it
     void orc_bsdf_unified(const orc_surface_desc* d, const float* wi, float* out)
     {

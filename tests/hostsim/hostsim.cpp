@@ -20,6 +20,7 @@ struct ZrTraverseStats { unsigned long long nodes, tris; };
 static thread_local ZrTraverseStats g_stats;
 #define ZR_TRAVERSE_STATS g_stats
 #include "../../zetaray_b200/csrc/zr_scene.cuh"
+#include "../../zetaray_b200/csrc/zr_bsdf.cuh"
 
 namespace zr
 {
@@ -180,4 +181,94 @@ extern "C" int hostsim_trace_stats(const void* nodes, const float* leafTris, con
         outNodes[i] = (uint32_t)g_stats.nodes; outTris[i] = (uint32_t)g_stats.tris;
     }
     return 0;
+}
+
+// ---- the device BSDF source (zr_bsdf.cuh) behind the same probe entry points the oracle exports (oracle/orc_testapi.cpp), so the
+// CPU tier can hold the two transcriptions of Common/BSDF.hlsli + BSDFSampling.hlsli to each other bit for bit ----
+extern "C"
+{
+    struct hostsim_surface_desc
+    {
+        float normal[3], wo[3]; uint32_t metallic; float roughness; float baseColor[3]; float eta_curr, eta_next; uint32_t specTr;
+        float trDepth, subsurface, coat_weight; float coat_color[3]; float coat_roughness, coat_ior;
+    };
+    static const uint16_t* g_rho = nullptr;
+    void hostsim_set_rho_lut(const uint16_t* data) { g_rho = data; }
+    static zr::BSDF::ShadingData mk(const hostsim_surface_desc* d)
+    {
+        using namespace zr;
+        return BSDF::ShadingData::Init(f3(d->normal[0], d->normal[1], d->normal[2]), f3(d->wo[0], d->wo[1], d->wo[2]), d->metallic != 0,
+            d->roughness, f3(d->baseColor[0], d->baseColor[1], d->baseColor[2]), d->eta_curr, d->eta_next, d->specTr != 0, d->trDepth,
+            d->subsurface, d->coat_weight, f3(d->coat_color[0], d->coat_color[1], d->coat_color[2]), d->coat_roughness, d->coat_ior, g_rho);
+    }
+    void hostsim_bsdf_sample(const hostsim_surface_desc* d, uint32_t seed, float* out)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        RNG rng; rng.State = seed;
+        BSDF::BSDFSample b = BSDF::SampleBSDF(f3(d->normal[0], d->normal[1], d->normal[2]), s, rng);
+        out[0] = b.wi.x; out[1] = b.wi.y; out[2] = b.wi.z; out[3] = (float)b.lobe; out[4] = b.pdf;
+        out[5] = b.bsdfOverPdf.x; out[6] = b.bsdfOverPdf.y; out[7] = b.bsdfOverPdf.z; out[8] = b.f.x; out[9] = b.f.y; out[10] = b.f.z;
+        out[11] = asfloat(rng.State);
+    }
+    void hostsim_bsdf_sample_nodiffuse(const hostsim_surface_desc* d, uint32_t seed, float* out)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        RNG rng; rng.State = seed;
+        BSDF::BSDFSample b = BSDF::SampleBSDF_NoDiffuse(f3(d->normal[0], d->normal[1], d->normal[2]), s, rng);
+        out[0] = b.wi.x; out[1] = b.wi.y; out[2] = b.wi.z; out[3] = (float)b.lobe; out[4] = b.pdf;
+        out[5] = b.bsdfOverPdf.x; out[6] = b.bsdfOverPdf.y; out[7] = b.bsdfOverPdf.z; out[8] = b.f.x; out[9] = b.f.y; out[10] = b.f.z;
+        out[11] = asfloat(rng.State);
+    }
+    void hostsim_bsdf_eval_sampler(const hostsim_surface_desc* d, const float* wi, uint32_t lobe, uint32_t seed, float* out)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        RNG rng; rng.State = seed;
+        BSDF::BSDFSamplerEval e = BSDF::EvalBSDFSampler(f3(d->normal[0], d->normal[1], d->normal[2]), s, f3(wi[0], wi[1], wi[2]), (BSDF::LOBE)lobe, rng);
+        out[0] = e.pdf; out[1] = e.bsdfOverPdf.x; out[2] = e.bsdfOverPdf.y; out[3] = e.bsdfOverPdf.z; out[4] = e.f.x; out[5] = e.f.y; out[6] = e.f.z;
+        out[7] = asfloat(rng.State);
+    }
+    float hostsim_bsdf_sampler_pdf(const hostsim_surface_desc* d, const float* wi, uint32_t seed)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        RNG rng; rng.State = seed;
+        return BSDF::BSDFSamplerPdf(f3(d->normal[0], d->normal[1], d->normal[2]), s, f3(wi[0], wi[1], wi[2]), rng);
+    }
+    float hostsim_bsdf_sampler_pdf_nodiffuse(const hostsim_surface_desc* d, const float* wi)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        return BSDF::BSDFSamplerPdf_NoDiffuse(f3(d->normal[0], d->normal[1], d->normal[2]), s, f3(wi[0], wi[1], wi[2]));
+    }
+    void hostsim_bsdf_unified(const hostsim_surface_desc* d, const float* wi, float* out)
+    {
+        using namespace zr;
+        BSDF::ShadingData s = mk(d);
+        s.SetWi(f3(wi[0], wi[1], wi[2]), f3(d->normal[0], d->normal[1], d->normal[2]));
+        float3 f = BSDF::Unified(s).f;
+        out[0] = f.x; out[1] = f.y; out[2] = f.z;
+    }
+}
+
+// ---- device storage codecs (zr_common.cuh) behind the oracle's probe names ----
+extern "C"
+{
+    void hostsim_oct32_roundtrip(const float* in, int n, float* out, uint32_t* enc)
+    {
+        for (int i = 0; i < n; i++)
+        {
+            const uint32_t e = zr::Math::EncodeOct32u(zr::f3(in[3 * i], in[3 * i + 1], in[3 * i + 2]));
+            const float3 d = zr::Math::DecodeOct32(e);
+            out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+            if (enc) enc[i] = e;
+        }
+    }
+    uint32_t hostsim_pack_r11g11b10(float r, float g, float b) { return zr::pack_r11g11b10(zr::f3(r, g, b)); }
+    void hostsim_unpack_r11g11b10(uint32_t p, float* out) { float3 c = zr::unpack_r11g11b10(p); out[0] = c.x; out[1] = c.y; out[2] = c.z; }
+    uint32_t hostsim_pack_snorm16x2(float x, float y) { return zr::pack_snorm16x2(zr::f2(x, y)); }
+    void hostsim_unpack_snorm16x2(uint32_t p, float* out) { float2 c = zr::unpack_snorm16x2(p); out[0] = c.x; out[1] = c.y; }
+    uint32_t hostsim_pack_half2(float a, float b) { return zr::pack_half2(a, b); }
 }

@@ -1,0 +1,109 @@
+"""CPU tier: the DEVICE source of the layered BSDF (zetaray_b200/csrc/zr_bsdf.cuh, compiled for the host by tests/hostsim with the
+product's numeric contract: no contraction, explicit fmaf, zr_fpmath transcendentals) against the oracle's restatement
+(oracle/orc_bsdf.h), bit for bit, over random surfaces of every material class: sampling (all lobes, incl. the no-diffuse sampler
+used by ReSTIR GI's MIS), sampler evaluation, sampler pdfs and the unified evaluation. The GPU tier checks the same code through
+whole kernels; this test catches a one-sided edit of either transcription where the driver runs its CPU suite, without a GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import hostsim, orc
+from tests.orc import ptr
+from tests.test_oracle_props import Surf
+
+
+def random_surface(rng):
+    s = Surf()
+    n = rng.normal(size=3); n /= np.linalg.norm(n)
+    wo = rng.normal(size=3); wo /= np.linalg.norm(wo)
+    if rng.random() < 0.85 and np.dot(wo, n) < 0:
+        wo = -wo                                         # mostly front-facing, some back-facing views
+    s.normal[:] = tuple(n.astype(np.float32)); s.wo[:] = tuple(wo.astype(np.float32))
+    kind = rng.integers(0, 6)
+    s.metallic = int(kind == 1)
+    s.roughness = float(np.float32(rng.choice([0.0, 0.02, 0.1, 0.3, 0.6, 1.0]) if rng.random() < 0.5 else rng.random()))
+    s.baseColor[:] = tuple(rng.random(3).astype(np.float32))
+    s.specTr = int(kind in (2, 3))
+    inside = kind == 3 and rng.random() < 0.5
+    ior = float(np.float32(1.0 + 1.4 * rng.random()))
+    s.eta_curr, s.eta_next = (ior, 1.0) if inside else (1.0, ior)
+    s.trDepth = float(np.float32(rng.random())) if kind == 3 else 0.0
+    s.subsurface = float(np.float32(rng.random())) if kind == 4 else 0.0
+    s.coat_weight = float(np.float32(rng.random())) if kind == 5 or rng.random() < 0.2 else 0.0
+    s.coat_color[:] = tuple(rng.random(3).astype(np.float32))
+    s.coat_roughness = float(np.float32(rng.choice([0.0, 0.05, 0.3]) if rng.random() < 0.5 else rng.random()))
+    s.coat_ior = float(np.float32(1.1 + rng.random()))
+    return s
+
+
+def same(a, b, n):
+    return np.frombuffer(a, dtype=np.uint32, count=n).tobytes() == np.frombuffer(b, dtype=np.uint32, count=n).tobytes()
+
+
+def test_bsdf_device_source_is_bit_identical_to_the_oracle():
+    from tests import scene_util
+    hs = hostsim.load()
+    o = orc.load()
+    lut = np.fromfile(os.path.join(scene_util.ROOT, "zetaray_b200", "assets", "rho_lut.bin"), dtype=np.uint16)
+    o.orc_set_rho_lut(ptr(lut)); hs.hostsim_set_rho_lut(ptr(lut))
+    o.orc_bsdf_sampler_pdf.restype = C.c_float
+    o.orc_bsdf_sampler_pdf_nodiffuse.restype = C.c_float
+    rng = np.random.default_rng(42)
+    a = (C.c_float * 12)(); b = (C.c_float * 12)()
+    lobes_seen = set()
+    n_sampled = 0
+    for it in range(6000):
+        s = random_surface(rng)
+        seed = int(rng.integers(1, 2**32 - 1))
+        o.orc_bsdf_sample(C.byref(s), seed, a); hs.hostsim_bsdf_sample(C.byref(s), seed, b)
+        assert same(a, b, 12), ("SampleBSDF", it, list(a), list(b))
+        lobes_seen.add(int(a[3])); n_sampled += a[4] > 0
+        wi = (C.c_float * 3)(a[0], a[1], a[2]) if a[4] > 0 and rng.random() < 0.7 else (C.c_float * 3)(*(lambda v: v / np.linalg.norm(v))(rng.normal(size=3)).astype(np.float32))
+        lobe = int(a[3])
+        o.orc_bsdf_eval_sampler(C.byref(s), wi, lobe, seed, a); hs.hostsim_bsdf_eval_sampler(C.byref(s), wi, lobe, seed, b)
+        assert same(a, b, 8), ("EvalBSDFSampler", it, list(a)[:8], list(b)[:8])
+        pa = o.orc_bsdf_sampler_pdf(C.byref(s), wi, seed); pb = hs.hostsim_bsdf_sampler_pdf(C.byref(s), wi, seed)
+        assert np.float32(pa).tobytes() == np.float32(pb).tobytes(), ("BSDFSamplerPdf", it, pa, pb)
+        o.orc_bsdf_unified(C.byref(s), wi, a); hs.hostsim_bsdf_unified(C.byref(s), wi, b)
+        assert same(a, b, 3), ("Unified", it, list(a)[:3], list(b)[:3])
+        o.orc_bsdf_sample_nodiffuse(C.byref(s), seed, a); hs.hostsim_bsdf_sample_nodiffuse(C.byref(s), seed, b)
+        assert same(a, b, 12), ("SampleBSDF_NoDiffuse", it, list(a), list(b))
+        pa = o.orc_bsdf_sampler_pdf_nodiffuse(C.byref(s), wi); pb = hs.hostsim_bsdf_sampler_pdf_nodiffuse(C.byref(s), wi)
+        assert np.float32(pa).tobytes() == np.float32(pb).tobytes(), ("BSDFSamplerPdf_NoDiffuse", it, pa, pb)
+    assert n_sampled > 4000 and len(lobes_seen) >= 4, (n_sampled, lobes_seen)
+
+
+def test_storage_codecs_device_source_vs_oracle():
+    """G-buffer / reservoir storage codecs of zr_common.cuh (host build) against the oracle's: octahedral normals, R11G11B10F
+    emissive colour, SNORM16 motion vectors, halves."""
+    hs = hostsim.load()
+    o = orc.load()
+    for f in (o.orc_pack_r11g11b10, o.orc_pack_snorm16x2, hs.hostsim_pack_r11g11b10, hs.hostsim_pack_snorm16x2, hs.hostsim_pack_half2):
+        f.restype = C.c_uint32
+    rng = np.random.default_rng(9)
+    n = 20000
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v = np.ascontiguousarray(v.astype(np.float32))
+    a = np.zeros((n, 3), dtype=np.float32); b = np.zeros((n, 3), dtype=np.float32); enc = np.zeros(n, dtype=np.uint32)
+    o.orc_oct32_roundtrip(ptr(v), n, ptr(a)); hs.hostsim_oct32_roundtrip(ptr(v), n, ptr(b), ptr(enc))
+    assert a.tobytes() == b.tobytes()
+    out_a = (C.c_float * 3)(); out_b = (C.c_float * 3)()
+    cols = np.concatenate([rng.random((3000, 3)) * rng.choice([1e-3, 1.0, 50.0, 7e4], (3000, 1)), [[0, 0, 0], [65504, 1e-8, 1.0]]]).astype(np.float32)
+    for c in cols:
+        pa = o.orc_pack_r11g11b10(C.c_float(c[0]), C.c_float(c[1]), C.c_float(c[2])); pb = hs.hostsim_pack_r11g11b10(C.c_float(c[0]), C.c_float(c[1]), C.c_float(c[2]))
+        assert pa == pb, (c, hex(pa), hex(pb))
+        o.orc_unpack_r11g11b10(pa, out_a); hs.hostsim_unpack_r11g11b10(pa, out_b)
+        assert bytes(out_a) == bytes(out_b)
+    mv = np.concatenate([rng.normal(size=(3000, 2)) * 0.3, [[0, 0], [1, -1], [2, -2], [1e-6, -1e-6]]]).astype(np.float32)
+    for m in mv:
+        pa = o.orc_pack_snorm16x2(C.c_float(m[0]), C.c_float(m[1])); pb = hs.hostsim_pack_snorm16x2(C.c_float(m[0]), C.c_float(m[1]))
+        assert pa == pb, (m, hex(pa), hex(pb))
+        o.orc_unpack_snorm16x2(pa, out_a); hs.hostsim_unpack_snorm16x2(pa, out_b)
+        assert bytes(out_a)[:8] == bytes(out_b)[:8]
+    h = np.concatenate([rng.normal(size=4000) * rng.choice([1e-6, 1.0, 300.0, 1e5], 4000), [0.0, -0.0, 65504.0, 65520.0, 1e-8, np.inf]]).astype(np.float32)
+    mine = np.array([hs.hostsim_pack_half2(C.c_float(x), C.c_float(-x)) for x in h], dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        want = h.astype(np.float16).view(np.uint16).astype(np.uint32) | ((-h).astype(np.float16).view(np.uint16).astype(np.uint32) << 16)
+    assert np.array_equal(mine, want)
