@@ -78,4 +78,57 @@ extern "C"
         float3 f = BSDF::Unified(s).f;
         out[0] = f.x; out[1] = f.y; out[2] = f.z;
     }
+
+    // ---- ray-query / material / light-sampling probes on a scene (mirrored by tests/hostsim for the device source) ----
+    // in: pos(3) normal(3) wi(3) transmissive; out: 24 words
+    void orc_probe_path_vertex(void* scene_, const float* in, uint32_t seed, uint32_t* out)
+    {
+        const Scene& sc = *(const Scene*)scene_;
+        const float3 pos = f3(in[0], in[1], in[2]), normal = f3(in[3], in[4], in[5]), wi = f3(in[6], in[7], in[8]);
+        const bool transmissive = in[9] != 0;
+        memset(out, 0, 24 * 4);
+        Hit h = FindClosest(sc, pos, normal, wi, transmissive);
+        out[0] = h.hit; out[1] = asuint(h.t); out[2] = asuint(h.uv.x); out[3] = asuint(h.uv.y);
+        out[4] = asuint(h.normal.x); out[5] = asuint(h.normal.y); out[6] = asuint(h.normal.z); out[7] = h.ID; out[8] = h.meshIdx; out[9] = h.matIdx;
+        if (!h.hit) return;
+        BSDF::ShadingData surface = BSDF::ShadingData::InitEmpty(); float eta;
+        const bool ok = GetMaterialData(sc, -wi, BSDF::ETA_AIR, h, surface, eta);
+        out[10] = ok; out[11] = asuint(eta);
+        if (!ok) return;
+        RNG rng = RNG::InitSeed(seed);
+        BSDF::BSDFSample b = BSDF::SampleBSDF(h.normal, surface, rng);
+        out[12] = asuint(b.wi.x); out[13] = asuint(b.wi.y); out[14] = asuint(b.wi.z); out[15] = (uint32_t)b.lobe; out[16] = asuint(b.pdf);
+        out[17] = asuint(b.bsdfOverPdf.x); out[18] = asuint(b.bsdfOverPdf.y); out[19] = asuint(b.bsdfOverPdf.z);
+        surface.SetWi(b.wi, h.normal);
+        const float3 f = BSDF::Unified(surface).f;
+        out[20] = asuint(f.x); out[21] = asuint(f.y); out[22] = asuint(f.z); out[23] = rng.State;
+    }
+    // in: as above; out: 12 words {hit, t, geoIdx, primIdx, emissiveTriIdx, bary(2), lightPos(3), visApprox, visPrecise} -- the two
+    // visibility queries go from pos along wi to the hit distance, target = the hit triangle's ID
+    void orc_probe_emissive_and_visibility(void* scene_, const float* in, uint32_t* out)
+    {
+        const Scene& sc = *(const Scene*)scene_;
+        const float3 pos = f3(in[0], in[1], in[2]), normal = f3(in[3], in[4], in[5]), wi = f3(in[6], in[7], in[8]);
+        const bool transmissive = in[9] != 0;
+        memset(out, 0, 12 * 4);
+        HitEmissive h = FindClosestEmissive(sc, pos, normal, wi, transmissive);
+        out[0] = h.hit; out[1] = asuint(h.t); out[2] = h.geoIdx; out[3] = h.primIdx; out[4] = h.emissiveTriIdx;
+        out[5] = asuint(h.bary.x); out[6] = asuint(h.bary.y); out[7] = asuint(h.lightPos.x); out[8] = asuint(h.lightPos.y); out[9] = asuint(h.lightPos.z);
+        if (!h.hit) return;
+        const uint32_t id = RNG::PCG3d(uint3{ h.geoIdx, 0u, h.primIdx }).x;
+        out[10] = Visibility_Segment(sc, pos, wi, h.t, normal, id, transmissive);
+        out[11] = Visibility_Segment_Precise(sc, pos, wi, h.t, normal, id, transmissive);
+    }
+    // out: 14 words {pos(3), normal(3), le(3), bary(2)->2, pdf, idx, ID, twoSided -> 15?}
+    void orc_probe_sample_light(void* scene_, const float* pos3, uint32_t sampleSetIdx, uint32_t seed, int advance, uint32_t* out)
+    {
+        const Scene& sc = *(const Scene*)scene_;
+        RNG rng = RNG::InitSeed(seed);
+        Light::LightSample ls = Light::SampleLight(sc, f3(pos3[0], pos3[1], pos3[2]), sampleSetIdx, rng, advance != 0);
+        out[0] = asuint(ls.pos.x); out[1] = asuint(ls.pos.y); out[2] = asuint(ls.pos.z);
+        out[3] = asuint(ls.normal.x); out[4] = asuint(ls.normal.y); out[5] = asuint(ls.normal.z);
+        out[6] = asuint(ls.le.x); out[7] = asuint(ls.le.y); out[8] = asuint(ls.le.z);
+        out[9] = asuint(ls.bary.x); out[10] = asuint(ls.bary.y); out[11] = asuint(ls.pdf); out[12] = ls.idx; out[13] = ls.ID; out[14] = ls.twoSided;
+        out[15] = rng.State;
+    }
 }

@@ -21,6 +21,7 @@ static thread_local ZrTraverseStats g_stats;
 #define ZR_TRAVERSE_STATS g_stats
 #include "../../zetaray_b200/csrc/zr_scene.cuh"
 #include "../../zetaray_b200/csrc/zr_bsdf.cuh"
+#include "../../zetaray_b200/csrc/zr_rt.cuh"
 
 namespace zr
 {
@@ -271,4 +272,75 @@ extern "C"
     uint32_t hostsim_pack_snorm16x2(float x, float y) { return zr::pack_snorm16x2(zr::f2(x, y)); }
     void hostsim_unpack_snorm16x2(uint32_t p, float* out) { float2 c = zr::unpack_snorm16x2(p); out[0] = c.x; out[1] = c.y; }
     uint32_t hostsim_pack_half2(float a, float b) { return zr::pack_half2(a, b); }
+}
+
+// ---- ray-query / material / light-sampling device source (zr_rt.cuh) on a host-resident scene ----
+extern "C"
+{
+    struct hostsim_scene
+    {
+        const void* vertices; const uint32_t* indices; const void* instances; const void* materials; const void* emissives;
+        const void* aliasTable; const void* nodes; const float* leafTris; const uint32_t* triMesh; const uint32_t* meshFirstTri;
+        const uint16_t* rho; uint32_t numInstances, numEmissives, numTris;
+    };
+    static zr::SceneDev dev_of(const hostsim_scene* h)
+    {
+        zr::SceneDev sc{};
+        sc.vertices = (const zr_vertex*)h->vertices; sc.indices = h->indices; sc.instances = (const zr_mesh_instance*)h->instances;
+        sc.materials = (const zr_material*)h->materials; sc.emissives = (const zr_emissive_tri*)h->emissives;
+        sc.aliasTable = (const zr_alias_entry*)h->aliasTable; sc.nodes = (const uint4*)h->nodes; sc.tris = (const float4*)h->leafTris;
+        sc.triMesh = h->triMesh; sc.meshFirstTri = h->meshFirstTri; sc.rho = h->rho;
+        sc.numInstances = h->numInstances; sc.numEmissives = h->numEmissives; sc.numTris = h->numTris;
+        return sc;
+    }
+    void hostsim_probe_path_vertex(const hostsim_scene* hsc, const float* in, uint32_t seed, uint32_t* out)
+    {
+        using namespace zr;
+        const SceneDev sc = dev_of(hsc);
+        const float3 pos = f3(in[0], in[1], in[2]), normal = f3(in[3], in[4], in[5]), wi = f3(in[6], in[7], in[8]);
+        const bool transmissive = in[9] != 0;
+        memset(out, 0, 24 * 4);
+        Hit h = FindClosest(sc, pos, normal, wi, transmissive);
+        out[0] = h.hit; out[1] = asuint(h.t); out[2] = asuint(h.uv.x); out[3] = asuint(h.uv.y);
+        out[4] = asuint(h.normal.x); out[5] = asuint(h.normal.y); out[6] = asuint(h.normal.z); out[7] = h.ID; out[8] = h.meshIdx; out[9] = h.matIdx;
+        if (!h.hit) return;
+        BSDF::ShadingData surface = BSDF::ShadingData::InitEmpty(); float eta;
+        const bool ok = GetMaterialData(sc, -wi, BSDF::ETA_AIR, h, surface, eta);
+        out[10] = ok; out[11] = asuint(eta);
+        if (!ok) return;
+        RNG rng; rng.State = seed;
+        BSDF::BSDFSample b = BSDF::SampleBSDF(h.normal, surface, rng);
+        out[12] = asuint(b.wi.x); out[13] = asuint(b.wi.y); out[14] = asuint(b.wi.z); out[15] = (uint32_t)b.lobe; out[16] = asuint(b.pdf);
+        out[17] = asuint(b.bsdfOverPdf.x); out[18] = asuint(b.bsdfOverPdf.y); out[19] = asuint(b.bsdfOverPdf.z);
+        surface.SetWi(b.wi, h.normal);
+        const float3 f = BSDF::Unified(surface).f;
+        out[20] = asuint(f.x); out[21] = asuint(f.y); out[22] = asuint(f.z); out[23] = rng.State;
+    }
+    void hostsim_probe_emissive_and_visibility(const hostsim_scene* hsc, const float* in, uint32_t* out)
+    {
+        using namespace zr;
+        const SceneDev sc = dev_of(hsc);
+        const float3 pos = f3(in[0], in[1], in[2]), normal = f3(in[3], in[4], in[5]), wi = f3(in[6], in[7], in[8]);
+        const bool transmissive = in[9] != 0;
+        memset(out, 0, 12 * 4);
+        HitEmissive h = FindClosestEmissive(sc, pos, normal, wi, transmissive);
+        out[0] = h.hit; out[1] = asuint(h.t); out[2] = h.geoIdx; out[3] = h.primIdx; out[4] = h.emissiveTriIdx;
+        out[5] = asuint(h.bary.x); out[6] = asuint(h.bary.y); out[7] = asuint(h.lightPos.x); out[8] = asuint(h.lightPos.y); out[9] = asuint(h.lightPos.z);
+        if (!h.hit) return;
+        const uint32_t id = RNG::PCG3d(make_uint3(h.geoIdx, 0u, h.primIdx)).x;
+        out[10] = Visibility_Segment(sc, pos, wi, h.t, normal, id, transmissive);
+        out[11] = Visibility_Segment_Precise(sc, pos, wi, h.t, normal, id, transmissive);
+    }
+    void hostsim_probe_sample_light(const hostsim_scene* hsc, const float* pos3, uint32_t sampleSetIdx, uint32_t seed, int advance, uint32_t* out)
+    {
+        using namespace zr;
+        const SceneDev sc = dev_of(hsc);
+        RNG rng; rng.State = seed;
+        Light::LightSample ls = Light::SampleLight(sc, f3(pos3[0], pos3[1], pos3[2]), sampleSetIdx, rng, advance != 0);
+        out[0] = asuint(ls.pos.x); out[1] = asuint(ls.pos.y); out[2] = asuint(ls.pos.z);
+        out[3] = asuint(ls.normal.x); out[4] = asuint(ls.normal.y); out[5] = asuint(ls.normal.z);
+        out[6] = asuint(ls.le.x); out[7] = asuint(ls.le.y); out[8] = asuint(ls.le.z);
+        out[9] = asuint(ls.bary.x); out[10] = asuint(ls.bary.y); out[11] = asuint(ls.pdf); out[12] = ls.idx; out[13] = ls.ID; out[14] = ls.twoSided;
+        out[15] = rng.State;
+    }
 }

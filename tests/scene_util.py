@@ -69,13 +69,24 @@ SCENES = {"cornell": cornell, "glossy": glossy_cornell, "glass": glass_cornell, 
 CAMERAS = {"atrium": (0.0, 1.7, -13.0), "atrium_lights": (0.0, 1.7, -13.0), "tunnel": (-1.6, 1.7, -4.0)}
 
 
+_RHO_LUT = None
+
+
+def rho_lut():
+    """The directional-albedo table, loaded once and kept alive for the life of the process: the oracle holds a bare pointer to it
+    (orc_set_rho_lut), so a per-object copy would dangle as soon as a temporary OracleScene is collected."""
+    global _RHO_LUT
+    if _RHO_LUT is None:
+        _RHO_LUT = np.fromfile(os.path.join(ROOT, "zetaray_b200", "assets", "rho_lut.bin"), dtype=np.uint16)
+        assert _RHO_LUT.size == 64 * 32 * 16
+    return _RHO_LUT
+
+
 class OracleScene:
     def __init__(self, flat):
         self.o = orc.load()
         self.flat = flat
-        lut_path = os.path.join(ROOT, "zetaray_b200", "assets", "rho_lut.bin")
-        self.lut = np.fromfile(lut_path, dtype=np.uint16)
-        assert self.lut.size == 64 * 32 * 16
+        self.lut = rho_lut()
         self.o.orc_set_rho_lut(ptr(self.lut))
         self.alias = np.zeros(max(len(flat.emissives), 1), dtype=ALIAS)
         self.o.orc_scene_create.restype = C.c_void_p

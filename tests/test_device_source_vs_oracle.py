@@ -46,7 +46,7 @@ def test_bsdf_device_source_is_bit_identical_to_the_oracle():
     from tests import scene_util
     hs = hostsim.load()
     o = orc.load()
-    lut = np.fromfile(os.path.join(scene_util.ROOT, "zetaray_b200", "assets", "rho_lut.bin"), dtype=np.uint16)
+    lut = scene_util.rho_lut()
     o.orc_set_rho_lut(ptr(lut)); hs.hostsim_set_rho_lut(ptr(lut))
     o.orc_bsdf_sampler_pdf.restype = C.c_float
     o.orc_bsdf_sampler_pdf_nodiffuse.restype = C.c_float
@@ -107,3 +107,70 @@ def test_storage_codecs_device_source_vs_oracle():
     with np.errstate(over="ignore"):
         want = h.astype(np.float16).view(np.uint16).astype(np.uint32) | ((-h).astype(np.float16).view(np.uint16).astype(np.uint32) << 16)
     assert np.array_equal(mine, want)
+
+
+class HostScene(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("instances", C.c_void_p), ("materials", C.c_void_p),
+                ("emissives", C.c_void_p), ("aliasTable", C.c_void_p), ("nodes", C.c_void_p), ("leafTris", C.c_void_p),
+                ("triMesh", C.c_void_p), ("meshFirstTri", C.c_void_p), ("rho", C.c_void_p),
+                ("numInstances", C.c_uint32), ("numEmissives", C.c_uint32), ("numTris", C.c_uint32)]
+
+
+@pytest.mark.parametrize("which,detail,nq", [("cornell", None, 3000), ("atrium", 0.5, 1200), ("tunnel", 0.35, 600)])
+def test_ray_query_material_and_light_sampling_device_source_vs_oracle(which, detail, nq):
+    """zr_rt.cuh on a host-resident scene (the product's BVH from zr_bvh_build_host, the flat buffers as uploaded) against the
+    oracle (brute-force ray queries): FindClosest + hit attributes, GetMaterialData (checked through a BSDF sample and a unified
+    evaluation on the fetched surface), FindClosestEmissive, both shadow-segment rules, light sampling through the alias table --
+    at secondary-path vertices of scenes with tens of thousands of triangles, hundreds of instances and all material classes."""
+    from tests import scene_util
+    from tests.test_bvh_host import world_tris, build
+    from tests.test_bvh_quality import ray_sets
+    from zetaray_b200 import procedural
+    hs = hostsim.load()
+    if which == "cornell":
+        flat, cam = scene_util.glass_cornell(), (0.0, 1.2, -4.043)
+    else:
+        make, cam = procedural.SCENES[which]
+        flat = make(detail)
+    osc = scene_util.OracleScene(flat)
+    o = osc.o
+    lut = osc.lut
+    hs.hostsim_set_rho_lut(ptr(lut))
+    wt, tri_mesh, first = world_tris(flat)
+    nodes, order, leaf, info = build(wt)
+    keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances, flat.materials, flat.emissives, osc.alias)]
+    hsc = HostScene(*[k.ctypes.data for k in keep], nodes.ctypes.data, leaf.ctypes.data, tri_mesh.ctypes.data, first.ctypes.data,
+                    lut.ctypes.data, len(flat.instances), len(flat.emissives), len(wt))
+
+    def closest(rays):
+        out = np.zeros((len(rays), 4), dtype=np.float32)
+        hs.hostsim_trace(ptr(nodes), ptr(leaf), ptr(tri_mesh), ptr(first), ptr(rays), len(rays), ptr(out), None, None, 8)
+        return out
+    prim, sec, sh = ray_sets(flat, wt, cam, closest)
+    rng = np.random.default_rng(5)
+    pick = rng.choice(len(sec), size=min(nq, len(sec)), replace=False)
+    a = (C.c_uint32 * 24)(); b = (C.c_uint32 * 24)()
+    hits = lights = 0
+    for k in pick:
+        # a path vertex: position on a surface, its geometric normal (= the direction ray_sets offset along), a sampled direction
+        pos = sec[k, 0:3]; wi = sec[k, 4:7]
+        nrm = wi / np.linalg.norm(wi)        # any normal with wi in its hemisphere serves the query (only the offset side matters)
+        for transmissive in (0.0, 1.0):
+            q = np.concatenate([pos, nrm, wi, [transmissive]]).astype(np.float32)
+            seed = int(rng.integers(1, 2**32 - 1))
+            o.orc_probe_path_vertex(osc.h, ptr(q), seed, a); hs.hostsim_probe_path_vertex(C.byref(hsc), ptr(q), seed, b)
+            assert bytes(a) == bytes(b), (which, int(k), list(a), list(b))
+            hits += a[0]
+            o.orc_probe_emissive_and_visibility(osc.h, ptr(q), a); hs.hostsim_probe_emissive_and_visibility(C.byref(hsc), ptr(q), b)
+            assert bytes(a)[:48] == bytes(b)[:48], (which, int(k), list(a)[:12], list(b)[:12])
+            lights += a[4] != 0xffffffff and a[0] != 0
+        # back-facing direction (transmission through the surface, or an early out when not transmissive)
+        q = np.concatenate([pos, -nrm, wi, [1.0]]).astype(np.float32)
+        o.orc_probe_path_vertex(osc.h, ptr(q), 7, a); hs.hostsim_probe_path_vertex(C.byref(hsc), ptr(q), 7, b)
+        assert bytes(a) == bytes(b)
+        seed = int(rng.integers(1, 2**32 - 1))
+        p3 = pos.astype(np.float32)
+        o.orc_probe_sample_light(osc.h, ptr(p3), 0, seed, 0, a); hs.hostsim_probe_sample_light(C.byref(hsc), ptr(p3), 0, seed, 0, b)
+        assert bytes(a)[:64] == bytes(b)[:64], (which, int(k), list(a)[:16], list(b)[:16])
+    assert hits > len(pick) // 4     # a good share of the queries hit something (the Cornell box is open at the front)
+    assert lights > 0                # and some BSDF-direction queries end on a light

@@ -32,8 +32,7 @@ def surf(roughness=0.5, metallic=0, base=(0.8, 0.8, 0.8), spec_tr=0, coat=0.0, c
 @pytest.fixture(scope="module")
 def o(oracle):
     from tests import scene_util
-    lut = np.fromfile(os.path.join(scene_util.ROOT, "zetaray_b200", "assets", "rho_lut.bin"), dtype=np.uint16)
-    oracle._lut_keep = lut
+    lut = scene_util.rho_lut()       # process-wide instance: the oracle keeps a bare pointer
     oracle.orc_set_rho_lut(ptr(lut))
     oracle.orc_bsdf_sampler_pdf.restype = C.c_float
     return oracle
