@@ -6,9 +6,13 @@
 //   ZetaCore/Math/OctahedralVector.h   oct32
 //   ZetaCore/Math/Vector.h             half, half3, unorm4
 //   ZetaCore/Math/Color.h              Float3ToRGB8
+//   ZetaRenderPass/Common/FrameConstants.h   cbFrameConstants (field offsets: the per-frame constant block the passes receive)
+//   the RT::MeshInstance / EmissiveTriangle / Material field offsets
 // Nothing here is product code and no reference source is copied.
 #include "ZetaCore/RayTracing/RtCommon.h"
 #include "ZetaCore/Core/Vertex.h"
+#include "ZetaRenderPass/Common/FrameConstants.h"
+#include <cstddef>
 #include <cstring>
 
 using namespace ZetaRay;
@@ -80,5 +84,98 @@ extern "C"
         memcpy(outRot4, &u, 8);
         half3 h(float3(s3[0], s3[1], s3[2]));
         memcpy(outScale3, &h, 6);
+    }
+
+    // byte offset of a field of cbFrameConstants (Common/FrameConstants.h), -1 if unknown; "" -> sizeof
+    int ref_frame_constants_offset(const char* field)
+    {
+        if (!field[0]) return (int)sizeof(cbFrameConstants);
+        if (!strcmp(field, "CurrView")) return (int)offsetof(cbFrameConstants, CurrView);
+        if (!strcmp(field, "PrevView")) return (int)offsetof(cbFrameConstants, PrevView);
+        if (!strcmp(field, "CurrViewInv")) return (int)offsetof(cbFrameConstants, CurrViewInv);
+        if (!strcmp(field, "PrevViewInv")) return (int)offsetof(cbFrameConstants, PrevViewInv);
+        if (!strcmp(field, "CurrViewProj")) return (int)offsetof(cbFrameConstants, CurrViewProj);
+        if (!strcmp(field, "PrevViewProj")) return (int)offsetof(cbFrameConstants, PrevViewProj);
+        if (!strcmp(field, "CameraPos")) return (int)offsetof(cbFrameConstants, CameraPos);
+        if (!strcmp(field, "CameraNear")) return (int)offsetof(cbFrameConstants, CameraNear);
+        if (!strcmp(field, "AspectRatio")) return (int)offsetof(cbFrameConstants, AspectRatio);
+        if (!strcmp(field, "PixelSpreadAngle")) return (int)offsetof(cbFrameConstants, PixelSpreadAngle);
+        if (!strcmp(field, "TanHalfFOV")) return (int)offsetof(cbFrameConstants, TanHalfFOV);
+        if (!strcmp(field, "dt")) return (int)offsetof(cbFrameConstants, dt);
+        if (!strcmp(field, "FrameNum")) return (int)offsetof(cbFrameConstants, FrameNum);
+        if (!strcmp(field, "CurrGBufferDescHeapOffset")) return (int)offsetof(cbFrameConstants, CurrGBufferDescHeapOffset);
+        if (!strcmp(field, "PrevGBufferDescHeapOffset")) return (int)offsetof(cbFrameConstants, PrevGBufferDescHeapOffset);
+        if (!strcmp(field, "BaseColorMapsDescHeapOffset")) return (int)offsetof(cbFrameConstants, BaseColorMapsDescHeapOffset);
+        if (!strcmp(field, "NormalMapsDescHeapOffset")) return (int)offsetof(cbFrameConstants, NormalMapsDescHeapOffset);
+        if (!strcmp(field, "MetallicRoughnessMapsDescHeapOffset")) return (int)offsetof(cbFrameConstants, MetallicRoughnessMapsDescHeapOffset);
+        if (!strcmp(field, "EmissiveMapsDescHeapOffset")) return (int)offsetof(cbFrameConstants, EmissiveMapsDescHeapOffset);
+        if (!strcmp(field, "EnvMapDescHeapOffset")) return (int)offsetof(cbFrameConstants, EnvMapDescHeapOffset);
+        if (!strcmp(field, "RenderWidth")) return (int)offsetof(cbFrameConstants, RenderWidth);
+        if (!strcmp(field, "RenderHeight")) return (int)offsetof(cbFrameConstants, RenderHeight);
+        if (!strcmp(field, "DisplayWidth")) return (int)offsetof(cbFrameConstants, DisplayWidth);
+        if (!strcmp(field, "DisplayHeight")) return (int)offsetof(cbFrameConstants, DisplayHeight);
+        if (!strcmp(field, "CurrCameraJitter")) return (int)offsetof(cbFrameConstants, CurrCameraJitter);
+        if (!strcmp(field, "PrevCameraJitter")) return (int)offsetof(cbFrameConstants, PrevCameraJitter);
+        if (!strcmp(field, "PlanetRadius")) return (int)offsetof(cbFrameConstants, PlanetRadius);
+        if (!strcmp(field, "SunCosAngularRadius")) return (int)offsetof(cbFrameConstants, SunCosAngularRadius);
+        if (!strcmp(field, "SunSinAngularRadius")) return (int)offsetof(cbFrameConstants, SunSinAngularRadius);
+        if (!strcmp(field, "pad")) return (int)offsetof(cbFrameConstants, pad);
+        if (!strcmp(field, "SunDir")) return (int)offsetof(cbFrameConstants, SunDir);
+        if (!strcmp(field, "SunIlluminance")) return (int)offsetof(cbFrameConstants, SunIlluminance);
+        if (!strcmp(field, "RayleighSigmaSColor")) return (int)offsetof(cbFrameConstants, RayleighSigmaSColor);
+        if (!strcmp(field, "RayleighSigmaSScale")) return (int)offsetof(cbFrameConstants, RayleighSigmaSScale);
+        if (!strcmp(field, "OzoneSigmaAColor")) return (int)offsetof(cbFrameConstants, OzoneSigmaAColor);
+        if (!strcmp(field, "OzoneSigmaAScale")) return (int)offsetof(cbFrameConstants, OzoneSigmaAScale);
+        if (!strcmp(field, "MieSigmaS")) return (int)offsetof(cbFrameConstants, MieSigmaS);
+        if (!strcmp(field, "MieSigmaA")) return (int)offsetof(cbFrameConstants, MieSigmaA);
+        if (!strcmp(field, "AtmosphereAltitude")) return (int)offsetof(cbFrameConstants, AtmosphereAltitude);
+        if (!strcmp(field, "g")) return (int)offsetof(cbFrameConstants, g);
+        if (!strcmp(field, "NumFramesCameraStatic")) return (int)offsetof(cbFrameConstants, NumFramesCameraStatic);
+        if (!strcmp(field, "CameraStatic")) return (int)offsetof(cbFrameConstants, CameraStatic);
+        if (!strcmp(field, "Accumulate")) return (int)offsetof(cbFrameConstants, Accumulate);
+        if (!strcmp(field, "SunMoved")) return (int)offsetof(cbFrameConstants, SunMoved);
+        if (!strcmp(field, "CameraRayUVGradsScale")) return (int)offsetof(cbFrameConstants, CameraRayUVGradsScale);
+        if (!strcmp(field, "MipBias")) return (int)offsetof(cbFrameConstants, MipBias);
+        if (!strcmp(field, "OneDivNumEmissiveTriangles")) return (int)offsetof(cbFrameConstants, OneDivNumEmissiveTriangles);
+        if (!strcmp(field, "NumEmissiveTriangles")) return (int)offsetof(cbFrameConstants, NumEmissiveTriangles);
+        if (!strcmp(field, "FocusDepth")) return (int)offsetof(cbFrameConstants, FocusDepth);
+        if (!strcmp(field, "LensRadius")) return (int)offsetof(cbFrameConstants, LensRadius);
+        if (!strcmp(field, "DoF")) return (int)offsetof(cbFrameConstants, DoF);
+        if (!strcmp(field, "pad2")) return (int)offsetof(cbFrameConstants, pad2);
+        return -1;
+    }
+    int ref_struct_offset(const char* strct, const char* field)
+    {
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "BaseVtxOffset")) return (int)offsetof(RT::MeshInstance, BaseVtxOffset);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "BaseIdxOffset")) return (int)offsetof(RT::MeshInstance, BaseIdxOffset);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "Rotation")) return (int)offsetof(RT::MeshInstance, Rotation);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "Scale")) return (int)offsetof(RT::MeshInstance, Scale);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "MatIdx")) return (int)offsetof(RT::MeshInstance, MatIdx);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "BaseEmissiveTriOffset")) return (int)offsetof(RT::MeshInstance, BaseEmissiveTriOffset);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "Translation")) return (int)offsetof(RT::MeshInstance, Translation);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "PrevRotation")) return (int)offsetof(RT::MeshInstance, PrevRotation);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "PrevScale")) return (int)offsetof(RT::MeshInstance, PrevScale);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "dTranslation")) return (int)offsetof(RT::MeshInstance, dTranslation);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "BaseColorTex")) return (int)offsetof(RT::MeshInstance, BaseColorTex);
+        if (!strcmp(strct, "MeshInstance") && !strcmp(field, "AlphaFactor_Cutoff")) return (int)offsetof(RT::MeshInstance, AlphaFactor_Cutoff);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "Vtx0")) return (int)offsetof(RT::EmissiveTriangle, Vtx0);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "V0V1")) return (int)offsetof(RT::EmissiveTriangle, V0V1);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "V0V2")) return (int)offsetof(RT::EmissiveTriangle, V0V2);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "EdgeLengths")) return (int)offsetof(RT::EmissiveTriangle, EdgeLengths);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "ID")) return (int)offsetof(RT::EmissiveTriangle, ID);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "PackedA")) return (int)offsetof(RT::EmissiveTriangle, PackedA);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "PackedB")) return (int)offsetof(RT::EmissiveTriangle, PackedB);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "UV0")) return (int)offsetof(RT::EmissiveTriangle, UV0);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "UV1")) return (int)offsetof(RT::EmissiveTriangle, UV1);
+        if (!strcmp(strct, "EmissiveTriangle") && !strcmp(field, "UV2")) return (int)offsetof(RT::EmissiveTriangle, UV2);
+        if (!strcmp(strct, "Material") && !strcmp(field, "BaseColorFactor")) return (int)offsetof(Material, BaseColorFactor);
+        if (!strcmp(strct, "Material") && !strcmp(field, "BaseColorTex_Subsurf_CoatWeight")) return (int)offsetof(Material, BaseColorTex_Subsurf_CoatWeight);
+        if (!strcmp(strct, "Material") && !strcmp(field, "NormalTex_TrDepth")) return (int)offsetof(Material, NormalTex_TrDepth);
+        if (!strcmp(strct, "Material") && !strcmp(field, "MRTex_SpecRoughness_CoatRoughness")) return (int)offsetof(Material, MRTex_SpecRoughness_CoatRoughness);
+        if (!strcmp(strct, "Material") && !strcmp(field, "EmissiveFactor_NormalScale")) return (int)offsetof(Material, EmissiveFactor_NormalScale);
+        if (!strcmp(strct, "Material") && !strcmp(field, "EmissiveStrength_IOR")) return (int)offsetof(Material, EmissiveStrength_IOR);
+        if (!strcmp(strct, "Material") && !strcmp(field, "EmissiveTex_AlphaCutoff_CoatIOR")) return (int)offsetof(Material, EmissiveTex_AlphaCutoff_CoatIOR);
+        if (!strcmp(strct, "Material") && !strcmp(field, "CoatColor_Flags")) return (int)offsetof(Material, CoatColor_Flags);
+        return -1;
     }
 }

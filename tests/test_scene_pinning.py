@@ -111,3 +111,25 @@ def test_instance_rotation_and_scale(ref):
         ref.ref_instance_rotation_scale(q32.ctypes.data_as(C.c_void_p), s32.ctypes.data_as(C.c_void_p), rot.ctypes.data_as(C.c_void_p),
                                         sc.ctypes.data_as(C.c_void_p))
         assert np.array_equal(inst["Rotation"], rot) and np.array_equal(inst["Scale"], sc), k
+
+
+def test_frame_constants_layout_matches_the_reference_header(ref):
+    """zr_frame_constants (include/zr_abi.h, mirrored by zetaray_b200._lib.FrameConstants) is cbFrameConstants field for field:
+    every offset and the size, taken from the reference's own Common/FrameConstants.h compiled by g++."""
+    from zetaray_b200 import _lib
+    FC = _lib.FrameConstants
+    assert ref.ref_frame_constants_offset(b"") == C.sizeof(FC) == 544
+    names = [f[0] for f in FC._fields_]
+    assert len(names) == 52
+    for name in names:
+        want = ref.ref_frame_constants_offset(name.encode())
+        assert want >= 0, "the reference has no field " + name
+        assert getattr(FC, name).offset == want, (name, getattr(FC, name).offset, want)
+
+
+def test_scene_struct_field_offsets(ref):
+    for strct, dt in (("MeshInstance", zs.MESH_INSTANCE), ("EmissiveTriangle", zs.EMISSIVE_TRI), ("Material", zs.MATERIAL)):
+        for name in dt.names:
+            want = ref.ref_struct_offset(strct.encode(), name.encode())
+            assert want >= 0, (strct, name)
+            assert dt.fields[name][1] == want, (strct, name, dt.fields[name][1], want)
