@@ -1,6 +1,7 @@
 // ORACLE -- test infrastructure, not product code (see orc_math.h header).
 // Small C entry points so the CPU-only tests can probe codecs and the BSDF restatement directly.
 #include "orc_scene.h"
+#include "orc_rpt.h"
 
 using namespace orc;
 
@@ -130,5 +131,18 @@ extern "C"
         out[6] = asuint(ls.le.x); out[7] = asuint(ls.le.y); out[8] = asuint(ls.le.z);
         out[9] = asuint(ls.bary.x); out[10] = asuint(ls.bary.y); out[11] = asuint(ls.pdf); out[12] = ls.idx; out[13] = ls.ID; out[14] = ls.twoSided;
         out[15] = rng.State;
+    }
+
+    // ReSTIR PT reservoir record: Load -> Write(M_max) -> out, and Load -> WriteReservoirData(M_max) over a copy of the input -> out2
+    void orc_probe_rpt_reservoir(const zr_rpt_reservoir* in, uint32_t n, uint32_t M_max, zr_rpt_reservoir* out, zr_rpt_reservoir* out2)
+    {
+        for (uint32_t i = 0; i < n; i++)
+        {
+            RPT::Reservoir r = RPT::Reservoir::Load(in[i]);
+            memset(&out[i], 0, sizeof(out[i]));
+            r.Write(out[i], M_max);
+            out2[i] = in[i];
+            r.WriteReservoirData(out2[i], M_max);
+        }
     }
 }

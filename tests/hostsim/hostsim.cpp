@@ -15,6 +15,13 @@ template<typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 template<typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+// a "block" of one thread: barriers are no-ops, block votes / ballots see only this lane (the split-phase functions of zr_rpt.cuh
+// are included for their per-thread arithmetic; wave-scope results are not compared on the host)
+static inline void __syncthreads() {}
+static inline int __syncthreads_or(int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template<typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 
 struct ZrTraverseStats { unsigned long long nodes, tris; };
 static thread_local ZrTraverseStats g_stats;
@@ -22,6 +29,7 @@ static thread_local ZrTraverseStats g_stats;
 #include "../../zetaray_b200/csrc/zr_scene.cuh"
 #include "../../zetaray_b200/csrc/zr_bsdf.cuh"
 #include "../../zetaray_b200/csrc/zr_rt.cuh"
+#include "../../zetaray_b200/csrc/zr_rpt.cuh"
 
 namespace zr
 {
@@ -342,5 +350,18 @@ extern "C"
         out[6] = asuint(ls.le.x); out[7] = asuint(ls.le.y); out[8] = asuint(ls.le.z);
         out[9] = asuint(ls.bary.x); out[10] = asuint(ls.bary.y); out[11] = asuint(ls.pdf); out[12] = ls.idx; out[13] = ls.ID; out[14] = ls.twoSided;
         out[15] = rng.State;
+    }
+}
+
+// ---- ReSTIR PT reservoir record codec (zr_rpt.cuh RPT::Reservoir) ----
+extern "C" void hostsim_probe_rpt_reservoir(const zr_rpt_reservoir* in, uint32_t n, uint32_t M_max, zr_rpt_reservoir* out, zr_rpt_reservoir* out2)
+{
+    for (uint32_t i = 0; i < n; i++)
+    {
+        zr::RPT::Reservoir r = zr::RPT::Reservoir::Load(in[i]);
+        memset(&out[i], 0, sizeof(out[i]));
+        r.Write(out[i], M_max);
+        out2[i] = in[i];
+        r.WriteReservoirData(out2[i], M_max);
     }
 }

@@ -174,3 +174,31 @@ def test_ray_query_material_and_light_sampling_device_source_vs_oracle(which, de
         assert bytes(a)[:64] == bytes(b)[:64], (which, int(k), list(a)[:16], list(b)[:16])
     assert hits > len(pick) // 4     # a good share of the queries hit something (the Cornell box is open at the front)
     assert lights > 0                # and some BSDF-direction queries end on a light
+
+
+@pytest.mark.parametrize("which", ["glossy", "glass", "tunnel"])
+def test_restir_pt_reservoir_record_codec(which):
+    """RPT::Reservoir of zr_rpt.cuh (host build) against the oracle's on real reservoirs: every 64-byte record an oracle frame
+    sequence produces (all reconnection cases k = 2 / k > 2, lobes, light types, empty reservoirs) is loaded and written back
+    (full write with the M clamp, and the partial WriteReservoirData) by both; the bytes must agree."""
+    from tests import scene_util, rpt_util
+    hs = hostsim.load()
+    w, h = 128, 72
+    R = rpt_util.OracleRenderer(scene_util.SCENES[which](), w, h)
+    cam = scene_util.CAMERAS.get(which)
+    seq = rpt_util.FrameSequence(w, h, cam_path=(lambda f: cam) if cam else None)
+    seen_k = set()
+    for fr in range(3):
+        fc = seq.next()
+        R.gbuffer(fc); R.rpt(fc)
+        res = np.ascontiguousarray(R.curr_reservoirs())
+        n = len(res)
+        seen_k |= set(np.unique(res["meta"] & 0xf).tolist())
+        for m_max in (0, 4, 10):
+            oa = np.zeros(n, dtype=rpt_util.RES); ob = np.zeros(n, dtype=rpt_util.RES)
+            da = np.zeros(n, dtype=rpt_util.RES); db = np.zeros(n, dtype=rpt_util.RES)
+            R.o.orc_probe_rpt_reservoir(ptr(res), n, m_max, ptr(oa), ptr(ob))
+            hs.hostsim_probe_rpt_reservoir(ptr(res), n, m_max, ptr(da), ptr(db))
+            assert oa.tobytes() == da.tobytes(), (which, fr, m_max, int((oa != da).sum()))
+            assert ob.tobytes() == db.tobytes(), (which, fr, m_max)
+    assert 0 in seen_k and 15 in seen_k
