@@ -145,4 +145,33 @@ extern "C"
             r.WriteReservoirData(out2[i], M_max);
         }
     }
+
+    // The hybrid shift of ReSTIR PT (Shift.hlsli: random replay for k > 2, then reconnection) applied to a path held in a
+    // 64-byte reservoir record, from a NEW primary vertex: the first hit of the camera ray (origin, dir).
+    // out (8 words): {valid destination, shift.target xyz, shift.partialJacobian, surfKMin1Transmissive, k, replay throughput.x}
+    void orc_probe_rpt_shift(void* scene_, const float* ray6, const zr_rpt_reservoir* rec, float alpha_min, uint32_t* out)
+    {
+        const Scene& sc = *(const Scene*)scene_;
+        memset(out, 0, 8 * 4);
+        const float3 o = f3(ray6[0], ray6[1], ray6[2]), d = f3(ray6[3], ray6[4], ray6[5]);
+        // the camera ray as a "path vertex" query: start slightly behind o along -d with d as the normal
+        Hit h = FindClosest(sc, o, d, d, false);
+        if (!h.hit) return;
+        BSDF::ShadingData surface = BSDF::ShadingData::InitEmpty(); float eta;
+        if (!GetMaterialData(sc, -d, BSDF::ETA_AIR, h, surface, eta)) return;
+        const float3 pos = mad(h.t, d, RTU::OffsetRayRTG(o, d));
+        RPT::Reservoir r = RPT::Reservoir::Load(*rec);
+        if (r.rc.Empty()) return;
+        out[0] = 1; out[6] = r.rc.k;
+        RPT::OffsetPathContext ctx = RPT::OffsetPathContext::Init(); const RPT::OffsetPathContext* pctx = nullptr;
+        if (r.rc.k > 2)
+        {
+            ctx = RPT::Replay_kGt2(sc, pos, h.normal, eta, surface, r.rc, alpha_min).Quantize();
+            pctx = &ctx;
+            out[7] = asuint(ctx.throughput.x);
+        }
+        RPT::OffsetPath shift = RPT::Shift2(sc, pos, h.normal, eta, surface, r.rc, pctx, alpha_min);
+        out[1] = asuint(shift.target.x); out[2] = asuint(shift.target.y); out[3] = asuint(shift.target.z);
+        out[4] = asuint(shift.partialJacobian); out[5] = shift.surfKMin1Tramsmissive;
+    }
 }

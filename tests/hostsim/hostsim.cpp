@@ -365,3 +365,29 @@ extern "C" void hostsim_probe_rpt_reservoir(const zr_rpt_reservoir* in, uint32_t
         r.WriteReservoirData(out2[i], M_max);
     }
 }
+
+// ---- the hybrid shift (zr_rpt.cuh Replay_kGt2_Sync / Shift2_Sync as a block of one thread) ----
+extern "C" void hostsim_probe_rpt_shift(const hostsim_scene* hsc, const float* ray6, const zr_rpt_reservoir* rec, float alpha_min, uint32_t* out)
+{
+    using namespace zr;
+    const SceneDev sc = dev_of(hsc);
+    memset(out, 0, 8 * 4);
+    const float3 o = f3(ray6[0], ray6[1], ray6[2]), d = f3(ray6[3], ray6[4], ray6[5]);
+    Hit h = FindClosest(sc, o, d, d, false);
+    if (!h.hit) return;
+    BSDF::ShadingData surface = BSDF::ShadingData::InitEmpty(); float eta;
+    if (!GetMaterialData(sc, -d, BSDF::ETA_AIR, h, surface, eta)) return;
+    const float3 pos = mad(h.t, d, RTU::OffsetRayRTG(o, d));
+    RPT::Reservoir r = RPT::Reservoir::Load(*rec);
+    if (r.rc.Empty()) return;
+    out[0] = 1; out[6] = r.rc.k;
+    RPT::OffsetPathContext ctx = RPT::OffsetPathContext::Init();
+    if (r.rc.k > 2)
+    {
+        ctx = RPT::Replay_kGt2_Sync(true, sc, pos, h.normal, eta, surface, r.rc, alpha_min).Quantize();
+        out[7] = asuint(ctx.throughput.x);
+    }
+    RPT::OffsetPath shift = RPT::Shift2_Sync(true, sc, pos, h.normal, eta, surface, r.rc, &ctx, alpha_min);
+    out[1] = asuint(shift.target.x); out[2] = asuint(shift.target.y); out[3] = asuint(shift.target.z);
+    out[4] = asuint(shift.partialJacobian); out[5] = shift.surfKMin1Tramsmissive;
+}

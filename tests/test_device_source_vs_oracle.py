@@ -202,3 +202,53 @@ def test_restir_pt_reservoir_record_codec(which):
             assert oa.tobytes() == da.tobytes(), (which, fr, m_max, int((oa != da).sum()))
             assert ob.tobytes() == db.tobytes(), (which, fr, m_max)
     assert 0 in seen_k and 15 in seen_k
+
+
+@pytest.mark.parametrize("which", ["glossy", "glass", "tunnel"])
+def test_restir_pt_hybrid_shift(which):
+    """The heart of ReSTIR PT on the CPU tier: random replay (k > 2) + reconnection shift of zr_rpt.cuh, run as a block of one
+    thread on a host-resident scene, against the oracle's Replay_kGt2 / Shift2. Paths come from real reservoirs of an oracle
+    frame sequence, destinations are first hits of camera rays through OTHER pixels (as spatial reuse does), so all three
+    reconnection cases, replayed prefixes through glossy / transmissive lobes, failed replays and occluded reconnections occur."""
+    from tests import scene_util, rpt_util
+    from tests.test_bvh_host import world_tris, build
+    from tests.test_procedural_scenes import _camera_rays
+    hs = hostsim.load()
+    w, h = 96, 54
+    flat = scene_util.SCENES[which]()
+    R = rpt_util.OracleRenderer(flat, w, h)
+    osc = R.osc
+    hs.hostsim_set_rho_lut(ptr(osc.lut))
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: cam)
+    for fr in range(3):
+        fc = seq.next()
+        R.gbuffer(fc); R.rpt(fc)
+    res = np.ascontiguousarray(R.curr_reservoirs())
+    wt, tri_mesh, first = world_tris(flat)
+    nodes, order, leaf, info = build(wt)
+    keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances, flat.materials, flat.emissives, osc.alias)]
+    hsc = HostScene(*[k.ctypes.data for k in keep], nodes.ctypes.data, leaf.ctypes.data, tri_mesh.ctypes.data, first.ctypes.data,
+                    osc.lut.ctypes.data, len(flat.instances), len(flat.emissives), len(wt))
+    rays = _camera_rays(np.array(cam, dtype=np.float32), w, h)
+    rng = np.random.default_rng(17)
+    nonempty = np.nonzero((res["meta"] & 0xf) != 15)[0]
+    a = (C.c_uint32 * 8)(); b = (C.c_uint32 * 8)()
+    stats = dict(valid=0, kgt2=0, nonzero=0, replay_ok=0)
+    alpha_min = C.c_float(float(np.float32(0.175) * np.float32(0.175)))
+    for it in range(2500):
+        src = int(nonempty[rng.integers(0, len(nonempty))])
+        sx, sy = src % w, src // w
+        dx, dy = rng.integers(-6, 7, 2)
+        px = int(np.clip(sx + dx, 0, w - 1)); py = int(np.clip(sy + dy, 0, h - 1))
+        ray = np.concatenate([rays[py * w + px, 0:3], rays[py * w + px, 4:7]]).astype(np.float32)
+        rec = res[src:src + 1]
+        R.o.orc_probe_rpt_shift(osc.h, ptr(ray), ptr(rec), alpha_min, a)
+        hs.hostsim_probe_rpt_shift(C.byref(hsc), ptr(ray), ptr(rec), alpha_min, b)
+        assert bytes(a) == bytes(b), (which, it, src, (px, py), list(a), list(b))
+        stats["valid"] += a[0]; stats["kgt2"] += a[6] > 2
+        stats["nonzero"] += (a[1] | a[2] | a[3]) != 0
+        stats["replay_ok"] += a[7] != 0
+    print(which, stats)
+    assert stats["valid"] > 500 and stats["nonzero"] > 150, stats
+    assert stats["kgt2"] > 10 and stats["replay_ok"] > 3, stats          # replayed prefixes occur and some replays succeed
