@@ -2,6 +2,7 @@
 // Small C entry points so the CPU-only tests can probe codecs and the BSDF restatement directly.
 #include "orc_scene.h"
 #include "orc_rpt.h"
+#include "orc_pixel.h"
 
 using namespace orc;
 
@@ -173,5 +174,32 @@ extern "C"
         RPT::OffsetPath shift = RPT::Shift2(sc, pos, h.normal, eta, surface, r.rc, pctx, alpha_min);
         out[1] = asuint(shift.target.x); out[2] = asuint(shift.target.y); out[3] = asuint(shift.target.z);
         out[4] = asuint(shift.partialJacobian); out[5] = shift.surfKMin1Tramsmissive;
+    }
+
+    // LoadPixel (the per-pixel reconstruction every lighting kernel starts with) over a whole G-buffer.
+    // out: 16 words per pixel {flags byte, roughness, z, pos(3), normal(3), origin(3), eta_next, then a BSDF sample's wi.x, pdf, bsdfOverPdf.x}
+    void orc_probe_load_pixels(void* scene_, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* coat, int prev, uint32_t* out)
+    {
+        Frame f;
+        f.sc = (const Scene*)scene_; f.fc = fc; f.core = core; f.me = nullptr; f.coat = coat; f.pcore = core; f.pcoat = coat;
+        f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+        for (uint32_t y = 0; y < f.H; y++)
+            for (uint32_t x = 0; x < f.W; x++)
+            {
+                uint32_t* o = out + ((size_t)y * f.W + x) * 16;
+                memset(o, 0, 64);
+                const GFlags fl = FlagsAt(core, f.W, x, y);
+                if (fl.invalid) { o[0] = 0xffffffffu; continue; }
+                Pixel p = LoadPixel(f, core, coat, (int)x, (int)y, prev != 0, (int)x, (int)y);
+                o[0] = (p.flags.transmissive) | (p.flags.emissive << 1) | (p.flags.trDepthGt0 << 3) | (p.flags.subsurface << 4) | (p.flags.coated << 5) | (p.flags.metallic << 7);
+                o[1] = asuint(p.roughness); o[2] = asuint(p.z);
+                o[3] = asuint(p.pos.x); o[4] = asuint(p.pos.y); o[5] = asuint(p.pos.z);
+                o[6] = asuint(p.normal.x); o[7] = asuint(p.normal.y); o[8] = asuint(p.normal.z);
+                o[9] = asuint(p.origin.x); o[10] = asuint(p.origin.y); o[11] = asuint(p.origin.z);
+                o[12] = asuint(p.eta_next);
+                RNG rng = RNG::InitSeed(x * 7919u + y * 104729u + 1u);
+                BSDF::BSDFSample b = BSDF::SampleBSDF(p.normal, p.surface, rng);
+                o[13] = asuint(b.wi.x); o[14] = asuint(b.pdf); o[15] = asuint(b.bsdfOverPdf.x);
+            }
     }
 }

@@ -30,6 +30,7 @@ static thread_local ZrTraverseStats g_stats;
 #include "../../zetaray_b200/csrc/zr_bsdf.cuh"
 #include "../../zetaray_b200/csrc/zr_rt.cuh"
 #include "../../zetaray_b200/csrc/zr_rpt.cuh"
+#include "../../zetaray_b200/csrc/zr_pixel.cuh"
 
 namespace zr
 {
@@ -390,4 +391,32 @@ extern "C" void hostsim_probe_rpt_shift(const hostsim_scene* hsc, const float* r
     RPT::OffsetPath shift = RPT::Shift2_Sync(true, sc, pos, h.normal, eta, surface, r.rc, &ctx, alpha_min);
     out[1] = asuint(shift.target.x); out[2] = asuint(shift.target.y); out[3] = asuint(shift.target.z);
     out[4] = asuint(shift.partialJacobian); out[5] = shift.surfKMin1Tramsmissive;
+}
+
+// ---- LoadPixel (zr_pixel.cuh) over a whole host-resident G-buffer ----
+extern "C" void hostsim_probe_load_pixels(const hostsim_scene* hsc, const zr_frame_constants* fc, const void* core, const void* coat, int prev, uint32_t* out)
+{
+    using namespace zr;
+    const SceneDev sc = dev_of(hsc);
+    FrameView f{};
+    f.fc = *fc; f.core = (const uint4*)core; f.coat = (const uint2*)coat; f.pcore = f.core; f.pcoat = f.coat;
+    f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+    for (uint32_t y = 0; y < f.H; y++)
+        for (uint32_t x = 0; x < f.W; x++)
+        {
+            uint32_t* o = out + ((size_t)y * f.W + x) * 16;
+            memset(o, 0, 64);
+            const GFlags fl = FlagsAt(f.core, f.W, (int)x, (int)y);
+            if (fl.invalid) { o[0] = 0xffffffffu; continue; }
+            Pixel p = LoadPixel(f, sc, f.core, f.coat, (int)x, (int)y, prev != 0, (int)x, (int)y);
+            o[0] = (p.flags.transmissive) | (p.flags.emissive << 1) | (p.flags.trDepthGt0 << 3) | (p.flags.subsurface << 4) | (p.flags.coated << 5) | (p.flags.metallic << 7);
+            o[1] = asuint(p.roughness); o[2] = asuint(p.z);
+            o[3] = asuint(p.pos.x); o[4] = asuint(p.pos.y); o[5] = asuint(p.pos.z);
+            o[6] = asuint(p.normal.x); o[7] = asuint(p.normal.y); o[8] = asuint(p.normal.z);
+            o[9] = asuint(p.origin.x); o[10] = asuint(p.origin.y); o[11] = asuint(p.origin.z);
+            o[12] = asuint(p.eta_next);
+            RNG rng; rng.State = x * 7919u + y * 104729u + 1u;
+            BSDF::BSDFSample b = BSDF::SampleBSDF(p.normal, p.surface, rng);
+            o[13] = asuint(b.wi.x); o[14] = asuint(b.pdf); o[15] = asuint(b.bsdfOverPdf.x);
+        }
 }

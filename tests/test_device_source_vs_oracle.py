@@ -252,3 +252,32 @@ def test_restir_pt_hybrid_shift(which):
     print(which, stats)
     assert stats["valid"] > 500 and stats["nonzero"] > 150, stats
     assert stats["kgt2"] > 10 and stats["replay_ok"] > 3, stats          # replayed prefixes occur and some replays succeed
+
+
+@pytest.mark.parametrize("which,dof", [("glossy", False), ("glass", True), ("atrium", False)])
+def test_load_pixel_reconstruction(which, dof):
+    """LoadPixel of zr_pixel.cuh -- depth -> world position (pinhole and thin lens, current and previous camera), normal / material
+    decode, coat plane, the ShadingData every lighting kernel starts from (checked through a BSDF sample) -- against the oracle's,
+    over whole G-buffers the oracle rendered."""
+    from tests import scene_util, rpt_util
+    hs = hostsim.load()
+    w, h = 160, 90
+    flat = scene_util.SCENES[which]()
+    R = rpt_util.OracleRenderer(flat, w, h)
+    osc = R.osc
+    hs.hostsim_set_rho_lut(ptr(osc.lut))
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: (cam[0] + 0.03 * f, cam[1], cam[2] + 0.02 * f))
+    hsc = HostScene()
+    hsc.rho = osc.lut.ctypes.data
+    for fr in range(2):
+        fc = seq.next()
+        if dof:
+            fc.DoF, fc.FocusDepth, fc.LensRadius = 1, 4.0, 0.02
+        core, depth, me, coat, _ = R.gbuffer(fc)
+        for prev in (0, 1):
+            a = np.zeros((w * h, 16), dtype=np.uint32); b = np.zeros((w * h, 16), dtype=np.uint32)
+            R.o.orc_probe_load_pixels(osc.h, C.byref(fc), ptr(core), ptr(coat), prev, ptr(a))
+            hs.hostsim_probe_load_pixels(C.byref(hsc), C.byref(fc), ptr(core), ptr(coat), prev, ptr(b))
+            assert a.tobytes() == b.tobytes(), (which, fr, prev, int((a != b).any(axis=1).sum()))
+            assert (a[:, 0] != 0xffffffff).mean() > 0.5
