@@ -1,7 +1,6 @@
 """CPU tier: traversal cost of the product's BVH on the benchmark-size scenes, counted on the host build of the traversal source
 (node visits and triangle tests per ray). Guards the builder against quality regressions and the traversal against rays that sweep
 the tree (degenerate rays must cost nothing); the numbers are the ones DESIGN.md section 10 quotes."""
-import ctypes as C
 
 import numpy as np
 import pytest

@@ -4,7 +4,6 @@ product's numeric contract: no contraction, explicit fmaf, zr_fpmath transcenden
 used by ReSTIR GI's MIS), sampler evaluation, sampler pdfs and the unified evaluation. The GPU tier checks the same code through
 whole kernels; this test catches a one-sided edit of either transcription where the driver runs its CPU suite, without a GPU."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
