@@ -202,4 +202,22 @@ extern "C"
                 o[13] = asuint(b.wi.x); o[14] = asuint(b.pdf); o[15] = asuint(b.bsdfOverPdf.x);
             }
     }
+
+    // LVG::Sample (Common/LightVoxelGrid.hlsli:54-68) at a position, with the frame's view matrix; out: 13 words
+    void orc_probe_lvg_sample(void* scene_, const zr_frame_constants* fc, const float* pos3, uint32_t seed, uint32_t* out)
+    {
+        const Scene& sc = *(const Scene*)scene_;
+        memset(out, 0, 13 * 4);
+        RNG rng = RNG::InitSeed(seed);
+        zr_voxel_sample v;
+        const bool ok = LVG::Sample(sc, f3(pos3[0], pos3[1], pos3[2]), f3(sc.lvgExtents[0], sc.lvgExtents[1], sc.lvgExtents[2]), sc.lvgOffsetY,
+            fc->CurrView, v, rng);
+        out[0] = ok; out[12] = rng.State;
+        if (!ok) return;
+        const float3 n = Math::DecodeOct32(v.normal);
+        out[1] = asuint(v.pos[0]); out[2] = asuint(v.pos[1]); out[3] = asuint(v.pos[2]);
+        out[4] = asuint(n.x); out[5] = asuint(n.y); out[6] = asuint(n.z);
+        out[7] = asuint(zr_f16_to_f32(v.le[0])); out[8] = asuint(zr_f16_to_f32(v.le[1])); out[9] = asuint(zr_f16_to_f32(v.le[2]));
+        out[10] = asuint(v.pdf); out[11] = v.ID;
+    }
 }

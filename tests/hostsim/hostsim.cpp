@@ -291,6 +291,9 @@ extern "C"
         const void* vertices; const uint32_t* indices; const void* instances; const void* materials; const void* emissives;
         const void* aliasTable; const void* nodes; const float* leafTris; const uint32_t* triMesh; const uint32_t* meshFirstTri;
         const uint16_t* rho; uint32_t numInstances, numEmissives, numTris;
+        // optional: presampled emissive sets and the light voxel grid, as the oracle built them
+        const void* sampleSets; uint32_t numSampleSets, sampleSetSize;
+        const void* lvg; uint32_t lvgDim[3]; float lvgExtents[3]; float lvgOffsetY;
     };
     static zr::SceneDev dev_of(const hostsim_scene* h)
     {
@@ -300,6 +303,10 @@ extern "C"
         sc.aliasTable = (const zr_alias_entry*)h->aliasTable; sc.nodes = (const uint4*)h->nodes; sc.tris = (const float4*)h->leafTris;
         sc.triMesh = h->triMesh; sc.meshFirstTri = h->meshFirstTri; sc.rho = h->rho;
         sc.numInstances = h->numInstances; sc.numEmissives = h->numEmissives; sc.numTris = h->numTris;
+        sc.sampleSets = (const zr_presampled_tri*)h->sampleSets; sc.numSampleSets = h->numSampleSets; sc.sampleSetSize = h->sampleSetSize;
+        sc.lvg = (const zr_voxel_sample*)h->lvg;
+        for (int i = 0; i < 3; i++) { sc.lvgDim[i] = h->lvgDim[i]; sc.lvgExtents[i] = h->lvgExtents[i]; }
+        sc.lvgOffsetY = h->lvgOffsetY;
         return sc;
     }
     void hostsim_probe_path_vertex(const hostsim_scene* hsc, const float* in, uint32_t seed, uint32_t* out)
@@ -419,4 +426,21 @@ extern "C" void hostsim_probe_load_pixels(const hostsim_scene* hsc, const zr_fra
             BSDF::BSDFSample b = BSDF::SampleBSDF(p.normal, p.surface, rng);
             o[13] = asuint(b.wi.x); o[14] = asuint(b.pdf); o[15] = asuint(b.bsdfOverPdf.x);
         }
+}
+
+extern "C" void hostsim_probe_lvg_sample(const hostsim_scene* hsc, const zr_frame_constants* fc, const float* pos3, uint32_t seed, uint32_t* out)
+{
+    using namespace zr;
+    const SceneDev sc = dev_of(hsc);
+    memset(out, 0, 13 * 4);
+    RNG rng; rng.State = seed;
+    LVG::VoxelLight v;
+    const bool ok = LVG::Sample(sc, f3(pos3[0], pos3[1], pos3[2]), f3(sc.lvgExtents[0], sc.lvgExtents[1], sc.lvgExtents[2]), sc.lvgOffsetY,
+        fc->CurrView, v, rng);
+    out[0] = ok; out[12] = rng.State;
+    if (!ok) return;
+    out[1] = asuint(v.pos.x); out[2] = asuint(v.pos.y); out[3] = asuint(v.pos.z);
+    out[4] = asuint(v.normal.x); out[5] = asuint(v.normal.y); out[6] = asuint(v.normal.z);
+    out[7] = asuint(v.le.x); out[8] = asuint(v.le.y); out[9] = asuint(v.le.z);
+    out[10] = asuint(v.pdf); out[11] = v.ID;
 }

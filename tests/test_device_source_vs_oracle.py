@@ -112,7 +112,9 @@ class HostScene(C.Structure):
     _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("instances", C.c_void_p), ("materials", C.c_void_p),
                 ("emissives", C.c_void_p), ("aliasTable", C.c_void_p), ("nodes", C.c_void_p), ("leafTris", C.c_void_p),
                 ("triMesh", C.c_void_p), ("meshFirstTri", C.c_void_p), ("rho", C.c_void_p),
-                ("numInstances", C.c_uint32), ("numEmissives", C.c_uint32), ("numTris", C.c_uint32)]
+                ("numInstances", C.c_uint32), ("numEmissives", C.c_uint32), ("numTris", C.c_uint32),
+                ("sampleSets", C.c_void_p), ("numSampleSets", C.c_uint32), ("sampleSetSize", C.c_uint32),
+                ("lvg", C.c_void_p), ("lvgDim", C.c_uint32 * 3), ("lvgExtents", C.c_float * 3), ("lvgOffsetY", C.c_float)]
 
 
 @pytest.mark.parametrize("which,detail,nq", [("cornell", None, 3000), ("atrium", 0.5, 1200), ("tunnel", 0.35, 600)])
@@ -280,3 +282,45 @@ def test_load_pixel_reconstruction(which, dof):
             hs.hostsim_probe_load_pixels(C.byref(hsc), C.byref(fc), ptr(core), ptr(coat), prev, ptr(b))
             assert a.tobytes() == b.tobytes(), (which, fr, prev, int((a != b).any(axis=1).sum()))
             assert (a[:, 0] != 0xffffffff).mean() > 0.5
+
+
+def test_presampled_sets_and_light_voxel_grid_consumers():
+    """Light::SampleLight's presampled-set branch (40-byte records, with and without the RNG advance the path tracer asks for) and
+    LVG::Sample (jittered position -> voxel -> one of its 64 records) of zr_rt.cuh against the oracle, on the sets and the grid the
+    oracle built for the many-lights atrium (>= 13107 emissive triangles, the reference's defaults 128 x 512 and 32 x 8 x 40)."""
+    from tests import scene_util, rpt_util
+    hs = hostsim.load()
+    w, h = 96, 54
+    flat = scene_util.atrium_many_lights()
+    R = rpt_util.OracleRenderer(flat, w, h)
+    osc = R.osc
+    osc.set_presampling(128, 512)
+    osc.set_light_voxel_grid((32, 8, 40), (0.6, 0.45, 0.6), 0.1)
+    cam = scene_util.CAMERAS["atrium_lights"]
+    fc = rpt_util.FrameSequence(w, h, cam_path=lambda f: cam).next()
+    core, depth, me, coat, _ = R.gbuffer(fc)          # runs presampling and the grid build for this frame
+    hsc = HostScene()
+    keep = [np.ascontiguousarray(x) for x in (flat.emissives, osc.alias)]
+    hsc.emissives, hsc.aliasTable = keep[0].ctypes.data, keep[1].ctypes.data
+    hsc.numEmissives = len(flat.emissives)
+    hsc.rho = osc.lut.ctypes.data
+    hsc.sampleSets, hsc.numSampleSets, hsc.sampleSetSize = osc.sample_sets.ctypes.data, 128, 512
+    hsc.lvg = osc.lvg.ctypes.data
+    hsc.lvgDim[:] = (32, 8, 40); hsc.lvgExtents[:] = (0.6, 0.45, 0.6); hsc.lvgOffsetY = 0.1
+    # positions: the primary hits of this frame (LoadPixel reconstruction) plus points far outside the grid
+    px = np.zeros((w * h, 16), dtype=np.uint32)
+    R.o.orc_probe_load_pixels(osc.h, C.byref(fc), ptr(core), ptr(coat), 0, ptr(px))
+    pos = px[px[:, 0] != 0xffffffff][:, 3:6].copy().view(np.float32)
+    rng = np.random.default_rng(23)
+    a = (C.c_uint32 * 16)(); b = (C.c_uint32 * 16)()
+    inside = 0
+    for k in range(3000):
+        p3 = pos[rng.integers(0, len(pos))].copy() if k % 10 else (rng.normal(size=3) * 40).astype(np.float32)
+        seed = int(rng.integers(1, 2**32 - 1)); sset = int(rng.integers(0, 128))
+        for adv in (0, 1):
+            R.o.orc_probe_sample_light(osc.h, ptr(p3), sset, seed, adv, a); hs.hostsim_probe_sample_light(C.byref(hsc), ptr(p3), sset, seed, adv, b)
+            assert bytes(a) == bytes(b), ("SampleLight presampled", k, adv, list(a), list(b))
+        R.o.orc_probe_lvg_sample(osc.h, C.byref(fc), ptr(p3), seed, a); hs.hostsim_probe_lvg_sample(C.byref(hsc), C.byref(fc), ptr(p3), seed, b)
+        assert bytes(a)[:52] == bytes(b)[:52], ("LVG::Sample", k, list(a)[:13], list(b)[:13])
+        inside += a[0]
+    assert 1500 < inside < 3000          # most positions fall into the grid, the far ones do not
