@@ -740,6 +740,57 @@ namespace
 
 extern "C"
 {
+    // Probe for the CPU-tier device-source parity test (tests/test_device_source_vs_oracle.py): ReSTIR GI's temporal reuse at one pixel,
+    // starting from a given initial reservoir record. Mirrors EstimateIndirectLighting :564-596 (candidate search, one- or
+    // two-candidate resampling). out: the resulting 48-byte record, then target_z (3 words), rng state, #valid candidates.
+    void orc_probe_rgi_temporal(void* scene, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* me, const orc::uint2* coat,
+        const orc::uint4* pcore, const orc::uint2* pcoat, const zr_rgi_reservoir* prevRes, const zr_rgi_reservoir* initial, int x, int y,
+        uint32_t seed, uint32_t M_max, uint32_t* out)
+    {
+        using namespace orc;
+        Frame f;
+        f.sc = (const Scene*)scene; f.fc = fc; f.core = core; f.me = me; f.coat = coat; f.pcore = pcore; f.pcoat = pcoat;
+        f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+        memset(out, 0, 17 * 4);
+        const size_t idx = (size_t)y * f.W + x;
+        const GFlags flags = FlagsAt(core, f.W, x, y);
+        if (flags.invalid || flags.emissive) return;
+        Pixel p = LoadPixel(f, core, coat, x, y, false, x, y);
+        const GCore g = LoadCore(core, idx);
+        const float3 wo = normalize(p.origin - p.pos);
+        BSDF::ShadingData surface0 = BSDF::ShadingData::Init(p.normal, wo, flags.metallic, g.roughness, f3(g.baseColor.x, g.baseColor.y, g.baseColor.z),
+            BSDF::ETA_AIR, p.eta_next, flags.transmissive);
+        GIReservoir r = GIReservoir::Init();
+        r.pos = f3(initial->pos[0], initial->pos[1], initial->pos[2]); r.ID = initial->ID;
+        r.Lo = f3(zr_f16_to_f32((uint16_t)(initial->Lo_rg & 0xffff)), zr_f16_to_f32((uint16_t)(initial->Lo_rg >> 16)), zr_f16_to_f32((uint16_t)(initial->Lo_b_M & 0xffff)));
+        r.M = (float)(uint16_t)zr_f16_to_f32((uint16_t)(initial->Lo_b_M >> 16));
+        r.w_sum = initial->w_sum; r.W = initial->W; r.normal = Math::DecodeOct32(initial->normal);
+        if (r.ID != UINT32_MAX_)
+        {
+            float3 wi = r.pos - p.pos;
+            const float t = length(wi);
+            wi = wi / fmaxf(t, 1e-6f);
+            surface0.SetWi(wi, p.normal);
+            r.target_z = r.Lo * BSDF::Unified(surface0).f;
+        }
+        RNG rng = RNG::InitSeed(seed);
+        const float2 renderDim = f2((float)f.W, (float)f.H);
+        const float2 motionVec = unpack_snorm16x2(me[idx].x);
+        const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / renderDim;
+        const float2 prevUV = currUV - motionVec;
+        TemporalSampleData data[2]; bool valid[2];
+        FindTemporalCandidate(f, x, y, p.pos, p.normal, p.z, g.roughness, surface0.specTr, prevUV, rng, data, valid);
+        if (valid[1] && g.roughness > 0.05f)
+            TemporalResample2(f, prevRes, p.pos, p.normal, surface0, data, r, rng);
+        else if (valid[0])
+            TemporalResample1(f, prevRes, p.pos, p.normal, surface0, data[0], r, rng);
+        zr_rgi_reservoir rec;
+        WriteReservoir(rec, r, (float)M_max);
+        memcpy(out, &rec, 48);
+        out[12] = asuint(r.target_z.x); out[13] = asuint(r.target_z.y); out[14] = asuint(r.target_z.z);
+        out[15] = rng.State; out[16] = (valid[0] ? 1u : 0u) + (valid[1] ? 1u : 0u);
+    }
+
     // IndirectLighting with INTEGRATOR::PATH_TRACING (IndirectLighting.cpp: RenderPathTracer; PathTracer/PathTracer.hlsl), emissive NEE.
     // params: the same GIParams words (only the bounce budgets and the Russian-roulette flag are read).
     void orc_pt_render(void* scene, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* me, const orc::uint2* coat,

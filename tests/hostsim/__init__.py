@@ -10,7 +10,7 @@ SO = os.path.join(HERE, "libhostsim.so")
 def build(force=False):
     src = os.path.join(HERE, "hostsim.cpp")
     csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "zetaray_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("zr_scene.cuh", "zr_common.cuh", "zr_bvh.h", "zr_bsdf.cuh", "zr_rt.cuh", "zr_rpt.cuh", "zr_pixel.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("zr_scene.cuh", "zr_common.cuh", "zr_bvh.h", "zr_bsdf.cuh", "zr_rt.cuh", "zr_rpt.cuh", "zr_pixel.cuh", "zr_rgi.cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")

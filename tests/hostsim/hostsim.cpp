@@ -31,6 +31,7 @@ static thread_local ZrTraverseStats g_stats;
 #include "../../zetaray_b200/csrc/zr_rt.cuh"
 #include "../../zetaray_b200/csrc/zr_rpt.cuh"
 #include "../../zetaray_b200/csrc/zr_pixel.cuh"
+#include "../../zetaray_b200/csrc/zr_rgi.cuh"
 
 namespace zr
 {
@@ -443,4 +444,56 @@ extern "C" void hostsim_probe_lvg_sample(const hostsim_scene* hsc, const zr_fram
     out[4] = asuint(v.normal.x); out[5] = asuint(v.normal.y); out[6] = asuint(v.normal.z);
     out[7] = asuint(v.le.x); out[8] = asuint(v.le.y); out[9] = asuint(v.le.z);
     out[10] = asuint(v.pdf); out[11] = v.ID;
+}
+
+// ---- ReSTIR GI temporal reuse (zr_rgi.cuh) at one pixel, from a given initial reservoir record ----
+extern "C" void hostsim_probe_rgi_temporal(const hostsim_scene* hsc, const zr_frame_constants* fc, const void* core, const void* me, const void* coat,
+    const void* pcore, const void* pcoat, const zr_rgi_reservoir* prevRes, const zr_rgi_reservoir* initial, int x, int y, uint32_t seed, uint32_t M_max,
+    uint32_t* out)
+{
+    using namespace zr;
+    const SceneDev sc = dev_of(hsc);
+    FrameView f{};
+    f.fc = *fc; f.core = (const uint4*)core; f.me = (const uint2*)me; f.coat = (const uint2*)coat; f.pcore = (const uint4*)pcore; f.pcoat = (const uint2*)pcoat;
+    f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+    memset(out, 0, 17 * 4);
+    const size_t idx = (size_t)y * f.W + x;
+    float roughness = 0;
+    const GFlags flags = FlagsAt(f.core, f.W, x, y, &roughness);
+    if (flags.invalid || flags.emissive) return;
+    Pixel p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
+    const uint4 g = ld128(&f.core[idx]);
+    const float3 baseColor = f3((float)(g.z & 0xff) / 255.0f, (float)((g.z >> 8) & 0xff) / 255.0f, (float)((g.z >> 16) & 0xff) / 255.0f);
+    const float3 wo = normalize(p.origin - p.pos);
+    BSDF::ShadingData surface0 = BSDF::ShadingData::Init(p.normal, wo, flags.metallic, roughness, baseColor, BSDF::ETA_AIR, p.eta_next, flags.transmissive,
+        0.0f, 0.0f, 0.0f, f3(0.0f), 0.0f, BSDF::DEFAULT_ETA_COAT, sc.rho);
+    GIReservoir r = GIReservoir::Init();
+    r.pos = f3(initial->pos[0], initial->pos[1], initial->pos[2]); r.ID = initial->ID;
+    r.Lo = f3(zr_f16_to_f32((uint16_t)(initial->Lo_rg & 0xffff)), zr_f16_to_f32((uint16_t)(initial->Lo_rg >> 16)), zr_f16_to_f32((uint16_t)(initial->Lo_b_M & 0xffff)));
+    r.M = (float)(uint16_t)zr_f16_to_f32((uint16_t)(initial->Lo_b_M >> 16));
+    r.w_sum = initial->w_sum; r.W = initial->W; r.normal = Math::DecodeOct32(initial->normal);
+    if (r.ID != UINT32_MAX_)
+    {
+        float3 wi = r.pos - p.pos;
+        const float t = length(wi);
+        wi = wi / fmaxf(t, 1e-6f);
+        surface0.SetWi(wi, p.normal);
+        r.target_z = r.Lo * BSDF::Unified(surface0).f;
+    }
+    RNG rng; rng.State = seed;
+    const float2 renderDim = f2((float)f.W, (float)f.H);
+    const float2 motionVec = unpack_snorm16x2(f.me[idx].x);
+    const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / renderDim;
+    const float2 prevUV = currUV - motionVec;
+    TemporalSampleData data[2]; bool valid[2];
+    FindTemporalCandidate(f, sc, x, y, p.pos, p.normal, p.z, roughness, surface0.specTr, prevUV, rng, data, valid);
+    if (valid[1] && roughness > 0.05f)
+        TemporalResample2(f, sc, prevRes, p.pos, p.normal, surface0, data, r, rng);
+    else if (valid[0])
+        TemporalResample1(f, sc, prevRes, p.pos, p.normal, surface0, data[0], r, rng);
+    zr_rgi_reservoir rec;
+    WriteReservoir(rec, r, (float)M_max);
+    memcpy(out, &rec, 48);
+    out[12] = asuint(r.target_z.x); out[13] = asuint(r.target_z.y); out[14] = asuint(r.target_z.z);
+    out[15] = rng.State; out[16] = (valid[0] ? 1u : 0u) + (valid[1] ? 1u : 0u);
 }

@@ -324,3 +324,64 @@ def test_presampled_sets_and_light_voxel_grid_consumers():
         assert bytes(a)[:52] == bytes(b)[:52], ("LVG::Sample", k, list(a)[:13], list(b)[:13])
         inside += a[0]
     assert 1500 < inside < 3000          # most positions fall into the grid, the far ones do not
+
+
+@pytest.mark.parametrize("which,dof", [("glossy", False), ("glass", False), ("atrium", False), ("glossy", True)])
+def test_restir_gi_temporal_reuse(which, dof):
+    """ReSTIR GI's temporal reuse of zr_rgi.cuh (candidate search in the previous frame, target function at the temporal pixel with its
+    visibility test, reconnection Jacobians, one- and two-candidate resampling, reservoir record codec) against the oracle's, pixel
+    by pixel: the initial reservoirs of frame n (an oracle render with reuse switched off) are resampled against the oracle's
+    frame n-1 reservoirs and G-buffer, with a translating camera so that reprojection is not the identity."""
+    from tests import scene_util, rpt_util
+    from tests.test_bvh_host import world_tris, build
+    hs = hostsim.load()
+    w, h = 128, 72
+    flat = scene_util.SCENES[which]()
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    path = lambda f: (cam[0] + 0.03 * f, cam[1], cam[2] + 0.02 * f)
+
+    def frames(temporal_last):
+        R = rpt_util.OracleRenderer(flat, w, h)
+        R.gi_params.update(stochastic_multi_bounce=0)
+        seq = rpt_util.FrameSequence(w, h, cam_path=path)
+        out = []
+        for fr in range(3):
+            fc = seq.next()
+            if dof:
+                fc.DoF, fc.FocusDepth, fc.LensRadius = 1, 4.0, 0.02
+            if fr == 2:
+                R.gi_params.update(temporal_resample=int(temporal_last))
+            gb = R.gbuffer(fc)
+            prev_res = R.gi_curr_reservoirs().copy()
+            R.rgi(fc)
+            out.append((fc, gb, R.gb[R.cur ^ 1], prev_res, R.gi_curr_reservoirs().copy()))
+        return R, out
+    R, seq_out = frames(temporal_last=False)
+    fc, gb, gb_prev, prev_res, initial = seq_out[2]        # frame 3: initial candidates only; prev_res = frame 2's output
+    osc = R.osc
+    hs.hostsim_set_rho_lut(ptr(osc.lut))
+    wt, tri_mesh, first = world_tris(flat)
+    nodes, order, leaf, info = build(wt)
+    keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances, flat.materials, flat.emissives, osc.alias)]
+    hsc = HostScene()
+    (hsc.vertices, hsc.indices, hsc.instances, hsc.materials, hsc.emissives, hsc.aliasTable) = [k.ctypes.data for k in keep]
+    hsc.nodes, hsc.leafTris, hsc.triMesh, hsc.meshFirstTri, hsc.rho = nodes.ctypes.data, leaf.ctypes.data, tri_mesh.ctypes.data, first.ctypes.data, osc.lut.ctypes.data
+    hsc.numInstances, hsc.numEmissives, hsc.numTris = len(flat.instances), len(flat.emissives), len(wt)
+    core, depth, me, coat, _ = gb
+    pcore, _, _, pcoat, _ = gb_prev
+    prev_res = np.ascontiguousarray(prev_res); initial = np.ascontiguousarray(initial)
+    rng = np.random.default_rng(31)
+    a = (C.c_uint32 * 17)(); b = (C.c_uint32 * 17)()
+    ncand = [0, 0, 0]
+    changed = 0
+    for k in range(2500):
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        seed = int(rng.integers(1, 2**32 - 1))
+        ini = initial[y * w + x:y * w + x + 1]
+        R.o.orc_probe_rgi_temporal(osc.h, C.byref(fc), ptr(core), ptr(me), ptr(coat), ptr(pcore), ptr(pcoat), ptr(prev_res), ptr(ini), x, y, seed, 10, a)
+        hs.hostsim_probe_rgi_temporal(C.byref(hsc), C.byref(fc), ptr(core), ptr(me), ptr(coat), ptr(pcore), ptr(pcoat), ptr(prev_res), ptr(ini), x, y, seed, 10, b)
+        assert bytes(a) == bytes(b), (which, k, (x, y), list(a), list(b))
+        ncand[min(a[16], 2)] += 1
+        changed += bytes(a)[:16] != ini.tobytes()[:16]      # the resampled reservoir picked the temporal sample
+    print(which, "candidates 0/1/2:", ncand, "sample replaced:", changed)
+    assert ncand[1] + ncand[2] > 1000 and changed > 50, (ncand, changed)
