@@ -617,6 +617,42 @@ namespace
 
 extern "C"
 {
+    // Probe for the CPU-tier device-source parity test: ReSTIR DI at one pixel as the temporal kernel does it (mirrored by
+    // tests/hostsim/hostsim_di.cpp). out (14 words): the 32-byte reservoir record, target (3), rng state, candidate valid, #BSDF samples
+    void orc_probe_rdi_pixel(void* scene, const zr_frame_constants* fc, const orc::uint4* core, const orc::uint2* me, const orc::uint2* coat,
+        const orc::uint4* pcore, const orc::uint2* pcoat, const zr_rdi_reservoir* prevRes, int x, int y, uint32_t sampleSetIdx, int temporal,
+        uint32_t M_max, uint32_t* out)
+    {
+        using namespace orc;
+        Frame f;
+        f.sc = (const Scene*)scene; f.fc = fc; f.core = core; f.me = me; f.coat = coat; f.pcore = pcore; f.pcoat = pcoat;
+        f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+        memset(out, 0, 14 * 4);
+        const size_t idx = (size_t)y * f.W + x;
+        const GFlags flags = FlagsAt(core, f.W, x, y);
+        if (flags.invalid || flags.emissive) { out[13] = 0xffffffffu; return; }
+        Pixel p = LoadPixel(f, core, coat, x, y, false, x, y);
+        RNG rng = RNG::Init((uint32_t)x, (uint32_t)y, fc->FrameNum);
+        const int numBsdfSamples = (!p.surface.GlossSpecular() && p.roughness < 0.3f) ? 2 : 1;
+        Reservoir r = RIS_InitialCandidates(*f.sc, p.pos, p.normal, p.roughness, p.surface, sampleSetIdx, numBsdfSamples, rng);
+        bool valid = false;
+        if (temporal)
+        {
+            const float2 motionVec = unpack_snorm16x2(me[idx].x);
+            const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / f2((float)f.W, (float)f.H);
+            const float2 prevUV = currUV - motionVec;
+            TemporalCandidate tc = FindTemporalCandidate(f, p.pos, p.normal, p.roughness, p.surface, prevUV);
+            valid = tc.valid;
+            if (tc.valid)
+                TemporalResample1(*f.sc, p.pos, p.normal, p.surface, tc, prevRes, f.W, r, rng);
+        }
+        zr_rdi_reservoir rec;
+        r.Write(rec, M_max);
+        memcpy(out, &rec, 32);
+        out[8] = asuint(r.target.x); out[9] = asuint(r.target.y); out[10] = asuint(r.target.z);
+        out[11] = rng.State; out[12] = valid; out[13] = (uint32_t)numBsdfSamples;
+    }
+
     void orc_rdi_set_sample_pattern(const float* p) { g_disk32 = p; }
 
     struct orc_rdi_params { uint32_t temporal_resample, spatial_resample, stochastic_spatial, extra_disocclusion_sampling, M_max; float alpha_min; };

@@ -2,27 +2,7 @@
 // Traverse<0/1>, TriHit, the node decode) for the host with g++, so that the BVH builder + traversal pair can be checked
 // against brute force on scenes of the benchmark's size (10^5 - 10^6 triangles) in the CPU test tier, where no GPU exists.
 // Nothing here is shipped or used by the product; the product path is the same source compiled by nvcc for sm_100a.
-#include <cstring>
-#include <cstdint>
-#include <cmath>
-#include <vector>
-#include <thread>
-#include <atomic>
-#include <cuda_runtime.h>      // vector types + make_float3 (host-usable)
-
-// host stand-ins for the few device intrinsics the headers use
-template<typename T> static inline T __ldg(const T* p) { return *p; }
-static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
-static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
-template<typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
-// a "block" of one thread: barriers are no-ops, block votes / ballots see only this lane (the split-phase functions of zr_rpt.cuh
-// are included for their per-thread arithmetic; wave-scope results are not compared on the host)
-static inline void __syncthreads() {}
-static inline int __syncthreads_or(int p) { return p; }
-static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
-template<typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-
+#include "prelude.h"
 struct ZrTraverseStats { unsigned long long nodes, tris; };
 static thread_local ZrTraverseStats g_stats;
 #define ZR_TRAVERSE_STATS g_stats

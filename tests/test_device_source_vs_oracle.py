@@ -385,3 +385,63 @@ def test_restir_gi_temporal_reuse(which, dof):
         changed += bytes(a)[:16] != ini.tobytes()[:16]      # the resampled reservoir picked the temporal sample
     print(which, "candidates 0/1/2:", ncand, "sample replaced:", changed)
     assert ncand[1] + ncand[2] > 1000 and changed > 50, (ncand, changed)
+
+
+class HostSceneDI(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("instances", C.c_void_p), ("materials", C.c_void_p),
+                ("emissives", C.c_void_p), ("aliasTable", C.c_void_p), ("nodes", C.c_void_p), ("leafTris", C.c_void_p),
+                ("triMesh", C.c_void_p), ("meshFirstTri", C.c_void_p), ("rho", C.c_void_p),
+                ("numInstances", C.c_uint32), ("numEmissives", C.c_uint32), ("numTris", C.c_uint32),
+                ("sampleSets", C.c_void_p), ("numSampleSets", C.c_uint32), ("sampleSetSize", C.c_uint32)]
+
+
+@pytest.mark.parametrize("which,presample", [("cornell", None), ("glossy", None), ("glass", (16, 64)), ("atrium", None)])
+def test_restir_di_candidates_and_temporal_reuse(which, presample):
+    """ReSTIR DI of zr_rdi.cuh (a block of one thread) against the oracle's, pixel by pixel, as the temporal kernel runs it: RIS over
+    1-2 BSDF and 3 light candidates with balance-heuristic MIS (alias table or presampled sets), the temporal candidate (plane /
+    roughness / material tests at the reprojected pixel), its resampling with the shift's target re-evaluation and shadow segment,
+    the 32-byte reservoir record -- on moving-camera oracle sequences, history = the oracle's previous-frame reservoirs."""
+    from tests import scene_util, rpt_util
+    from tests.test_bvh_host import world_tris, build
+    hs = hostsim.load_di()
+    w, h = 128, 72
+    flat = scene_util.SCENES[which]()
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    R = rpt_util.OracleRenderer(flat, w, h)
+    osc = R.osc
+    if presample:
+        osc.set_presampling(*presample)
+    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: (cam[0] + 0.03 * f, cam[1], cam[2] + 0.02 * f))
+    for fr in range(3):
+        fc = seq.next()
+        gb = R.gbuffer(fc)
+        prev_res = np.ascontiguousarray(R.di_curr_reservoirs().copy())      # before this frame's DI pass: last frame's output
+        gb_prev = R.gb[R.cur ^ 1]
+        R.rdi(fc)
+    wt, tri_mesh, first = world_tris(flat)
+    if presample:
+        osc.set_presampling(*presample)        # world_tris() created a second oracle scene; keep this one's configuration in force
+    nodes, order, leaf, info = build(wt)
+    keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances, flat.materials, flat.emissives, osc.alias)]
+    hsc = HostSceneDI()
+    (hsc.vertices, hsc.indices, hsc.instances, hsc.materials, hsc.emissives, hsc.aliasTable) = [k.ctypes.data for k in keep]
+    hsc.nodes, hsc.leafTris, hsc.triMesh, hsc.meshFirstTri, hsc.rho = nodes.ctypes.data, leaf.ctypes.data, tri_mesh.ctypes.data, first.ctypes.data, osc.lut.ctypes.data
+    hsc.numInstances, hsc.numEmissives, hsc.numTris = len(flat.instances), len(flat.emissives), len(wt)
+    if presample:
+        hsc.sampleSets, hsc.numSampleSets, hsc.sampleSetSize = osc.sample_sets.ctypes.data, presample[0], presample[1]
+    core, depth, me, coat, _ = gb
+    pcore, _, _, pcoat, _ = gb_prev
+    rng = np.random.default_rng(41)
+    a = (C.c_uint32 * 14)(); b = (C.c_uint32 * 14)()
+    stats = dict(shaded=0, temporal_valid=0, lit=0, two_bsdf=0)
+    for k in range(2500):
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        sset = int(rng.integers(0, presample[0])) if presample else 0
+        for temporal in (0, 1):
+            R.o.orc_probe_rdi_pixel(osc.h, C.byref(fc), ptr(core), ptr(me), ptr(coat), ptr(pcore), ptr(pcoat), ptr(prev_res), x, y, sset, temporal, 20, a)
+            hs.hostsim_probe_rdi_pixel(C.byref(hsc), C.byref(fc), ptr(core), ptr(me), ptr(coat), ptr(pcore), ptr(pcoat), ptr(prev_res), x, y, sset, temporal, 20, b)
+            assert bytes(a) == bytes(b), (which, k, (x, y), temporal, list(a), list(b))
+        if a[13] != 0xffffffff:
+            stats["shaded"] += 1; stats["temporal_valid"] += a[12]; stats["lit"] += a[3] != 0xffffffff; stats["two_bsdf"] += a[13] == 2
+    print(which, stats)
+    assert stats["shaded"] > 1200 and stats["temporal_valid"] > 600 and stats["lit"] > 600, stats
