@@ -65,4 +65,52 @@ extern "C"
         out[8] = asuint(r.target.x); out[9] = asuint(r.target.y); out[10] = asuint(r.target.z);
         out[11] = rng.State; out[12] = valid; out[13] = (uint32_t)numBsdfSamples;
     }
+
+    // Pairwise-MIS spatial reuse (PairwiseMIS.hlsli) of the centre pixel (x, y) with neighbours (nx[i], ny[i]): the centre reservoir is
+    // completed from the emissive buffer + target plane as k_di_spatial does it; neighbours enter with their own LoadPixel surface.
+    // out (14 words): the resulting 32-byte record (Write with M_max 0 = no clamp), target (3), W, m_c, rng state
+    void hostsim_probe_rdi_pairwise(const hostsim_di_scene* hsc, const zr_frame_constants* fc, const void* core, const void* coat,
+        const zr_rdi_reservoir* res, const void* target, int x, int y, const int* nx, const int* ny, int numNeighbors, uint32_t seed, uint32_t* out)
+    {
+        using namespace zr;
+        const SceneDev sc = dev_of(hsc);
+        FrameView f{};
+        f.fc = *fc; f.core = (const uint4*)core; f.coat = (const uint2*)coat; f.pcore = f.core; f.pcoat = f.coat;
+        f.W = fc->RenderWidth; f.H = fc->RenderHeight;
+        memset(out, 0, 14 * 4);
+        const size_t idx = (size_t)y * f.W + x;
+        const GFlags flags = FlagsAt(f.core, f.W, x, y);
+        if (flags.invalid || flags.emissive) { out[13] = 0xffffffffu; return; }
+        Pixel p = LoadPixel(f, sc, f.core, f.coat, x, y, false, x, y);
+        Reservoir r = Reservoir::Load(res[idx]);
+        if (r.lightIdx != UINT32_MAX_)
+        {
+            const zr_emissive_tri& tri = sc.emissives[r.lightIdx];
+            r.lightID = tri.ID;
+            const float3 vtx0 = Light::Vtx0(tri);
+            const float3 vtx1 = Light::DecodeEmissiveTriV1(tri);
+            const float3 vtx2 = Light::DecodeEmissiveTriV2(tri);
+            r.lightPos = (1.0f - r.bary.x - r.bary.y) * vtx0 + r.bary.x * vtx1 + r.bary.y * vtx2;
+            r.lightNormal = cross(vtx1 - vtx0, vtx2 - vtx0);
+            r.lightNormal = dot(r.lightNormal, r.lightNormal) == 0 ? r.lightNormal : normalize(r.lightNormal);
+            r.doubleSided = Light::IsDoubleSided(tri);
+            r.target = abs3(LoadTarget((const uint2*)target, idx));
+        }
+        RNG rng; rng.State = seed;
+        PairwiseMIS mis = PairwiseMIS::Init((uint32_t)numNeighbors, r);
+        for (int i = 0; i < numNeighbors; i++)
+        {
+            const GFlags fi = FlagsAt(f.core, f.W, nx[i], ny[i]);
+            if (fi.invalid || fi.emissive) continue;
+            Pixel pi = LoadPixel(f, sc, f.core, f.coat, nx[i], ny[i], false, nx[i], ny[i]);
+            const Reservoir r_i = Reservoir::Load(res[(size_t)ny[i] * f.W + nx[i]]);
+            mis.Stream_Sync(true, sc, r, p.pos, p.normal, p.surface, r_i, pi.pos, pi.normal, pi.surface, rng);
+        }
+        mis.End(r, rng);
+        zr_rdi_reservoir rec;
+        mis.r_s.Write(rec, 0xffffffffu);
+        memcpy(out, &rec, 32);
+        out[8] = asuint(mis.r_s.target.x); out[9] = asuint(mis.r_s.target.y); out[10] = asuint(mis.r_s.target.z);
+        out[11] = asuint(mis.r_s.W); out[12] = asuint(mis.m_c); out[13] = rng.State;
+    }
 }

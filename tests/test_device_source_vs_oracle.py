@@ -445,3 +445,50 @@ def test_restir_di_candidates_and_temporal_reuse(which, presample):
             stats["shaded"] += 1; stats["temporal_valid"] += a[12]; stats["lit"] += a[3] != 0xffffffff; stats["two_bsdf"] += a[13] == 2
     print(which, stats)
     assert stats["shaded"] > 1200 and stats["temporal_valid"] > 600 and stats["lit"] > 600, stats
+
+
+@pytest.mark.parametrize("which", ["glossy", "atrium"])
+def test_restir_di_pairwise_mis(which):
+    """PairwiseMIS of zr_rdi.cuh (Stream_Sync with both shift directions: target re-evaluation at the other pixel, the two shadow
+    segments, the m_i / m_c weights; End) against the oracle's, for centre pixels with 1-4 neighbours drawn within the spatial
+    radius, on the reservoirs and the target plane of an oracle frame sequence."""
+    from tests import scene_util, rpt_util
+    from tests.test_bvh_host import world_tris, build
+    hs = hostsim.load_di()
+    w, h = 128, 72
+    flat = scene_util.SCENES[which]()
+    cam = scene_util.CAMERAS.get(which, (0.0, 1.2, -4.043))
+    R = rpt_util.OracleRenderer(flat, w, h)
+    osc = R.osc
+    seq = rpt_util.FrameSequence(w, h, cam_path=lambda f: cam)
+    for fr in range(3):
+        fc = seq.next()
+        gb = R.gbuffer(fc)
+        R.rdi(fc)
+    res = np.ascontiguousarray(R.di_curr_reservoirs())
+    target = np.ascontiguousarray(R.di_target)
+    wt, tri_mesh, first = world_tris(flat)
+    nodes, order, leaf, info = build(wt)
+    keep = [np.ascontiguousarray(x) for x in (flat.vertices, flat.indices, flat.instances, flat.materials, flat.emissives, osc.alias)]
+    hsc = HostSceneDI()
+    (hsc.vertices, hsc.indices, hsc.instances, hsc.materials, hsc.emissives, hsc.aliasTable) = [k.ctypes.data for k in keep]
+    hsc.nodes, hsc.leafTris, hsc.triMesh, hsc.meshFirstTri, hsc.rho = nodes.ctypes.data, leaf.ctypes.data, tri_mesh.ctypes.data, first.ctypes.data, osc.lut.ctypes.data
+    hsc.numInstances, hsc.numEmissives, hsc.numTris = len(flat.instances), len(flat.emissives), len(wt)
+    core, depth, me, coat, _ = gb
+    rng = np.random.default_rng(43)
+    a = (C.c_uint32 * 14)(); b = (C.c_uint32 * 14)()
+    shaded = picked_neighbor = 0
+    for k in range(2000):
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        n = int(rng.integers(1, 5))
+        nx = np.clip(x + rng.integers(-16, 17, n), 0, w - 1).astype(np.int32)
+        ny = np.clip(y + rng.integers(-16, 17, n), 0, h - 1).astype(np.int32)
+        seed = int(rng.integers(1, 2**32 - 1))
+        R.o.orc_probe_rdi_pairwise(osc.h, C.byref(fc), ptr(core), ptr(coat), ptr(res), ptr(target), x, y, ptr(nx), ptr(ny), n, seed, a)
+        hs.hostsim_probe_rdi_pairwise(C.byref(hsc), C.byref(fc), ptr(core), ptr(coat), ptr(res), ptr(target), x, y, ptr(nx), ptr(ny), n, seed, b)
+        assert bytes(a) == bytes(b), (which, k, (x, y), list(zip(nx, ny)), list(a), list(b))
+        if not (a[13] == 0xffffffff and a[0] == 0 and a[11] == 0):
+            shaded += 1
+            picked_neighbor += a[3] != int(res[y * w + x]["lightIdx"]) or a[0] != int(res[y * w + x]["bary"])
+    print(which, "shaded", shaded, "result differs from the centre sample", picked_neighbor)
+    assert shaded > 800 and picked_neighbor > 100
