@@ -46,6 +46,8 @@ enum
 /* Last error message of the calling thread ("" if none). */
 ZR_API const char* zr_last_error(void);
 /* Library/ABI version: (major << 16) | minor. */
+/* (major << 16) | minor; additions bump the minor. 1.1 added zr_bvh_build_host, zr_renderer_set_integrator,
+ * zr_renderer_get_gi_pass, zr_renderer_apply_scene_settings and zr_gi_pass_set_method. */
 ZR_API uint32_t zr_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------
