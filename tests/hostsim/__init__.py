@@ -17,12 +17,12 @@ def _deps(src):
     return [src, os.path.join(HERE, "prelude.h")] + hdrs
 
 
-def _build(src, so, force):
+def _build(src, so, force, defines=()):
     if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in _deps(src)):
         return so
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I" + cuda_inc,
-           "-D__forceinline__=inline __attribute__((always_inline))", src, "-o", so, "-lpthread"]
+           "-D__forceinline__=inline __attribute__((always_inline))"] + ["-D" + d for d in defines] + [src, "-o", so, "-lpthread"]
     subprocess.check_call(cmd)
     return so
 
@@ -43,3 +43,13 @@ def load():
 def load_di():
     build()
     return C.CDLL(SO_DI)
+
+
+def load_variant(name, defines):
+    """A host build of the same sources with experiment switches of the device headers turned on (e.g. the register-ordered
+    traversal, -DZR_TRAVERSE_REGISTER_ORDER), so that a variant prepared for a GPU A/B is already known to be correct."""
+    so = _build(os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "libhostsim_%s.so" % name), False, defines)
+    lib = C.CDLL(so)
+    lib.hostsim_validate.restype = C.c_uint64
+    return lib
+
