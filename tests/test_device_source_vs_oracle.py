@@ -173,6 +173,10 @@ def test_ray_query_material_and_light_sampling_device_source_vs_oracle(which, de
         p3 = pos.astype(np.float32)
         o.orc_probe_sample_light(osc.h, ptr(p3), 0, seed, 0, a); hs.hostsim_probe_sample_light(C.byref(hsc), ptr(p3), 0, seed, 0, b)
         assert bytes(a)[:64] == bytes(b)[:64], (which, int(k), list(a)[:16], list(b)[:16])
+    # the degenerate query the path tracer issues after a failed BSDF sample on a transmissive surface: wi = 0 -> no hit, on both sides
+    q = np.concatenate([sec[pick[0], 0:3], [0, 0, 1], [0, 0, 0], [1.0]]).astype(np.float32)
+    o.orc_probe_emissive_and_visibility(osc.h, ptr(q), a); hs.hostsim_probe_emissive_and_visibility(C.byref(hsc), ptr(q), b)
+    assert bytes(a)[:48] == bytes(b)[:48] and a[0] == 0
     assert hits > len(pick) // 4     # a good share of the queries hit something (the Cornell box is open at the front)
     assert lights > 0                # and some BSDF-direction queries end on a light
 
