@@ -6,7 +6,8 @@
 # All three are host-verified for correctness (tests/test_bvh_random.py, tests/test_device_source_vs_oracle.py); none is timed yet.
 set -e
 cd "$(dirname "$0")/.."
-for v in "${@:-regorder skipzero rgicut}"; do
+vars=("$@"); [ ${#vars[@]} -eq 0 ] && vars=(regorder skipzero rgicut)
+for v in "${vars[@]}"; do
   case $v in
     regorder) f=-DZR_TRAVERSE_REGISTER_ORDER ;;
     skipzero) f=-DZR_SKIP_ZERO_WI_QUERIES ;;
