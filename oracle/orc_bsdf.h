@@ -6,8 +6,9 @@
 //   ZetaRenderPass/Common/BSDFSampling.hlsli  SampleBSDF* :59-338, EvalBSDFSampler* :340-563,
 //                                             BSDFSamplerPdf* :565-765
 //   ZetaRenderPass/Common/RT.hlsli:264-288    BalanceHeuristic / BalanceHeuristic3 / PowerHeuristic
-// Parity unpinned: the reference has no tests for this code. The directional-albedo table is
-// zetaray_b200/assets/rho_lut.bin (re-derived, tools/gen_rho_lut.py).
+// Parity unpinned: the reference has no tests for this code (an independently written fp64 evaluator,
+// oracle/indep_bsdf.py, cross-checks it). The directional-albedo table is the reference's own
+// Assets/LUT/rho.dds payload (zetaray_b200/assets/rho_lut.bin, tools/extract_reference_tables.py).
 #pragma once
 #include "orc_math.h"
 

@@ -308,7 +308,7 @@ struct zr_direct_pass
         if (!fp || fread(pat, 4, 64, fp) != 64)
         {
             if (fp) fclose(fp);
-            zr::set_error("zr_direct_pass: cannot read %s (run tools/gen_sample_patterns.py)", path.c_str());
+            zr::set_error("zr_direct_pass: cannot read %s (tools/extract_reference_tables.py writes it)", path.c_str());
             return ZR_ERR_NOT_INITIALIZED;
         }
         fclose(fp);

@@ -1084,7 +1084,7 @@ struct zr_indirect_pass
         if (!fp || fread(pat.data(), 4, 1024, fp) != 1024)
         {
             if (fp) fclose(fp);
-            zr::set_error("zr_indirect_pass: cannot read %s (run tools/gen_sample_patterns.py)", path.c_str());
+            zr::set_error("zr_indirect_pass: cannot read %s (tools/extract_reference_tables.py writes it)", path.c_str());
             return ZR_ERR_NOT_INITIALIZED;
         }
         fclose(fp);

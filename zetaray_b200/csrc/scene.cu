@@ -134,7 +134,7 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
         if (!f || fread(rho.data(), 2, rho.size(), f) != rho.size())
         {
             if (f) fclose(f);
-            set_error("zr_scene_create: cannot read %s (run tools/gen_rho_lut.py)", path.c_str());
+            set_error("zr_scene_create: cannot read %s (tools/extract_reference_tables.py writes it)", path.c_str());
             zr_scene_destroy(sc);
             return ZR_ERR_NOT_INITIALIZED;
         }
