@@ -331,10 +331,12 @@ extern "C"
         ZR_CUDA(cudaMalloc(&out->d_motion_emissive, n * 8));
         ZR_CUDA(cudaMalloc(&out->d_coat, n * 8));
         if (with_tridiff) ZR_CUDA(cudaMalloc(&out->d_tridiff, n * 24));
+        ZR_CLEAR_BEGIN();
         ZR_CUDA(cudaMemset(out->d_core, 0, n * 16));
         ZR_CUDA(cudaMemset(out->d_depth, 0, n * 4));
         ZR_CUDA(cudaMemset(out->d_motion_emissive, 0, n * 8));
         ZR_CUDA(cudaMemset(out->d_coat, 0, n * 8));
+        ZR_CLEAR_END();
         return ZR_OK;
     }
     void zr_gbuffer_free(zr_gbuffer* g)

@@ -445,11 +445,13 @@ struct zr_taa_pass
     {
         Release();
         width = w; height = h;
+        ZR_CLEAR_BEGIN();
         for (int i = 0; i < 2; i++)
         {
             ZR_CUDA(cudaMalloc(&d_tex[i], (size_t)w * h * sizeof(uint2)));
             ZR_CUDA(cudaMemset(d_tex[i], 0, (size_t)w * h * sizeof(uint2)));
         }
+        ZR_CLEAR_END();
         isTemporalTexValid = false;
         return ZR_OK;
     }

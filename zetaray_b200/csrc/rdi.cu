@@ -285,9 +285,11 @@ struct zr_direct_pass
     zr_status ResetTemporal()
     {
         const size_t n = (size_t)width * height;
+        ZR_CLEAR_BEGIN();
         for (int i = 0; i < 2; i++) ZR_CUDA(cudaMemset(d_res[i], 0, n * sizeof(zr_rdi_reservoir)));
         ZR_CUDA(cudaMemset(d_target, 0, n * 8));
         ZR_CUDA(cudaMemset(d_final, 0, n * 16));
+        ZR_CLEAR_END();
         currTemporalIdx = 0; isTemporalReservoirValid = false; resetTemporalTextures = true;
         return ZR_OK;
     }

@@ -1061,6 +1061,7 @@ struct zr_indirect_pass
     zr_status ResetTemporal()
     {
         const size_t n = (size_t)width * height;
+        ZR_CLEAR_BEGIN();
         for (int i = 0; i < 2; i++)
         {
             ZR_CUDA(cudaMemset(d_res[i], 0, n * sizeof(zr_rpt_reservoir)));
@@ -1069,6 +1070,7 @@ struct zr_indirect_pass
         ZR_CUDA(cudaMemset(d_target, 0, n * 16));
         ZR_CUDA(cudaMemset(d_final, 0, n * 16));
         ZR_CUDA(cudaMemset(d_neighbor, 0, n * 2));
+        ZR_CLEAR_END();
         currTemporalIdx = 0;
         isTemporalReservoirValid = false;
         resetTemporalTextures = true;
@@ -1305,7 +1307,7 @@ extern "C"
     }
     zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1)
     {
-        if (!p || y0 >= y1) { zr::set_error("zr_indirect_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        if (!p || y0 >= y1 || y0 >= p->height) { zr::set_error("zr_indirect_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
         p->rowBegin = y0; p->rowEnd = y1;
         return ZR_OK;
     }

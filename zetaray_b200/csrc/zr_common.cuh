@@ -62,6 +62,12 @@ void set_error(const char* fmt, ...);
 zr_status cuda_fail(cudaError_t e, const char* what);
 void count_launch(uint64_t n = 1);
 #define ZR_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return zr::cuda_fail(e__, #expr); } while (0)
+// Host-side clears (reset / resize / alloc) run on the legacy default stream, which is NOT ordered against the
+// cudaStreamNonBlocking streams the frames are recorded on: wait for whatever may still use the buffers before the
+// memsets (ZR_CLEAR_BEGIN) and for the memsets themselves before returning (ZR_CLEAR_END), so that a Render enqueued
+// right after the call can neither be overwritten by a late memset nor overwrite an early one. These are rare host calls.
+#define ZR_CLEAR_BEGIN() ZR_CUDA(cudaDeviceSynchronize())
+#define ZR_CLEAR_END() ZR_CUDA(cudaStreamSynchronize(cudaStreamLegacy))
 void prof_before(const char* name, cudaStream_t stream);
 void prof_after();
 #define ZR_PROF(name, stream) zr::prof_before(name, (cudaStream_t)(stream))
