@@ -470,7 +470,12 @@ typedef enum zr_indirect_stage
 {
     ZR_RPT_STAGE_ALL = 0, ZR_RPT_STAGE_PATHTRACE = 1, ZR_RPT_STAGE_TEMPORAL = 2, ZR_RPT_STAGE_SPATIAL = 3
 } zr_indirect_stage;
+/* execution model of the spatial reuse pass (same results): per-case shift queues + TMA-staged streaming merge (default), or the
+ * fused kernel that does both shifts and the merge per pixel. Switch for measurements; ZETARAY_B200_SPATIAL=fused|queued sets the
+ * initial value. */
+typedef enum zr_indirect_execution { ZR_RPT_EXEC_FUSED = 0, ZR_RPT_EXEC_QUEUED = 1 } zr_indirect_execution;
 ZR_API zr_status zr_indirect_pass_create(uint32_t width, uint32_t height, zr_indirect_pass** out);
+ZR_API zr_status zr_indirect_pass_set_execution(zr_indirect_pass* p, zr_indirect_execution mode);
 ZR_API zr_status zr_indirect_pass_resize(zr_indirect_pass* p, uint32_t width, uint32_t height);
 ZR_API zr_status zr_indirect_pass_reset_temporal(zr_indirect_pass* p);
 ZR_API zr_status zr_indirect_pass_default_params(zr_indirect_params* out);

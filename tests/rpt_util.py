@@ -66,7 +66,10 @@ from zetaray_b200.camera import halton, FrameSequence  # noqa: E402,F401  (moved
 class OracleRenderer:
     """Reference-shaped frame loop on the CPU oracle."""
 
-    def __init__(self, flat, w, h, nthreads=8):
+    def __init__(self, flat, w, h, nthreads=None):
+        # results do not depend on the thread count (scan-line parallel, per-pixel state only); large frames use every core
+        if nthreads is None:
+            nthreads = 8 if w * h <= 512 * 512 else max(8, min(os.cpu_count() or 8, 128))
         self.osc = scene_util.OracleScene(flat)
         self.o = self.osc.o
         self.w, self.h, self.nthreads = w, h, nthreads

@@ -15,8 +15,8 @@
 //                         boiling-suppression wave sums)
 //   k_spatial          == Replay x2 + Reconnect_CtS + Reconnect_StC fused, run in the StC-sorted order
 // Per-pixel state moves as 128-bit accesses: 64-byte reservoir records, float4 target/final, uint4 G-buffer.
-#include "zr_rpt.cuh"
-#include "zr_pixel.cuh"
+#include "zr_rpt_io.cuh"
+#include "zr_rpt_spatial.h"
 #include "zr_schedule.h"
 #include <cstdio>
 #include <string>
@@ -29,16 +29,6 @@ namespace
 {
     using namespace RPT;
 
-    struct RptParams
-    {
-        uint32_t maxNonTrBounces, maxGlossyTrBounces, russianRoulette, M_max_temporal, M_max_spatial;
-        uint32_t boilingSuppression, sortSpatial;
-        float alpha_min;
-        uint32_t temporalResample, resetTemporal, spatialFlag;
-        uint32_t rowBegin, rowEnd;      // rows this rank owns (multi-GPU); whole image by default
-        unsigned long long* costMap;    // optional: SM cycles spent per 32x32-pixel tile ((W + 31) / 32 per row)
-    };
-
     // accounts the cycles a block took to the tile of its first pixel
     ZR_D void AccountCost(unsigned long long* costMap, uint32_t W, uint32_t H, uint32_t x, uint32_t y, long long t0)
     {
@@ -47,21 +37,6 @@ namespace
     }
 
     __constant__ float c_disk512[1024];
-
-    ZR_D void LoadRecord(const zr_rpt_reservoir* __restrict__ p, zr_rpt_reservoir& r)
-    {
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-        uint4 v[4] = { q[0], q[1], q[2], q[3] };
-        memcpy(&r, v, 64);
-    }
-    ZR_D void StoreRecord(zr_rpt_reservoir* __restrict__ p, const zr_rpt_reservoir& r)
-    {
-        uint4 v[4];
-        memcpy(v, &r, 64);
-        uint4* q = reinterpret_cast<uint4*>(p);
-        q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = v[3];
-    }
-    ZR_D uint4 LoadQ0(const zr_rpt_reservoir* __restrict__ p) { return *reinterpret_cast<const uint4*>(p); }
 
     // -------------------------------------------------------------------------------------------
     // PathTrace
@@ -634,15 +609,6 @@ namespace
         neighbor[idx] = (uint16_t)((mx & 0xff) | ((my & 0xff) << 8));
     }
 
-    ZR_D bool NeighborOf(const FrameView& f, const uint16_t* __restrict__ neighbor, int x, int y, int& nx, int& ny)
-    {
-        const uint16_t nb = __ldg(&neighbor[(size_t)y * f.W + x]);
-        const int ox = nb & 0xff, oy = nb >> 8;
-        if (ox == 0xff) return false;
-        nx = ox - 32 + x; ny = oy - 32 + y;
-        return true;
-    }
-
     // -------------------------------------------------------------------------------------------
     // Sort (ReSTIR_PT_Sort.hlsl): counting sort of a 32x32 tile by reconnection k. One block per tile,
     // each thread owns a 2x2 quad. Ranks are class-major, then thread (wave, lane) order, then quad
@@ -775,33 +741,6 @@ namespace
     // -------------------------------------------------------------------------------------------
     // Spatial reuse: Reconnect_CtS + Reconnect_StC for the same pixel, in the StC-sorted thread order
     // -------------------------------------------------------------------------------------------
-    ZR_D void SuppressOutlier(float waveAvgExclusive, Reservoir& r)
-    {
-        if (r.w_sum > 50 * waveAvgExclusive)
-        {
-            r.M = 0; r.w_sum = 0; r.W = 0; r.rc.Clear();
-        }
-    }
-
-    ZR_D void CopyToNextFrame(const zr_rpt_reservoir& in, zr_rpt_reservoir* __restrict__ outPtr, Reservoir r_curr, uint32_t M_max)
-    {
-        if (!r_curr.rc.Empty())
-        {
-            r_curr.Load_Reconnection(in);
-            zr_rpt_reservoir out;
-            r_curr.Write(out, M_max);
-            StoreRecord(outPtr, out);
-        }
-        else
-        {
-            // WriteReservoirData: A.x and B of the OUTPUT record; its other bytes keep their old contents
-            const uint4 old = LoadQ0(outPtr);
-            const uint32_t k = r_curr.rc.k;   // EMPTY
-            const uint32_t mm = r_curr.M < M_max ? r_curr.M : M_max;
-            st128(outPtr, make_uint4((old.x & 0xffffff00u) | ((k | (mm << 4)) & 0xff), asuint(r_curr.w_sum), asuint(r_curr.W), old.w));
-        }
-    }
-
     // A block is ZR_RPT_THREADS/64 consecutive 8x8 groups of the reference's swizzled dispatch (two waves each).
     __global__ void ZR_LB(ZR_RPT_THREADS) k_spatial(SceneDev sc, FrameView f, RptParams prm, const zr_rpt_reservoir* __restrict__ resIn,
         zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target, float4* __restrict__ finalImg,
@@ -1012,6 +951,9 @@ struct zr_indirect_pass
     // block schedules (zr_schedule.h), rebuilt when the rows or the tile costs change
     zr::TileCosts tileCosts;
     zr::BlockSchedule schedPathTrace, schedTemporal, schedSpatial;
+    // spatial reuse: per-case shift queues + TMA-staged streaming merge (rpt_spatial.cu) by default, the fused kernel on request
+    zr::SpatialQueued spatialQueued;
+    int execution = ZR_RPT_EXEC_QUEUED;
     zr_status UpdateSchedules()
     {
         const uint32_t y0 = rowBegin, y1 = rowEnd < height ? rowEnd : height, v = tileCosts.version;
@@ -1038,6 +980,7 @@ struct zr_indirect_pass
     {
         for (int i = 0; i < 2; i++) { if (d_res[i]) cudaFree(d_res[i]); d_res[i] = nullptr; if (d_threadMap[i]) cudaFree(d_threadMap[i]); d_threadMap[i] = nullptr; }
         schedPathTrace.Release(); schedTemporal.Release(); schedSpatial.Release();
+        spatialQueued.Release();
         if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final); if (d_neighbor) cudaFree(d_neighbor);
         d_target = d_final = nullptr; d_neighbor = nullptr;
     }
@@ -1055,6 +998,8 @@ struct zr_indirect_pass
         ZR_CUDA(cudaMalloc(&d_target, n * 16));
         ZR_CUDA(cudaMalloc(&d_final, n * 16));
         ZR_CUDA(cudaMalloc(&d_neighbor, n * 2));
+        zr_status st = spatialQueued.Resize(w, h, d_res[0], d_res[1]);
+        if (st != ZR_OK) return st;
         return ResetTemporal();
     }
 
@@ -1185,11 +1130,19 @@ struct zr_indirect_pass
                     k_sort<<<dim3(sx, sy), 256, 0, stream>>>(f, 3, 1u, rin, nullptr, d_neighbor, d_threadMap[1], sx, sy);
                     ZR_LAUNCH_CHECK();
                 }
-                const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
-                ZR_PROF("k_spatial", stream);
-                k_spatial<<<schedSpatial.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
-                    d_threadMap[1], dispX, dispY, schedSpatial.d_order);
-                ZR_LAUNCH_CHECK();
+                if (execution == ZR_RPT_EXEC_QUEUED)
+                {
+                    st = spatialQueued.Run(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor, d_threadMap[1], stream);
+                    if (st != ZR_OK) return st;
+                }
+                else
+                {
+                    const uint32_t dispX = (width + 7) / 8, dispY = (height + 7) / 8;
+                    ZR_PROF("k_spatial", stream);
+                    k_spatial<<<schedSpatial.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor,
+                        d_threadMap[1], dispX, dispY, schedSpatial.d_order);
+                    ZR_LAUNCH_CHECK();
+                }
                 if (exchange)
                 {
                     const zr_image2d plane{ rout, width, height, width * 64u, 64u };
@@ -1211,6 +1164,8 @@ extern "C"
         if (!out || !width || !height) { zr::set_error("zr_indirect_pass_create: bad args"); return ZR_ERR_INVALID_ARG; }
         zr_indirect_pass* p = new zr_indirect_pass();
         zr_indirect_pass::Defaults(&p->params);
+        if (const char* e = getenv("ZETARAY_B200_SPATIAL"))      // A/B switch for measurements: "fused" | "queued"
+            p->execution = std::string(e) == "fused" ? ZR_RPT_EXEC_FUSED : ZR_RPT_EXEC_QUEUED;
         zr_status s = p->OnWindowResized(width, height);
         if (s != ZR_OK) { p->Release(); delete p; return s; }
         *out = p;
@@ -1303,6 +1258,12 @@ extern "C"
     {
         if (!p) return ZR_ERR_INVALID_ARG;
         p->d_costMap = (unsigned long long*)d_cycles;
+        return ZR_OK;
+    }
+    zr_status zr_indirect_pass_set_execution(zr_indirect_pass* p, zr_indirect_execution mode)
+    {
+        if (!p || (mode != ZR_RPT_EXEC_FUSED && mode != ZR_RPT_EXEC_QUEUED)) { zr::set_error("zr_indirect_pass_set_execution: bad args"); return ZR_ERR_INVALID_ARG; }
+        p->execution = (int)mode;
         return ZR_OK;
     }
     zr_status zr_indirect_pass_set_rows(zr_indirect_pass* p, uint32_t y0, uint32_t y1)

@@ -1,0 +1,482 @@
+// rpt_spatial.cu -- ReSTIR PT spatial reuse as classify -> per-case shift queues -> TMA-staged streaming merge.
+//
+// Replaces the same reference dispatches as the fused k_spatial in rpt.cu (ReSTIR_PT_Replay x2, ReSTIR_PT_Reconnect_CtS.hlsl:46-230,
+// ReSTIR_PT_Reconnect_StC.hlsl:150-352) and produces the same bytes; only the execution model differs (zr_rpt_spatial.h).
+//
+// Why the split: the fused kernel evaluates two hybrid shifts inline per pixel, so a warp idles on sky pixels, on pixels without a
+// neighbour, on the other reconnection cases' phases (17 of 32 lanes active on the Cornell frame, 9 on the tunnel), and the 128 k
+// instructions of both shifts + merge share one register allocation. Here
+//   * the shifts run from queues holding (pixel, direction) items of ONE reconnection case and replay class, drained by
+//     persistent blocks: every lane of every warp has work and the other cases' phases do not exist in the kernel;
+//   * what remains per pixel -- MIS weights, reservoir update, boiling suppression, the 64-byte record and the colour -- is a
+//     bandwidth-bound pass: the block's 32x32 tile of reservoirs arrives by TMA (cp.async.bulk.tensor.2d, double buffered, one
+//     mbarrier per stage) while the previous tile is merged, every other access is a coalesced 128-bit row segment, and the wave
+//     sums of the boiling filter are taken over the SAME 32 pixels as in the reference's sorted dispatch by routing the four
+//     per-pixel terms through shared memory (pixel order -> sorted thread order -> xor-butterfly -> back).
+#include "zr_rpt_spatial.h"
+#include "zr_tma.cuh"
+
+namespace zr
+{
+namespace
+{
+    using namespace RPT;
+
+#ifndef ZR_SHIFT_THREADS
+#define ZR_SHIFT_THREADS 512
+#endif
+#ifndef ZR_SHIFT_MINBLOCKS
+#define ZR_SHIFT_MINBLOCKS 2
+#endif
+    constexpr uint32_t NO_ITEM = 0xffffffffu;
+
+    // queue class of a reservoir's sample from its metadata word: (case 1, 2, 3) x (k == 2, k > 2)
+    ZR_D uint32_t ShiftClass(uint32_t meta)
+    {
+        const uint32_t kMin2 = meta & 0xf;                              // never EMPTY here
+        const uint32_t lt_k = (meta >> 14) & 3, lt_k1 = (meta >> 16) & 3;
+        const uint32_t c = lt_k1 != 0 ? 1u : (lt_k != 0 ? 2u : 0u);     // Reconnection::IsCase2 / IsCase3 / IsCase1
+        return c * 2 + (kMin2 > 0 ? 1u : 0u);
+    }
+
+    // ---------------------------------------------------------------------------------------------------------------
+    // classify: one thread per pixel of the owned rows
+    // ---------------------------------------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(256) k_spatial_classify(FrameView f, RptParams prm, const zr_rpt_reservoir* __restrict__ resIn,
+        const uint16_t* __restrict__ neighbor, uint32_t* __restrict__ queue, uint32_t* __restrict__ counters, uint32_t capacity)
+    {
+        __shared__ uint32_t s_count[SpatialQueued::NUM_CLASSES], s_base[SpatialQueued::NUM_CLASSES];
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t x = blockIdx.x * 32 + lane;
+        const uint32_t y = prm.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
+        if (threadIdx.x < SpatialQueued::NUM_CLASSES) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t cls[2] = { NO_ITEM, NO_ITEM };     // [0] current -> neighbour (CtS), [1] neighbour -> current (StC)
+        if (x < f.W && y < f.H && y < prm.rowEnd)
+        {
+            const GFlags flags = FlagsAt(f.core, f.W, (int)x, (int)y);
+            int nx = 0, ny = 0;
+            if (!(flags.invalid || flags.emissive) && NeighborOf(f, neighbor, (int)x, (int)y, nx, ny))
+            {
+                const uint4 q0 = ld128(&resIn[(size_t)y * f.W + x]);
+                const uint4 qn = ld128(&resIn[(size_t)ny * f.W + nx]);
+                const bool selfEmpty = (q0.x & 0xf) == Reconnection::EMPTY, nEmpty = (qn.x & 0xf) == Reconnection::EMPTY;
+                const uint32_t M_n = (qn.x >> 4) & 0xf;
+                if (asfloat(q0.y) != 0 && !selfEmpty && M_n > 0) cls[0] = ShiftClass(q0.x);
+                if (!nEmpty) cls[1] = ShiftClass(qn.x);
+            }
+        }
+        // block-aggregated append: warp ballots -> shared counters -> one global atomic per class and block
+        uint32_t offs[2] = { 0, 0 };
+        const uint32_t lt = (1u << lane) - 1;
+#pragma unroll
+        for (uint32_t c = 0; c < SpatialQueued::NUM_CLASSES; c++)
+        {
+            const uint32_t m0 = __ballot_sync(0xffffffffu, cls[0] == c), m1 = __ballot_sync(0xffffffffu, cls[1] == c);
+            const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
+            uint32_t base = 0;
+            if (n && lane == 0) base = atomicAdd(&s_count[c], n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cls[0] == c) offs[0] = base + __popc(m0 & lt);
+            if (cls[1] == c) offs[1] = base + n0 + __popc(m1 & lt);
+        }
+        __syncthreads();
+        if (threadIdx.x < SpatialQueued::NUM_CLASSES)
+            s_base[threadIdx.x] = s_count[threadIdx.x] ? atomicAdd(&counters[threadIdx.x], s_count[threadIdx.x]) : 0;
+        __syncthreads();
+#pragma unroll
+        for (uint32_t d = 0; d < 2; d++)
+            if (cls[d] != NO_ITEM)
+                queue[(size_t)cls[d] * capacity + s_base[cls[d]] + offs[d]] = x | (y << 16) | (d << 31);
+    }
+
+    // ---------------------------------------------------------------------------------------------------------------
+    // shift: persistent blocks drain the queue of one class
+    // ---------------------------------------------------------------------------------------------------------------
+    template<int CASE, bool REPLAY>
+    __global__ void __launch_bounds__(ZR_SHIFT_THREADS, ZR_SHIFT_MINBLOCKS) k_shift(SceneDev sc, FrameView f, RptParams prm,
+        const zr_rpt_reservoir* __restrict__ resIn, const uint16_t* __restrict__ neighbor, const uint32_t* __restrict__ queue,
+        uint32_t* __restrict__ counters, uint32_t cls, ShiftResult* __restrict__ out)
+    {
+        __shared__ uint32_t s_base;
+        const uint32_t total = counters[cls];
+        for (;;)
+        {
+            __syncthreads();
+            if (threadIdx.x == 0) s_base = atomicAdd(&counters[8 + cls], (uint32_t)ZR_SHIFT_THREADS);
+            __syncthreads();
+            const uint32_t base = s_base;
+            if (base >= total) break;
+            const bool act = base + threadIdx.x < total;
+            // item -> whose sample (src), shifted to which primary vertex (px, py; coat parameters read at cx, cy -- the reference
+            // reads the centre pixel's coat there, Reconnect_CtS.hlsl:100), replayed from which (rx, ry)
+            int x = 0, y = 0, px = 0, py = 0, cx = 0, cy = 0, rx = 0, ry = 0;
+            uint32_t dir = 0;
+            size_t src = 0;
+            if (act)
+            {
+                const uint32_t item = __ldg(&queue[base + threadIdx.x]);
+                x = (int)(item & 0xffff); y = (int)((item >> 16) & 0x7fff); dir = item >> 31;
+                int nx = 0, ny = 0;
+                NeighborOf(f, neighbor, x, y, nx, ny);
+                if (dir == 0) { src = (size_t)y * f.W + x; px = nx; py = ny; cx = x; cy = y; rx = nx; ry = ny; }
+                else { src = (size_t)ny * f.W + nx; px = x; py = y; cx = x; cy = y; rx = x; ry = y; }
+            }
+            Reservoir r = Reservoir::Init();
+            Pixel p, pr;
+            if (act)
+            {
+                zr_rpt_reservoir rec;
+                LoadRecord(&resIn[src], rec);
+                r = Reservoir::Load_NonReconnection(rec);
+                r.rc.x_k_in_motion = false;
+                r.Load_Reconnection(rec);
+                p = LoadPixel(f, sc, f.core, f.coat, px, py, false, cx, cy);
+            }
+            OffsetPathContext ctx = OffsetPathContext::Init();
+            if (REPLAY)
+            {
+                if (act)
+                    pr = LoadPixel(f, sc, f.core, f.coat, rx, ry, false, rx, ry);
+                ZR_PHASE();
+                ctx = Replay_kGt2_Sync(act, sc, pr.pos, pr.normal, pr.eta_next, pr.surface, r.rc, prm.alpha_min);
+                if (act)
+                    ctx = ctx.Quantize();
+            }
+            const OffsetPath shift = Shift2_Sync<CASE>(act, sc, p.pos, p.normal, p.eta_next, p.surface, r.rc, &ctx, prm.alpha_min);
+            if (act)
+            {
+                ShiftResult* o = &out[(size_t)y * f.W + x];
+                if (dir == 0)
+                    *reinterpret_cast<float2*>(&o->ctsTargetLum) = f2(Math::Luminance(shift.target), shift.partialJacobian);
+                else
+                {
+                    // the merge accepts the shifted sample only for 1e-5 < J / J_n < 100, so a Jacobian that is not positive is
+                    // as good as zero; positive ones carry the "x_{k-1} transmissive" bit of the shifted path in the sign
+                    const float J = shift.partialJacobian;
+                    const float Jenc = J > 0 ? (shift.surfKMin1Tramsmissive ? -J : J) : 0.0f;
+                    st128(o, make_uint4(asuint(shift.target.x), asuint(shift.target.y), asuint(shift.target.z), asuint(Jenc)));
+                }
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------------
+    // merge: persistent blocks, one 32x32 tile per iteration
+    // ---------------------------------------------------------------------------------------------------------------
+    struct MergeSmem
+    {
+        uint4 rec[2][1024][4];      // stage x pixel-of-tile x 64-byte record (TMA destination: 32 rows of 2048 bytes)
+        float val[2][1024];         // [0] w_sum on entry, [1] the pixel's term of the final sum
+        float sum[2][1024];         // [0] wave sum of val[0], [1] wave total of the final sums
+        uint8_t cls[1024];          // which of the three final sums the pixel contributes to (0 = none)
+        uint8_t visited[1024];      // a thread position of the sorted dispatch maps to this pixel
+        unsigned long long bar[2];
+    };
+
+    __global__ void __launch_bounds__(1024, 1) k_spatial_merge(const __grid_constant__ CUtensorMap mapIn, FrameView f, RptParams prm,
+        const zr_rpt_reservoir* __restrict__ resIn, zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target,
+        float4* __restrict__ finalImg, const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap,
+        const ShiftResult* __restrict__ shiftRes, uint32_t tilesX, uint32_t tileRow0, uint32_t numTiles)
+    {
+        extern __shared__ __align__(128) unsigned char smemRaw[];
+        MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smemRaw);
+        const zr_frame_constants& fc = f.fc;
+        const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        constexpr uint32_t TILE_BYTES = 1024 * 64;
+
+        if (t == 0)
+        {
+            tma::MbarInit(reinterpret_cast<uint64_t*>(&sm.bar[0]), 1);
+            tma::MbarInit(reinterpret_cast<uint64_t*>(&sm.bar[1]), 1);
+            tma::FenceBarrierInit();
+        }
+        __syncthreads();
+        auto issue = [&](uint32_t tile, uint32_t stage)
+        {
+            const uint32_t tx = tile % tilesX, ty = tileRow0 + tile / tilesX;
+            uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar[stage]);
+            tma::MbarArriveExpectTx(bar, TILE_BYTES);
+            tma::Load2D(&sm.rec[stage][0][0], &mapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
+        };
+        if (t == 0 && blockIdx.x < numTiles)
+            issue(blockIdx.x, 0);
+
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, it++)
+        {
+            const uint32_t stage = it & 1, parity = (it >> 1) & 1;
+            const uint32_t tileX = tile % tilesX, tileY = tileRow0 + tile / tilesX;
+            // prefetch the next tile into the other stage (its readers finished at the end of the previous iteration)
+            if (t == 0 && tile + gridDim.x < numTiles)
+            {
+                tma::FenceProxyAsync();
+                issue(tile + gridDim.x, stage ^ 1);
+            }
+            // ---- phase 1 (pixel order): everything but the wave sums ----
+            const int x = (int)(tileX * 32 + lane), y = (int)(tileY * 32 + warp);
+            const bool inImage = (uint32_t)x < f.W && (uint32_t)y < f.H;
+            const size_t idx = inImage ? (size_t)y * f.W + x : 0;
+            bool act = inImage && y >= (int)prm.rowBegin && y < (int)prm.rowEnd;
+            if (act)
+            {
+                const GFlags flags = FlagsAt(f.core, f.W, x, y);
+                if (flags.invalid || flags.emissive) act = false;
+            }
+            int nx = 0, ny = 0;
+            bool hasN = false;
+            float4 tg = f4(0, 0, 0, 0);
+            uint4 sh0 = make_uint4(0, 0, 0, 0);
+            float2 sh1 = f2(0, 0);
+            uint4 n0 = make_uint4(Reconnection::EMPTY, 0, 0, 0), n1 = make_uint4(0, 0, 0, 0);
+            if (act)
+            {
+                tg = __ldg(&target[idx]);
+                hasN = NeighborOf(f, neighbor, x, y, nx, ny);
+                if (hasN)
+                {
+                    const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
+                    n0 = __ldg(&nrec[0]); n1 = __ldg(&nrec[1]);
+                    const uint4* sp = reinterpret_cast<const uint4*>(&shiftRes[idx]);
+                    sh0 = __ldg(&sp[0]);
+                    sh1 = __ldg(reinterpret_cast<const float2*>(&sp[1]));
+                }
+            }
+            sm.visited[t] = 0;
+            tma::MbarWait(reinterpret_cast<uint64_t*>(&sm.bar[stage]), parity);
+
+            zr_rpt_reservoir rec;
+            {
+                uint4 v[4] = { sm.rec[stage][t][0], sm.rec[stage][t][1], sm.rec[stage][t][2], sm.rec[stage][t][3] };
+                memcpy(&rec, v, 64);
+            }
+            Reservoir r_curr = Reservoir::Load_NonReconnection(rec);
+            r_curr.target = f3(tg.x, tg.y, tg.z);
+            const float wsum0 = act ? r_curr.w_sum : 0.0f;
+            uint32_t M_max = prm.M_max_spatial;
+            M_max = !r_curr.rc.Empty() && r_curr.rc.lobe_k_min_1 == BSDF::GLOSSY_T ? (M_max < 4 ? M_max : 4) : M_max;
+            // class 1: no neighbour; class 2: neighbour's reservoir holds no sample; class 3: full merge
+            uint32_t cls = 0, M_new = 0;
+            bool changed = false, surfKMin1Tr = false;
+            zr_rpt_reservoir recN;
+            Reservoir r_spatial = Reservoir::Init();
+            if (act && !hasN)
+                cls = 1;
+            else if (act)
+            {
+                memset(&recN, 0, sizeof(recN));
+                memcpy(&recN, &n0, 16); memcpy(reinterpret_cast<unsigned char*>(&recN) + 16, &n1, 16);
+                r_spatial = Reservoir::Load_NonReconnection(recN);
+                // Reconnect_CtS: MIS weight of the current sample among (current, neighbour)
+                if ((r_curr.w_sum != 0) && !r_curr.rc.Empty() && (r_spatial.M > 0))
+                {
+                    const float target_spatial = sh1.x;
+                    if (target_spatial > 0)
+                    {
+                        const float selfJ = (r_curr.rc.IsCase3() && r_curr.rc.lobe_k_min_1 == BSDF::ALL) ? 1.0f : asfloat(rec.jacobian_or_seed_nee);
+                        const float targetLum_curr = r_curr.W > 0 ? r_curr.w_sum / r_curr.W : 0;
+                        const float jacobian = selfJ > 0 ? sh1.y / selfJ : 0;
+                        const float numerator = (float)r_curr.M * targetLum_curr;
+                        const float denom = numerator + (float)r_spatial.M * target_spatial * jacobian;
+                        const float m_curr = denom > 0 ? numerator / denom : 0;
+                        r_curr.w_sum *= m_curr;
+                    }
+                }
+                M_new = r_curr.M + r_spatial.M;
+                if (r_spatial.rc.Empty())
+                    cls = 2;                // W and M are set after the outlier test (phase 3)
+                else
+                {
+                    cls = 3;
+                    M_max = r_spatial.rc.x_k_in_motion ? (M_max < 4 ? M_max : 4) : M_max;
+                    r_spatial.rc.x_k_in_motion = false;
+                    const float nJ = (r_spatial.rc.IsCase3() && r_spatial.rc.lobe_k_min_1 == BSDF::ALL) ? 1.0f : asfloat(recN.jacobian_or_seed_nee);
+                    const float3 shTarget = f3(asfloat(sh0.x), asfloat(sh0.y), asfloat(sh0.z));
+                    const float shJ = fabsf(asfloat(sh0.w));
+                    surfKMin1Tr = (sh0.w >> 31) != 0;
+                    const float targetLum_curr = Math::Luminance(shTarget);
+                    const float targetLum_spatial = r_spatial.W > 0 ? r_spatial.w_sum / r_spatial.W : 0;
+                    const float jacobian = nJ > 0 ? shJ / nJ : 0;
+                    if (targetLum_curr > 1e-6f && jacobian > 1e-5f && jacobian < 100)
+                    {
+                        const uint3 h = RNG::PCG3d(make_uint3((uint32_t)x, (uint32_t)y, (uint32_t)y));
+                        RNG rng = RNG::Init(h.x, h.z, fc.FrameNum + 511);
+                        const float numerator = (float)r_spatial.M * targetLum_spatial;
+                        const float denom = numerator / jacobian + (float)r_curr.M * targetLum_curr;
+                        const float m_spatial = denom > 0 ? numerator / denom : 0;
+                        const float w_spatial = m_spatial * r_spatial.W * targetLum_curr;
+                        if (r_curr.Update(w_spatial, shTarget, r_spatial.rc, rng))
+                        {
+                            // the accepted sample is the neighbour's: the rest of its record (second 32 bytes)
+                            const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
+                            const uint4 n2 = __ldg(&nrec[2]), n3 = __ldg(&nrec[3]);
+                            memcpy(reinterpret_cast<unsigned char*>(&recN) + 32, &n2, 16);
+                            memcpy(reinterpret_cast<unsigned char*>(&recN) + 48, &n3, 16);
+                            r_spatial.Load_Reconnection(recN);
+                            r_curr.rc = r_spatial.rc;
+                            r_curr.rc.partialJacobian = shJ;
+                            changed = true;
+                        }
+                    }
+                    const float targetLum = Math::Luminance(r_curr.target);
+                    r_curr.W = targetLum > 0 ? r_curr.w_sum / targetLum : 0;
+                    r_curr.M = M_new;
+                }
+            }
+            sm.val[0][t] = wsum0;
+            sm.val[1][t] = act ? r_curr.w_sum : 0.0f;
+            sm.cls[t] = (uint8_t)cls;
+            __syncthreads();
+
+            // ---- phase 2 (sorted thread order): thread position -> pixel, xor-butterfly over the reference's waves ----
+            {
+                const int sx = (int)(tileX * 32 + (warp & 3) * 8 + (lane & 7)), sy = (int)(tileY * 32 + (warp >> 2) * 4 + (lane >> 3));
+                bool on = (uint32_t)sx < f.W && (uint32_t)sy < f.H;
+                int lx = sx - (int)(tileX * 32), ly = sy - (int)(tileY * 32);
+                if (on && prm.sortSpatial)
+                {
+                    const uint16_t enc = __ldg(&threadMap[(size_t)sy * f.W + sx]);
+                    if (enc & (1u << 15)) on = false;
+                    lx += (int)(enc & 0x3f) - 31;
+                    ly += (int)((enc >> 7) & 0x3f) - 31;
+                }
+                if (on && ((uint32_t)lx >= 32u || (uint32_t)ly >= 32u)) on = false;      // cannot happen: the sort permutes within a tile
+                const uint32_t lp = on ? (uint32_t)(ly * 32 + lx) : 0;
+                const float v0 = on ? sm.val[0][lp] : 0.0f, v1 = on ? sm.val[1][lp] : 0.0f;
+                const uint32_t c = on ? sm.cls[lp] : 0;
+                const float waveSum = WaveSum32(v0);
+                float waveAcc = WaveSum32(c == 1 ? v1 : 0.0f);
+                waveAcc += WaveSum32(c == 2 ? v1 : 0.0f);
+                const float total = waveAcc + WaveSum32(c == 3 ? v1 : 0.0f);
+                if (on)
+                {
+                    sm.sum[0][lp] = waveSum; sm.sum[1][lp] = total;
+                    sm.visited[lp] = 1;
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 3 (pixel order): boiling suppression, record, colour ----
+            if (act && sm.visited[t])
+            {
+                const float avgEx0 = (sm.sum[0][t] - wsum0) / 32.0f;
+                if (cls == 1)
+                {
+                    if (prm.boilingSuppression) SuppressOutlier(avgEx0, r_curr);
+                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
+                    CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
+                }
+                else if (cls == 2)
+                {
+                    if (prm.boilingSuppression) SuppressOutlier(avgEx0, r_curr);
+                    const float targetLum = Math::Luminance(r_curr.target);
+                    r_curr.W = targetLum > 0 ? r_curr.w_sum / targetLum : 0;
+                    r_curr.M = M_new;
+                    CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
+                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
+                }
+                else
+                {
+                    if (prm.boilingSuppression)
+                        SuppressOutlier((sm.sum[1][t] - r_curr.w_sum) / 32.0f, r_curr);
+                    if (changed)
+                    {
+                        const uint32_t mmax = surfKMin1Tr ? (M_max < 4 ? M_max : 4) : M_max;
+                        zr_rpt_reservoir out;
+                        r_curr.Write(out, mmax);
+                        StoreRecord(&resOut[idx], out);
+                    }
+                    else
+                        CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
+                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
+                }
+            }
+            __syncthreads();        // the stage's records and the exchange arrays are free again
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------------------------
+void SpatialQueued::Release()
+{
+    if (d_queue) cudaFree(d_queue);
+    if (d_counters) cudaFree(d_counters);
+    if (d_shift) cudaFree(d_shift);
+    d_queue = nullptr; d_counters = nullptr; d_shift = nullptr;
+    ready = false;
+}
+
+zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* res0, const zr_rpt_reservoir* res1)
+{
+    Release();
+    width = w; height = h;
+    const size_t n = (size_t)w * h;
+    capacity = 2 * n;
+    ZR_CUDA(cudaMalloc(&d_queue, NUM_CLASSES * capacity * sizeof(uint32_t)));
+    ZR_CUDA(cudaMalloc(&d_counters, 16 * sizeof(uint32_t)));
+    ZR_CUDA(cudaMalloc(&d_shift, n * sizeof(ShiftResult)));
+    ZR_CUDA(cudaMemset(d_shift, 0, n * sizeof(ShiftResult)));
+    const zr_rpt_reservoir* planes[2] = { res0, res1 };
+    for (int i = 0; i < 2; i++)
+    {
+        mapBase[i] = planes[i];
+        if (!tma::EncodePlane2D(&mapRes[i], planes[i], w, h, 64, (uint64_t)w * 64, 32, 32))
+        {
+            set_error("zr_indirect_pass: cuTensorMapEncodeTiled failed for the %ux%u reservoir plane", w, h);
+            return ZR_ERR_CUDA;
+        }
+    }
+    int dev = 0;
+    ZR_CUDA(cudaGetDevice(&dev));
+    ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
+    ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    ready = true;
+    return ZR_OK;
+}
+
+zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn,
+    zr_rpt_reservoir* resOut, const float4* target, float4* finalImg, const uint16_t* neighbor, const uint16_t* threadMap, cudaStream_t stream)
+{
+    if (!ready) { set_error("zr_indirect_pass: queued spatial path is not initialised"); return ZR_ERR_NOT_INITIALIZED; }
+    const int plane = resIn == mapBase[0] ? 0 : (resIn == mapBase[1] ? 1 : -1);
+    if (plane < 0) { set_error("zr_indirect_pass: spatial input is not one of the pass's reservoir planes"); return ZR_ERR_INVALID_ARG; }
+    const uint32_t rows = prm.rowEnd - prm.rowBegin;
+    ZR_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(uint32_t), stream));
+    {
+        ZR_PROF("k_spatial_classify", stream);
+        k_spatial_classify<<<dim3((width + 31) / 32, (rows + 7) / 8), 256, 0, stream>>>(f, prm, resIn, neighbor, d_queue, d_counters, (uint32_t)capacity);
+        ZR_LAUNCH_CHECK();
+    }
+    {
+        // persistent blocks: as many as are resident at once; a block whose queue is empty leaves at its first claim
+        const uint32_t grid = (uint32_t)numSMs * ZR_SHIFT_MINBLOCKS;
+        ZR_PROF("k_shift", stream);
+#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS) \
+        k_shift<CASE, REPLAY><<<grid, ZR_SHIFT_THREADS, 0, stream>>>(sc, f, prm, resIn, neighbor, d_queue + (size_t)(CLS) * capacity, d_counters, CLS, d_shift); \
+        zr::count_launch()
+        ZR_LAUNCH_SHIFT(1, false, 0);
+        ZR_LAUNCH_SHIFT(1, true, 1);
+        ZR_LAUNCH_SHIFT(2, false, 2);
+        ZR_LAUNCH_SHIFT(2, true, 3);
+        ZR_LAUNCH_SHIFT(3, false, 4);
+        ZR_LAUNCH_SHIFT(3, true, 5);
+#undef ZR_LAUNCH_SHIFT
+        zr::prof_after();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return zr::cuda_fail(e, "k_shift launch");
+    }
+    {
+        const uint32_t tilesX = (width + 31) / 32;
+        const uint32_t tileRow0 = prm.rowBegin / 32, tileRow1 = (prm.rowEnd + 31) / 32;
+        const uint32_t numTiles = tilesX * (tileRow1 - tileRow0);
+        const uint32_t grid = numTiles < (uint32_t)numSMs ? numTiles : (uint32_t)numSMs;
+        ZR_PROF("k_spatial_merge", stream);
+        k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(mapRes[plane], f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
+            d_shift, tilesX, tileRow0, numTiles);
+        ZR_LAUNCH_CHECK();
+    }
+    return ZR_OK;
+}
+} // namespace zr

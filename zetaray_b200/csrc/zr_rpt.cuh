@@ -597,12 +597,16 @@ namespace RPT
     //   sampler eval at x_{k-1} | closest hit towards x_k | attributes + material at y_k | BSDF value at the
     //   reconnection vertex | shadow segment (case 3) | sampler eval (case 1, or lobe-sampled NEE) | sampler pdf (light-sampled NEE)
     // `replayed` = context from Replay_kGt2_Sync (already quantised) when k > 2.
+    // CASE: 0 = the reconnection case is read from `rc` (fused kernels); 1 / 2 / 3 = every thread of the block holds that case
+    // (the queued kernels draw their work from per-case queues), so the phases of the other cases compile away.
+    template<int CASE = 0>
     ZR_D OffsetPath Shift2_Sync(bool act, const SceneDev& sc, float3 pos, float3 normal, float ior, const ShadingData& surface,
         const Reconnection& rc, const OffsetPathContext* replayed, float alpha_min)
     {
         OffsetPath ret; ret.target = f3(0); ret.partialJacobian = 0; ret.surfKMin1Tramsmissive = false;
         OffsetPathContext ctx = OffsetPathContext::Init();
-        const bool case1 = rc.IsCase1(), case2 = rc.IsCase2(), case3 = rc.IsCase3();
+        const bool case1 = CASE == 0 ? rc.IsCase1() : CASE == 1, case2 = CASE == 0 ? rc.IsCase2() : CASE == 2,
+            case3 = CASE == 0 ? rc.IsCase3() : CASE == 3;
         bool go = act;
         if (go)
         {

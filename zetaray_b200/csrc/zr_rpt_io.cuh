@@ -1,0 +1,76 @@
+// zr_rpt_io.cuh -- ReSTIR PT per-pixel I/O shared by the fused kernels (rpt.cu) and the queued spatial path
+// (rpt_spatial.cu): kernel parameter block, 128-bit record accesses, neighbour lookup, the boiling-suppression rule
+// (ReSTIR_PT/Util.hlsli:58-67) and the "reservoir did not change" copy of Reconnect_StC (ReSTIR_PT_Reconnect_StC.hlsl:83-106).
+#pragma once
+#include "zr_rpt.cuh"
+#include "zr_pixel.cuh"
+
+namespace zr
+{
+struct RptParams
+{
+    uint32_t maxNonTrBounces, maxGlossyTrBounces, russianRoulette, M_max_temporal, M_max_spatial;
+    uint32_t boilingSuppression, sortSpatial;
+    float alpha_min;
+    uint32_t temporalResample, resetTemporal, spatialFlag;
+    uint32_t rowBegin, rowEnd;      // rows this rank owns (multi-GPU); whole image by default
+    unsigned long long* costMap;    // optional: SM cycles spent per 32x32-pixel tile ((W + 31) / 32 per row)
+};
+
+namespace
+{
+    using namespace RPT;
+
+    ZR_D void LoadRecord(const zr_rpt_reservoir* __restrict__ p, zr_rpt_reservoir& r)
+    {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 v[4] = { q[0], q[1], q[2], q[3] };
+        memcpy(&r, v, 64);
+    }
+    ZR_D void StoreRecord(zr_rpt_reservoir* __restrict__ p, const zr_rpt_reservoir& r)
+    {
+        uint4 v[4];
+        memcpy(v, &r, 64);
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = v[3];
+    }
+    ZR_D uint4 LoadQ0(const zr_rpt_reservoir* __restrict__ p) { return *reinterpret_cast<const uint4*>(p); }
+
+    ZR_D bool NeighborOf(const FrameView& f, const uint16_t* __restrict__ neighbor, int x, int y, int& nx, int& ny)
+    {
+        const uint16_t nb = __ldg(&neighbor[(size_t)y * f.W + x]);
+        const int ox = nb & 0xff, oy = nb >> 8;
+        if (ox == 0xff) return false;
+        nx = ox - 32 + x; ny = oy - 32 + y;
+        return true;
+    }
+
+    ZR_D void SuppressOutlier(float waveAvgExclusive, Reservoir& r)
+    {
+        if (r.w_sum > 50 * waveAvgExclusive)
+        {
+            r.M = 0; r.w_sum = 0; r.W = 0; r.rc.Clear();
+        }
+    }
+
+    ZR_D void CopyToNextFrame(const zr_rpt_reservoir& in, zr_rpt_reservoir* __restrict__ outPtr, Reservoir r_curr, uint32_t M_max)
+    {
+        if (!r_curr.rc.Empty())
+        {
+            r_curr.Load_Reconnection(in);
+            zr_rpt_reservoir out;
+            r_curr.Write(out, M_max);
+            StoreRecord(outPtr, out);
+        }
+        else
+        {
+            // WriteReservoirData: A.x and B of the OUTPUT record; its other bytes keep their old contents
+            const uint4 old = LoadQ0(outPtr);
+            const uint32_t k = r_curr.rc.k;   // EMPTY
+            const uint32_t mm = r_curr.M < M_max ? r_curr.M : M_max;
+            st128(outPtr, make_uint4((old.x & 0xffffff00u) | ((k | (mm << 4)) & 0xff), asuint(r_curr.w_sum), asuint(r_curr.W), old.w));
+        }
+    }
+
+}
+} // namespace zr
