@@ -10,12 +10,18 @@ temporal + spatial path reuse) -> compositing + firefly filter -> TAA. Nothing i
   value   frames timed with CUDA events on the launching stream, per-frame inputs already on the device
   e2e     the same frames through the C-ABI with HOST buffers in the timed region: the frame constants come from
           pinned host memory every frame and the anti-aliased RGBA16F image is read back to pinned host memory
-  roofline        the kernel with the largest share of the frame: algorithmic bytes / event-timed duration
+  roofline        the judged bandwidth kernel -- the streaming merge of the spatial resample (k_spatial_merge): algorithmic
+                  bytes / event-timed duration against the measured HBM peak; `dominant` names the kernel with the largest share
+                  of the frame (traversal / issue bound, no bandwidth claim); `traffic` = DRAM bytes per launch from the committed
+                  ncu capture, only if that capture was taken from the kernel sources that are being timed
   cpu_baseline    the CPU oracle (a port: the reference ships no CPU renderer) on a bounded sample of the workload
-  --impl reference   the same CPU path with every host core (the only CPU arm the reference's math has)
+  c1_alias_table  config C1: alias-table build, device (zr_alias_table_build) next to the CPU reference-equivalent
+  --impl reference   the same CPU path with every host core (the only CPU arm the reference's math has); this arm
+                  does not map libzetaray_b200.so (ZETARAY_B200_STRUCTS_ONLY)
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -41,6 +47,15 @@ ALG_BYTES = {
     "k_spatial_search": 16 + 16 + 2.0,
     "k_sort": 16 + 2 + 4 + 2.0,
     "k_spatial": 16 + 64 + 16 + 2 + 2 + 16 + 64 + 64 + 16.0,  # fused CtS+StC (SURVEY 8d B_spatial = 294 with 62 B planes)
+    # queued spatial path (rpt_spatial.cu). Per pixel with a usable neighbour (the common case; pixels without one move less, so
+    # image-wide figures are upper bounds of the bytes and lower bounds of the time-per-byte):
+    "k_spatial_classify": 4 + 2 + 16 + 16 + 8.0,               # flags, neighbour, own + neighbour header -> two queue items
+    "k_shift": 2 * (4 + 2 + 64 + 16 + 8) + 16 + 8.0,           # per item: queue entry, neighbour map, record, G-buffer core + coat -> result
+    # merge: flags 4, neighbour 2, thread map 2, own record 64 (TMA tile), target 16, neighbour record 64, both shift results 32
+    # -> record 64 + colour 16
+    "k_spatial_merge": 4 + 2 + 2 + 64 + 16 + 64 + 32 + 64 + 16.0,
+    "k_svgf_temporal": 16 + 8 + 16 + 8 + 16 + 16 + 8 + 8.0,    # core, motion, signal, prev guide, history -> history, colour+variance, guide
+    "k_svgf_atrous": 28.0,                                     # colour 8 + depth 4 + normal 4 + variance 2 -> colour 8 + variance 2 (x passes)
     "k_firefly": 16 + 16 + 4 + 16 + 16.0,   # fused compositing + firefly: direct, indirect, depth, core(flags) -> composited
     "k_taa": 16 + 4 + 8 + 8 + 8.0,
 }
@@ -73,6 +88,62 @@ def _clock_summary(samples):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "reasons": reasons}
 
 
+def kernel_sources_hash():
+    """Identifies the kernels an ncu capture belongs to: sha256 over the CUDA sources + the compile flags."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "zetaray_b200", "csrc")
+    for f in sorted(os.listdir(d)) + ["../build.py", "../../include/zr_fpmath.h"]:
+        p = os.path.join(d, f)
+        if os.path.isfile(p):
+            h.update(f.encode()); h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def alias_table_leg(st):
+    """Config C1: alias-table build at N = 2 / 13 107 / 10^6 emissive triangles, device vs CPU.
+    The device build is normalise + partition in parallel and the pairing loop on ONE lane: Vose's LIFO pairing order defines the
+    table (Math/Sampling.cpp:27-158), and `alias-table indices bit-exact` rules out the parallel constructions (they produce a
+    different, equally valid table). It runs once per light-set change, not per frame."""
+    import numpy as np
+    import torch
+    from zetaray_b200 import lib, check
+    from tests import orc
+    from tests.orc import ptr
+    o = orc.load()
+    ref = None
+    try:
+        ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_alias.so"))
+    except OSError:
+        pass
+    out = []
+    E16 = np.dtype([("a", "<f4"), ("b", "<f4"), ("c", "<f4"), ("d", "<u4")])
+    for n in (2, 13107, 1000000):
+        rng = np.random.default_rng(n)
+        w = (rng.random(n, dtype=np.float32) * 100).astype(np.float32)
+        d_w = torch.from_numpy(w).cuda()
+        d_t = torch.zeros(n * 16, dtype=torch.uint8, device="cuda")
+        d_s = torch.zeros(2 * n + 16, dtype=torch.int32, device="cuda")
+        reps = 3 if n > 100000 else 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(reps + 1):
+            if i == 1:
+                e0.record(torch.cuda.current_stream())
+            check(lib.zr_alias_table_build(C.c_void_p(d_w.data_ptr()), C.c_uint32(n), C.c_void_p(d_t.data_ptr()), C.c_void_p(d_s.data_ptr()), st))
+        e1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        gpu_ms = e0.elapsed_time(e1) / reps
+        table = np.zeros(n, dtype=E16)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            wc = w.copy()
+            o.orc_alias_build_emissive(ptr(wc), C.c_int64(n), 0, ptr(table))
+        cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+        same = d_t.cpu().numpy().view(E16).tobytes() == table.tobytes()
+        out.append({"n": n, "gpu_ms": round(gpu_ms, 4), "cpu_port_ms": round(cpu_ms, 4), "identical": bool(same)})
+    return {"what": "alias-table build (normalise + Vose), one call", "cpu": "oracle port, 1 thread (the reference's BuildAliasTable is scalar + AVX2 normalise)",
+            "sizes": out}
+
+
 def cpu_frames(w, h, nframes, nthreads, warm=3):
     """Times the CPU oracle on `nframes` steady-state frames of w x h (after `warm` untimed frames)."""
     from tests import scene_util, rpt_util
@@ -101,6 +172,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["ZETARAY_B200_STRUCTS_ONLY"] = "1"      # ctypes mirrors of the ABI structs only: the product library is not mapped
     cores = os.cpu_count() or 1
     sw, sh = 960, 540
     # one renderer, `warmup` frames to reach steady state (temporal + spatial reuse on), then the timed frames
@@ -244,8 +316,8 @@ def main():
 
     # ---- e2e: host buffers in, host image out, every frame (rank 0 holds the host side) ----
     n_e2e = max(3, min(args.steps, 20))
-    fc_host = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8).pin_memory()
-    fc_dev = torch.empty(C.sizeof(_lib.FrameConstants), dtype=torch.uint8, device="cuda")
+    # host -> device per frame: the 544-byte cbFrameConstants block, which the C-ABI takes from host memory by value and every
+    # kernel receives as launch parameters (there is no other per-frame input: scene and history stay resident)
     # the image read-back of frame i runs on a copy stream while frame i + 1 renders (TAA ping-pongs between two
     # images, so the one being copied is only read by the next frame); the host consumes frame i - 1 while i renders
     out_host = [torch.empty(W * H * 8, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -258,8 +330,6 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     for i, fc in enumerate(fcs2):
-        C.memmove(fc_host.data_ptr(), C.addressof(fc), C.sizeof(fc))
-        fc_dev.copy_(fc_host, non_blocking=True)            # H2D of the per-frame inputs
         frame(fc)
         if rank == 0:
             b = i & 1
@@ -322,24 +392,42 @@ def main():
             kernels.append({"kernel": name, "ms_per_frame": round(msf, 4), "share": round(msf / tot, 4),
                             "alg_bytes_per_px": ab, "achieved_gbs": None if gbs is None else round(gbs, 1),
                             "frac": None if gbs is None else round(gbs / peak, 4)})
+        by_name = {k["kernel"]: k for k in kernels}
+        judged = by_name.get("k_spatial_merge") or by_name.get("k_spatial") or kernels[0]
         top = kernels[0]
-        traffic = None
+        traffic, traffic_note = None, "no ncu capture committed for these kernel sources"
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1c_ncu_traffic.json")))[top["kernel"]]["dram_bytes"]
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+            if cap.get("kernel_sources_sha16") == kernel_sources_hash():
+                traffic = cap["kernels"][judged["kernel"]]["dram_bytes"]
+                traffic_note = "profiles/r2_ncu_traffic.json (same kernel sources as timed)"
+            else:
+                traffic_note = "profiles/r2_ncu_traffic.json was captured from other kernel sources: not reported"
         except Exception:
             pass
-        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
-                    "note": "algorithmic bytes/px x pixels / CUDA-event duration; traversal-bound kernels are listed for share, "
-                            "their HBM fraction is informational (SURVEY 8d)"}
+        spatial_ms = sum(by_name[k]["ms_per_frame"] for k in ("k_spatial_search", "k_sort", "k_spatial_classify", "k_shift", "k_spatial_merge", "k_spatial") if k in by_name)
+        roofline = {"kernel": judged["kernel"], "bound": "hbm", "achieved": judged["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": judged["frac"], "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                    "alg_bytes_per_px": judged["alg_bytes_per_px"],
+                    "spatial_resample_ms_total": round(spatial_ms, 4),
+                    "dominant": {"kernel": top["kernel"], "share": top["share"], "ms_per_frame": top["ms_per_frame"],
+                                 "bound": "traversal latency / instruction issue (no bandwidth claim, SURVEY 8d)"},
+                    "note": "algorithmic bytes/px x pixels / CUDA-event duration; pixels = the whole frame, although sky / emissive pixels "
+                            "(44 % of this view) move only their flags, so the fraction understates the rate on the pixels that do the work"}
 
     # ---- CPU baseline (rank 0, N == 1): bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        mp, spf = cpu_frames(480, 270, 2, cores)
+        mp, spf = cpu_frames(960, 540, 5, cores)
         cpu = {"value": round(mp, 4), "unit": "Mpaths/s", "cores": cores, "kind": "port",
-               "sample": "2 steady-state frames at 480x270 (1/16 of the 1080p pixels, same scene/params), %d threads, %.2f s/frame" % (cores, spf)}
+               "sample": "5 steady-state frames at 960x540 (1/4 of the 1080p pixels, same scene/params), %d threads, %.2f s/frame" % (cores, spf)}
+    c1 = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            c1 = alias_table_leg(st)
+        except Exception as e:      # the leg is informational; the frame numbers above do not depend on it
+            c1 = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -354,7 +442,7 @@ def main():
                     "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},
             "gpu_launches": int(launches),
             "clocks": _clock_summary(clocks),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "c1_alias_table": c1,
         }
         print(json.dumps(line))
     if world > 1:

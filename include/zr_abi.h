@@ -548,6 +548,37 @@ ZR_API zr_status zr_compositing_pass_set_rows(zr_compositing_pass* p, uint32_t y
 ZR_API zr_status zr_compositing_pass_get_output(zr_compositing_pass* p, zr_image2d* out);
 ZR_API void zr_compositing_pass_destroy(zr_compositing_pass* p);
 
+/* ------------------------------------------------------------------------------------------
+ * SVGF denoiser (no reference counterpart: ZetaRay ships none; BASELINE.json north_star / config 3).
+ * Temporal accumulation of colour + luminance moments -> variance, then `num_passes` a-trous wavelet passes (step 1, 2, 4, ...)
+ * with depth / normal / variance-guided luminance edge stops; the algorithm is defined by oracle/orc_svgf.cpp.
+ * d_signal: RGBA32F image (the Compositing output); output: RGBA32F, alpha = filtered variance. Slots between Compositing and TAA.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zr_svgf_pass zr_svgf_pass;
+typedef struct zr_svgf_params
+{
+    float sigma_z;          /* relative depth tolerance per unit step (0.02) */
+    float k_n;              /* normal falloff: weight = max(0, 1 - k_n (1 - n.n')) (16) */
+    float sigma_l;          /* luminance tolerance in standard deviations (4) */
+    uint32_t radius;        /* 2 = 5x5 B3-spline taps, 1 = 3x3 binomial taps */
+    uint32_t num_passes;    /* 1..5 */
+} zr_svgf_params;
+typedef enum zr_svgf_output
+{
+    ZR_SVGF_DENOISED = 0,       /* RGBA32F, pitch = width */
+    ZR_SVGF_ACCUMULATED = 1,    /* 4 x half {rgb, variance} after the temporal stage (overwritten by the second a-trous pass) */
+    ZR_SVGF_GUIDE = 2,          /* {f32 view depth, oct32 normal} */
+    ZR_SVGF_HISTORY = 3         /* {half4 colour | half m1, m2, N, 0}: next frame's history */
+} zr_svgf_output;
+ZR_API zr_status zr_svgf_pass_create(uint32_t width, uint32_t height, zr_svgf_pass** out);
+ZR_API zr_status zr_svgf_pass_resize(zr_svgf_pass* p, uint32_t width, uint32_t height);
+ZR_API zr_status zr_svgf_pass_reset_temporal(zr_svgf_pass* p);
+ZR_API zr_status zr_svgf_pass_default_params(zr_svgf_params* out);
+ZR_API zr_status zr_svgf_pass_set_params(zr_svgf_pass* p, const zr_svgf_params* params);
+ZR_API zr_status zr_svgf_pass_render(zr_svgf_pass* p, const zr_frame_inputs* in, const void* d_signal, void* stream);
+ZR_API zr_status zr_svgf_pass_get_output(zr_svgf_pass* p, zr_svgf_output id, zr_image2d* out);     /* internal planes: pitch_bytes > width * texel */
+ZR_API void zr_svgf_pass_destroy(zr_svgf_pass* p);
+
 /* ---- TAA (TAA/TAA.cpp:87-123) ---- */
 typedef struct zr_taa_pass zr_taa_pass;
 ZR_API zr_status zr_taa_pass_create(uint32_t width, uint32_t height, zr_taa_pass** out);
@@ -582,6 +613,8 @@ typedef struct zr_renderer zr_renderer;
 typedef struct zr_renderer_desc { uint32_t width, height; int with_tridiff; int two_streams; } zr_renderer_desc;
 ZR_API zr_status zr_renderer_create(const zr_renderer_desc* desc, zr_scene* scene, zr_renderer** out);
 ZR_API zr_status zr_renderer_render(zr_renderer* r, const zr_frame_constants* frame, void* stream);
+/* optional SVGF stage between Compositing and TAA (BASELINE config 3); *out_pass (may be NULL) receives the pass for set_params */
+ZR_API zr_status zr_renderer_set_denoiser(zr_renderer* r, int enable, zr_svgf_pass** out_pass);
 ZR_API zr_status zr_renderer_get_output(zr_renderer* r, zr_image2d* out);      /* TAA output, RGBA16F */
 ZR_API zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** gbuffer, zr_direct_pass** direct,
     zr_indirect_pass** indirect, zr_compositing_pass** compositing, zr_taa_pass** taa);

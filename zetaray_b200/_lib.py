@@ -21,7 +21,17 @@ def _load():
     return C.CDLL(SO_PATH)
 
 
-lib = _load()
+class _NoLibrary:
+    """ZETARAY_B200_STRUCTS_ONLY=1 (bench.py's CPU reference arm): only the ctypes mirrors of the ABI structs are needed, the
+    shared library is NOT mapped into the process; any call through `lib` fails loudly."""
+
+    def __getattr__(self, name):
+        if name in ("zr_last_error", "zr_abi_version", "zr_kernel_launch_count"):
+            return type("_Stub", (), {"restype": None, "argtypes": None})()
+        raise ZRError("zetaray_b200 was imported with ZETARAY_B200_STRUCTS_ONLY=1: %s is not available in this process" % name)
+
+
+lib = _NoLibrary() if os.environ.get("ZETARAY_B200_STRUCTS_ONLY") == "1" else _load()
 
 u32, u64, f32, vp, i32 = C.c_uint32, C.c_uint64, C.c_float, C.c_void_p, C.c_int32
 
@@ -76,6 +86,10 @@ class SceneDesc(C.Structure):
 class DirectParams(C.Structure):
     _fields_ = [("temporal_resample", u32), ("spatial_resample", u32), ("stochastic_spatial", u32),
                 ("extra_disocclusion_sampling", u32), ("M_max", u32), ("alpha_min", f32)]
+
+
+class SvgfParams(C.Structure):
+    _fields_ = [("sigma_z", f32), ("k_n", f32), ("sigma_l", f32), ("radius", u32), ("num_passes", u32)]
 
 
 class IndirectParams(C.Structure):

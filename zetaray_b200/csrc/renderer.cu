@@ -9,7 +9,7 @@
 //   every frame       zr_presample_emissives       when presampling is on (the reference: >= 13107 emissive triangles)
 //                     GBufferRT
 //                     DirectLighting  ||  IndirectLighting      second stream, joined before Compositing
-//                     Compositing (+ firefly filter) -> TAA
+//                     Compositing (+ firefly filter) -> [SVGF denoise, zr_renderer_set_denoiser] -> TAA
 //
 // The renderer owns the double-buffered G-buffers (DefaultRendererImpl.h:111-121) and the pass objects; callers reach
 // the passes through zr_renderer_get_*_pass to set parameters, exactly like the reference's UI callbacks do.
@@ -31,6 +31,7 @@ struct zr_renderer
     zr_integrator integrator = ZR_INTEGRATOR_RESTIR_PT;     // RenderSettings::Indirect default, DefaultRendererImpl.h:64
     zr_compositing_pass* compositing = nullptr;
     zr_taa_pass* taa = nullptr;
+    zr_svgf_pass* svgf = nullptr;                   // optional denoise stage between Compositing and TAA (BASELINE config 3)
     cudaStream_t side = nullptr;            // DirectLighting runs here when twoStreams
     cudaEvent_t evGBuffer = nullptr, evDirect = nullptr;
     bool twoStreams = true;
@@ -44,6 +45,8 @@ struct zr_renderer
         gi = nullptr;
         if (compositing) zr_compositing_pass_destroy(compositing);
         if (taa) zr_taa_pass_destroy(taa);
+        if (svgf) zr_svgf_pass_destroy(svgf);
+        svgf = nullptr;
         gbufferPass = nullptr; direct = nullptr; indirect = nullptr; compositing = nullptr; taa = nullptr;
         for (int i = 0; i < 2; i++) zr_gbuffer_free(&gbuffer[i]);
         if (side) cudaStreamDestroy(side);
@@ -143,6 +146,13 @@ extern "C"
         if (s != ZR_OK) return s;
         s = zr_compositing_pass_get_output(r->compositing, &comp);
         if (s != ZR_OK) return s;
+        if (r->svgf)
+        {
+            s = zr_svgf_pass_render(r->svgf, &in, comp.d_ptr, stream);
+            if (s != ZR_OK) return s;
+            s = zr_svgf_pass_get_output(r->svgf, ZR_SVGF_DENOISED, &comp);
+            if (s != ZR_OK) return s;
+        }
         s = zr_taa_pass_render(r->taa, &in, comp.d_ptr, stream);
         if (s != ZR_OK) return s;
         r->framesRendered++;
@@ -173,6 +183,16 @@ extern "C"
         if (s != ZR_OK) return s;
         r->integrator = method;
         return ZR_OK;
+    }
+    // SVGF between Compositing and TAA (enable != 0 creates the pass with its defaults; 0 removes it and its history)
+    zr_status zr_renderer_set_denoiser(zr_renderer* r, int enable, zr_svgf_pass** out_pass)
+    {
+        if (!r) return ZR_ERR_INVALID_ARG;
+        zr_status s = ZR_OK;
+        if (enable && !r->svgf) s = zr_svgf_pass_create(r->width, r->height, &r->svgf);
+        if (!enable && r->svgf) { zr_svgf_pass_destroy(r->svgf); r->svgf = nullptr; }
+        if (out_pass) *out_pass = r->svgf;
+        return s;
     }
     zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi)
     {

@@ -15,6 +15,7 @@
 //     per-pixel terms through shared memory (pixel order -> sorted thread order -> xor-butterfly -> back).
 #include "zr_rpt_spatial.h"
 #include "zr_tma.cuh"
+#include <cstdlib>
 
 namespace zr
 {
@@ -22,12 +23,6 @@ namespace
 {
     using namespace RPT;
 
-#ifndef ZR_SHIFT_THREADS
-#define ZR_SHIFT_THREADS 512
-#endif
-#ifndef ZR_SHIFT_MINBLOCKS
-#define ZR_SHIFT_MINBLOCKS 2
-#endif
     constexpr uint32_t NO_ITEM = 0xffffffffu;
 
     // queue class of a reservoir's sample from its metadata word: (case 1, 2, 3) x (k == 2, k > 2)
@@ -93,8 +88,9 @@ namespace
     // ---------------------------------------------------------------------------------------------------------------
     // shift: persistent blocks drain the queue of one class
     // ---------------------------------------------------------------------------------------------------------------
-    template<int CASE, bool REPLAY>
-    __global__ void __launch_bounds__(ZR_SHIFT_THREADS, ZR_SHIFT_MINBLOCKS) k_shift(SceneDev sc, FrameView f, RptParams prm,
+    // THREADS x MINB fixes the register budget (65536 / (THREADS * MINB) per thread) and the warps resident per SM
+    template<int CASE, bool REPLAY, int THREADS, int MINB>
+    __global__ void __launch_bounds__(THREADS, MINB) k_shift(SceneDev sc, FrameView f, RptParams prm,
         const zr_rpt_reservoir* __restrict__ resIn, const uint16_t* __restrict__ neighbor, const uint32_t* __restrict__ queue,
         uint32_t* __restrict__ counters, uint32_t cls, ShiftResult* __restrict__ out)
     {
@@ -103,7 +99,7 @@ namespace
         for (;;)
         {
             __syncthreads();
-            if (threadIdx.x == 0) s_base = atomicAdd(&counters[8 + cls], (uint32_t)ZR_SHIFT_THREADS);
+            if (threadIdx.x == 0) s_base = atomicAdd(&counters[8 + cls], (uint32_t)THREADS);
             __syncthreads();
             const uint32_t base = s_base;
             if (base >= total) break;
@@ -399,6 +395,28 @@ namespace
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
+namespace
+{
+    // persistent blocks: as many as are resident at once; a block whose queue is empty leaves at its first claim
+    template<int THREADS, int MINB>
+    void LaunchShifts(const SpatialQueued& q, const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn,
+        const uint16_t* neighbor, cudaStream_t stream)
+    {
+        const uint32_t grid = (uint32_t)q.numSMs * MINB;
+#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS) \
+        k_shift<CASE, REPLAY, THREADS, MINB><<<grid, THREADS, 0, stream>>>(sc, f, prm, resIn, neighbor, q.d_queue + (size_t)(CLS) * q.capacity, \
+            q.d_counters, CLS, q.d_shift); \
+        zr::count_launch()
+        ZR_LAUNCH_SHIFT(1, false, 0);
+        ZR_LAUNCH_SHIFT(1, true, 1);
+        ZR_LAUNCH_SHIFT(2, false, 2);
+        ZR_LAUNCH_SHIFT(2, true, 3);
+        ZR_LAUNCH_SHIFT(3, false, 4);
+        ZR_LAUNCH_SHIFT(3, true, 5);
+#undef ZR_LAUNCH_SHIFT
+    }
+}
+
 void SpatialQueued::Release()
 {
     if (d_queue) cudaFree(d_queue);
@@ -432,6 +450,7 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
     ZR_CUDA(cudaGetDevice(&dev));
     ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
     ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    if (const char* e = getenv("ZETARAY_B200_SHIFT_CFG")) shiftConfig = atoi(e);      // measurement switch (block size x register budget)
     ready = true;
     return ZR_OK;
 }
@@ -450,19 +469,15 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
         ZR_LAUNCH_CHECK();
     }
     {
-        // persistent blocks: as many as are resident at once; a block whose queue is empty leaves at its first claim
-        const uint32_t grid = (uint32_t)numSMs * ZR_SHIFT_MINBLOCKS;
         ZR_PROF("k_shift", stream);
-#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS) \
-        k_shift<CASE, REPLAY><<<grid, ZR_SHIFT_THREADS, 0, stream>>>(sc, f, prm, resIn, neighbor, d_queue + (size_t)(CLS) * capacity, d_counters, CLS, d_shift); \
-        zr::count_launch()
-        ZR_LAUNCH_SHIFT(1, false, 0);
-        ZR_LAUNCH_SHIFT(1, true, 1);
-        ZR_LAUNCH_SHIFT(2, false, 2);
-        ZR_LAUNCH_SHIFT(2, true, 3);
-        ZR_LAUNCH_SHIFT(3, false, 4);
-        ZR_LAUNCH_SHIFT(3, true, 5);
-#undef ZR_LAUNCH_SHIFT
+        switch (shiftConfig)
+        {
+        case 1: LaunchShifts<256, 2>(*this, sc, f, prm, resIn, neighbor, stream); break;
+        case 2: LaunchShifts<512, 1>(*this, sc, f, prm, resIn, neighbor, stream); break;
+        case 3: LaunchShifts<256, 4>(*this, sc, f, prm, resIn, neighbor, stream); break;
+        case 4: LaunchShifts<128, 4>(*this, sc, f, prm, resIn, neighbor, stream); break;
+        default: LaunchShifts<512, 2>(*this, sc, f, prm, resIn, neighbor, stream); break;
+        }
         zr::prof_after();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return zr::cuda_fail(e, "k_shift launch");

@@ -36,6 +36,7 @@ struct SpatialQueued
     CUtensorMap mapRes[2];                      // the two reservoir planes as [H][W] x 64 B, 32x32-pixel boxes
     const void* mapBase[2] = { nullptr, nullptr };
     int numSMs = 0;
+    int shiftConfig = 0;                        // k_shift block size x register budget (0 = 512 threads x 64 registers)
     bool ready = false;
 
     zr_status Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* res0, const zr_rpt_reservoir* res1);

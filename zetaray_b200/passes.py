@@ -143,6 +143,16 @@ def download_image(img, dtype, comps):
     return out
 
 
+def download_image_pitched(img, dtype, comps):
+    """An image whose rows are padded (pitch_bytes > width * texel_bytes): downloads the pitched rows and crops them."""
+    item = np.dtype(dtype).itemsize * comps
+    assert img.texel_bytes == item and img.pitch_bytes % item == 0
+    raw = np.zeros((img.height, img.pitch_bytes // item, comps), dtype=dtype)
+    check(lib.zr_memcpy_d2h(_vp(raw), C.c_void_p(img.d_ptr), C.c_size_t(raw.nbytes), None))
+    check(lib.zr_stream_synchronize(None))
+    return np.ascontiguousarray(raw[:, :img.width]).reshape(img.width * img.height, comps)
+
+
 class _Pass:
     prefix = None
 
@@ -339,6 +349,33 @@ class TAA(_Pass):
         return img
 
 
+class SVGF(_Pass):
+    """SVGF denoiser (zr_svgf_pass_*): RGBA32F signal in, RGBA32F out (alpha = filtered variance); between Compositing and TAA."""
+    prefix = "zr_svgf_pass"
+
+    def __init__(self, w, h):
+        self.handle = C.c_void_p()
+        check(lib.zr_svgf_pass_create(w, h, C.byref(self.handle)))
+        self.params = _lib.SvgfParams()
+        check(lib.zr_svgf_pass_default_params(C.byref(self.params)))
+
+    def SetParams(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        check(lib.zr_svgf_pass_set_params(self.handle, C.byref(self.params)))
+
+    def ResetTemporal(self):
+        check(lib.zr_svgf_pass_reset_temporal(self.handle))
+
+    def Render(self, fi, d_signal, stream=None):
+        check(lib.zr_svgf_pass_render(self.handle, C.byref(fi), C.c_void_p(d_signal), stream))
+
+    def GetOutput(self, which=0):
+        img = _lib.Image2D()
+        check(lib.zr_svgf_pass_get_output(self.handle, which, C.byref(img)))
+        return img
+
+
 class _Borrowed:
     """A pass handle owned by a Renderer: same verbs as the owning classes, never destroyed from here."""
 
@@ -351,6 +388,9 @@ class _Borrowed:
         if cls is IndirectLighting:
             self.params = _lib.IndirectParams()
             check(lib.zr_indirect_pass_default_params(C.byref(self.params)))
+        if cls is SVGF:
+            self.params = _lib.SvgfParams()
+            check(lib.zr_svgf_pass_default_params(C.byref(self.params)))
 
 
 class Renderer:
@@ -378,6 +418,12 @@ class Renderer:
             h = C.c_void_p()
             check(lib.zr_renderer_get_gi_pass(self.handle, C.byref(h)))
             self.gi = _Borrowed(IndirectLightingGI, h)
+
+    def SetDenoiser(self, enable=True):
+        """SVGF between Compositing and TAA (BASELINE config 3)."""
+        h = C.c_void_p()
+        check(lib.zr_renderer_set_denoiser(self.handle, int(enable), C.byref(h)))
+        self.svgf = _Borrowed(SVGF, h) if enable else None
 
     def ApplySceneSettings(self, use_lvg=False):
         """The reference's host decision: presampled sets iff >= 13107 emissive triangles, LVG only with them."""
