@@ -43,6 +43,9 @@ ALG_BYTES = {
     "k_di_temporal": 16 + 8 + 16 + 32 + 32 + 8 + 16.0,   # core, motion, prev core, prev reservoir -> reservoir, target, final
     "k_di_spatial": 16 + 32 + 8 + 1.5 * (16 + 32) + 16.0,  # self + 1-2 neighbours -> final
     "k_pathtrace": 16 + 64 + 16.0 + 3 * 192,   # core -> reservoir + target, plus ~192 B of scene gathers per bounce
+    "k_temporal_classify": 16 + 8 + 16 + 8 + 8 + 16 + 16 + 1 + 8.0,   # core, motion, prev core, coats, both headers -> flag byte, items
+    "k_shift_temporal": 2 * (4 + 8 + 64 + 16 + 8) + 16 + 8.0,
+    "k_temporal_merge": 4 + 64 + 16 + 1 + 8 + 64 + 32 + 64 + 16.0,
     "k_temporal": 16 + 8 + 64 + 16 + 16 + 64 + 64 + 16.0,   # fused CtT+TtC (SURVEY 8d 'temporal resample': 308 with 62 B planes)
     "k_spatial_search": 16 + 16 + 2.0,
     "k_sort": 16 + 2 + 4 + 2.0,
@@ -120,7 +123,8 @@ def alias_table_leg(st):
     for n in (2, 13107, 1000000):
         rng = np.random.default_rng(n)
         w = (rng.random(n, dtype=np.float32) * 100).astype(np.float32)
-        d_w = torch.from_numpy(w).cuda()
+        d_w0 = torch.from_numpy(w).cuda()
+        d_w = d_w0.clone()
         d_t = torch.zeros(n * 16, dtype=torch.uint8, device="cuda")
         d_s = torch.zeros(2 * n + 16, dtype=torch.int32, device="cuda")
         reps = 3 if n > 100000 else 20
@@ -128,6 +132,7 @@ def alias_table_leg(st):
         for i in range(reps + 1):
             if i == 1:
                 e0.record(torch.cuda.current_stream())
+            d_w.copy_(d_w0)                                # the build normalises the weights in place
             check(lib.zr_alias_table_build(C.c_void_p(d_w.data_ptr()), C.c_uint32(n), C.c_void_p(d_t.data_ptr()), C.c_void_p(d_s.data_ptr()), st))
         e1.record(torch.cuda.current_stream())
         torch.cuda.synchronize()
@@ -385,10 +390,19 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         tot = sum(kern.values())
-        own_rows = H if sharded.plan is None else (sharded.plan.rows(rank)[1] - sharded.plan.rows(rank)[0])    # rank 0's strip
+        y0, y1 = (0, H) if sharded.plan is None else sharded.plan.rows(rank)      # rank 0's strip
+        own_rows = y1 - y0
+        # pixels that carry a surface (the lighting kernels move only the 4-byte flag word of the others: sky, light sources)
+        core = gb.download()[0]        # the per-kernel timing frames above rendered into `gb` (sharded.render)
+        fl = core[:, 3].reshape(H, W)[y0:y1] & 0xff
+        surf = int((((fl >> 2) & 1) == 0).sum() - ((((fl >> 2) & 1) == 0) & (((fl >> 1) & 1) == 1)).sum())
+        px_all = W * own_rows
+        PER_SURFACE_PIXEL = ("k_di_temporal", "k_di_spatial", "k_pathtrace", "k_temporal", "k_spatial", "k_spatial_classify", "k_shift",
+                             "k_spatial_merge", "k_temporal_classify", "k_shift_temporal", "k_temporal_merge", "k_spatial_search", "k_sort")
         for name, msf in sorted(kern.items(), key=lambda kv: -kv[1]):
             ab = ALG_BYTES.get(name)
-            gbs = (ab * W * own_rows / (msf * 1e-3) / 1e9) if ab else None
+            nbytes = None if not ab else (ab * surf + 4.0 * (px_all - surf) if name in PER_SURFACE_PIXEL else ab * px_all)
+            gbs = (nbytes / (msf * 1e-3) / 1e9) if ab else None
             kernels.append({"kernel": name, "ms_per_frame": round(msf, 4), "share": round(msf / tot, 4),
                             "alg_bytes_per_px": ab, "achieved_gbs": None if gbs is None else round(gbs, 1),
                             "frac": None if gbs is None else round(gbs / peak, 4)})
@@ -412,8 +426,9 @@ def main():
                     "spatial_resample_ms_total": round(spatial_ms, 4),
                     "dominant": {"kernel": top["kernel"], "share": top["share"], "ms_per_frame": top["ms_per_frame"],
                                  "bound": "traversal latency / instruction issue (no bandwidth claim, SURVEY 8d)"},
-                    "note": "algorithmic bytes/px x pixels / CUDA-event duration; pixels = the whole frame, although sky / emissive pixels "
-                            "(44 % of this view) move only their flags, so the fraction understates the rate on the pixels that do the work"}
+                    "surface_pixel_fraction": round(surf / px_all, 4),
+                    "note": "algorithmic bytes = bytes/px x pixels that carry a surface + 4 B (the flag word) x the others (sky, light sources), "
+                            "/ CUDA-event duration"}
 
     # ---- CPU baseline (rank 0, N == 1): bounded sample of the same workload ----
     cpu = None

@@ -61,6 +61,9 @@ def main():
             r.SetMethod(Renderer.RESTIR_GI)
         if cfg["pt"]:
             r.indirect.SetParams(**cfg["pt"])
+        if os.environ.get("ZR_DENOISE"):            # SVGF between Compositing and TAA; ZR_DENOISE=<radius> (1: 3x3 taps, 2: 5x5 taps)
+            r.SetDenoiser(True)
+            r.svgf.SetParams(radius=int(os.environ["ZR_DENOISE"]))
         return r, pres, lvg
 
     r, pres, lvg = make_renderer(True)

@@ -325,53 +325,6 @@ namespace
     }
 
     // -------------------------------------------------------------------------------------------
-    // shared lookups
-    // -------------------------------------------------------------------------------------------
-    ZR_D bool PrevPixel(const FrameView& f, int x, int y, int& ppx, int& ppy)
-    {
-        const float2 renderDim = f2((float)f.W, (float)f.H);
-        const float2 motionVec = unpack_snorm16x2(__ldg(&f.me[(size_t)y * f.W + x].x));
-        const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / renderDim;
-        const float2 prevUV = currUV - motionVec;
-        const float2 pp = prevUV * renderDim;
-        ppx = (int)pp.x; ppy = (int)pp.y;
-        return !(prevUV.x < 0.0f || prevUV.y < 0.0f || prevUV.x > 1.0f || prevUV.y > 1.0f);
-    }
-
-    ZR_D bool PlaneHeuristic(float3 prevPos, float3 normal, float3 pos, float linearDepth, float th)
-    {
-        return fabsf(dot(normal, prevPos - pos)) <= th * linearDepth;
-    }
-
-    ZR_D void XkToPrev(const SceneDev& sc, Reconnection& rc)
-    {
-        const zr_mesh_instance md = LoadInstance(sc, rc.meshIdx);
-        const float4 q_curr = normalize(Math::DecodeNormalized4(md.Rotation));
-        const float3 T = f3(md.Translation[0], md.Translation[1], md.Translation[2]);
-        const float3 x_local = Math::InverseTransformTRS(rc.x_k, T, q_curr, h3(md.Scale));
-        const float3 prevTranslation = T - h3(md.dTranslation);
-        const float4 q_prev = normalize(Math::DecodeNormalized4(md.PrevRotation));
-        rc.x_k = Math::TransformTRS(x_local, prevTranslation, q_prev, h3(md.PrevScale));
-    }
-    ZR_D void XkToCurr(const SceneDev& sc, Reconnection& rc)
-    {
-        const zr_mesh_instance md = LoadInstance(sc, rc.meshIdx);
-        const float3 T = f3(md.Translation[0], md.Translation[1], md.Translation[2]);
-        const float3 dT = h3(md.dTranslation);
-        const float3 prevTranslation = T - dT;
-        const float4 q_prev = normalize(Math::DecodeNormalized4(md.PrevRotation));
-        const float3 prevScale = h3(md.PrevScale), scale = h3(md.Scale);
-        const float3 x_local = Math::InverseTransformTRS(rc.x_k, prevTranslation, q_prev, prevScale);
-        const float4 q_curr = normalize(Math::DecodeNormalized4(md.Rotation));
-        rc.x_k = Math::TransformTRS(x_local, T, q_curr, scale);
-        const float4 dRot = f4(q_prev.x - q_curr.x, q_prev.y - q_curr.y, q_prev.z - q_curr.z, q_prev.w - q_curr.w);
-        const float3 dScale = prevScale - scale;
-        rc.x_k_in_motion = dot(dT, dT) > 0;
-        rc.x_k_in_motion = rc.x_k_in_motion || dot(dRot, dRot) > 0;
-        rc.x_k_in_motion = rc.x_k_in_motion || dot(dScale, dScale) > 0;
-    }
-
-    // -------------------------------------------------------------------------------------------
     // Temporal reuse: Reconnect_CtT then Reconnect_TtC for the same pixel (replay inline).
     // A block is 32 x ZR_RPT_THREADS/32 pixels, one warp per 8x4 tile; block-synchronous phases throughout,
     // so no thread leaves before the last barrier.
@@ -953,6 +906,7 @@ struct zr_indirect_pass
     zr::BlockSchedule schedPathTrace, schedTemporal, schedSpatial;
     // spatial reuse: per-case shift queues + TMA-staged streaming merge (rpt_spatial.cu) by default, the fused kernel on request
     zr::SpatialQueued spatialQueued;
+    zr::TemporalQueued temporalQueued;
     int execution = ZR_RPT_EXEC_QUEUED;
     zr_status UpdateSchedules()
     {
@@ -981,6 +935,7 @@ struct zr_indirect_pass
         for (int i = 0; i < 2; i++) { if (d_res[i]) cudaFree(d_res[i]); d_res[i] = nullptr; if (d_threadMap[i]) cudaFree(d_threadMap[i]); d_threadMap[i] = nullptr; }
         schedPathTrace.Release(); schedTemporal.Release(); schedSpatial.Release();
         spatialQueued.Release();
+        temporalQueued.Release();
         if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final); if (d_neighbor) cudaFree(d_neighbor);
         d_target = d_final = nullptr; d_neighbor = nullptr;
     }
@@ -999,6 +954,8 @@ struct zr_indirect_pass
         ZR_CUDA(cudaMalloc(&d_final, n * 16));
         ZR_CUDA(cudaMalloc(&d_neighbor, n * 2));
         zr_status st = spatialQueued.Resize(w, h, d_res[0], d_res[1]);
+        if (st != ZR_OK) return st;
+        st = temporalQueued.Resize(w, h);
         if (st != ZR_OK) return st;
         return ResetTemporal();
     }
@@ -1102,10 +1059,18 @@ struct zr_indirect_pass
         }
         if (doTemporal && lastStage != ZR_RPT_STAGE_PATHTRACE)
         {
-            ZR_PROF("k_temporal", stream);
-            k_temporal<<<schedTemporal.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
-                d_target, d_final, (width + 31) / 32, schedTemporal.d_order);
-            ZR_LAUNCH_CHECK();
+            if (execution == ZR_RPT_EXEC_QUEUED)
+            {
+                st = temporalQueued.Run(spatialQueued, in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, stream);
+                if (st != ZR_OK) return st;
+            }
+            else
+            {
+                ZR_PROF("k_temporal", stream);
+                k_temporal<<<schedTemporal.count, ZR_RPT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur],
+                    d_target, d_final, (width + 31) / 32, schedTemporal.d_order);
+                ZR_LAUNCH_CHECK();
+            }
         }
         // reservoirs written so far are read by neighbours (spatial pass) and by the next frame's temporal pass
         if (exchange)

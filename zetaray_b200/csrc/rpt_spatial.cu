@@ -14,25 +14,14 @@
 //     sums of the boiling filter are taken over the SAME 32 pixels as in the reference's sorted dispatch by routing the four
 //     per-pixel terms through shared memory (pixel order -> sorted thread order -> xor-butterfly -> back).
 #include "zr_rpt_spatial.h"
+#include "zr_rpt_shift.cuh"
 #include "zr_tma.cuh"
-#include <cstdlib>
 
 namespace zr
 {
 namespace
 {
     using namespace RPT;
-
-    constexpr uint32_t NO_ITEM = 0xffffffffu;
-
-    // queue class of a reservoir's sample from its metadata word: (case 1, 2, 3) x (k == 2, k > 2)
-    ZR_D uint32_t ShiftClass(uint32_t meta)
-    {
-        const uint32_t kMin2 = meta & 0xf;                              // never EMPTY here
-        const uint32_t lt_k = (meta >> 14) & 3, lt_k1 = (meta >> 16) & 3;
-        const uint32_t c = lt_k1 != 0 ? 1u : (lt_k != 0 ? 2u : 0u);     // Reconnection::IsCase2 / IsCase3 / IsCase1
-        return c * 2 + (kMin2 > 0 ? 1u : 0u);
-    }
 
     // ---------------------------------------------------------------------------------------------------------------
     // classify: one thread per pixel of the owned rows
@@ -41,8 +30,7 @@ namespace
         const uint16_t* __restrict__ neighbor, uint32_t* __restrict__ queue, uint32_t* __restrict__ counters, uint32_t capacity)
     {
         __shared__ uint32_t s_count[SpatialQueued::NUM_CLASSES], s_base[SpatialQueued::NUM_CLASSES];
-        const uint32_t lane = threadIdx.x & 31;
-        const uint32_t x = blockIdx.x * 32 + lane;
+        const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
         const uint32_t y = prm.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
         if (threadIdx.x < SpatialQueued::NUM_CLASSES) s_count[threadIdx.x] = 0;
         __syncthreads();
@@ -61,100 +49,8 @@ namespace
                 if (!nEmpty) cls[1] = ShiftClass(qn.x);
             }
         }
-        // block-aggregated append: warp ballots -> shared counters -> one global atomic per class and block
-        uint32_t offs[2] = { 0, 0 };
-        const uint32_t lt = (1u << lane) - 1;
-#pragma unroll
-        for (uint32_t c = 0; c < SpatialQueued::NUM_CLASSES; c++)
-        {
-            const uint32_t m0 = __ballot_sync(0xffffffffu, cls[0] == c), m1 = __ballot_sync(0xffffffffu, cls[1] == c);
-            const uint32_t n0 = __popc(m0), n = n0 + __popc(m1);
-            uint32_t base = 0;
-            if (n && lane == 0) base = atomicAdd(&s_count[c], n);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cls[0] == c) offs[0] = base + __popc(m0 & lt);
-            if (cls[1] == c) offs[1] = base + n0 + __popc(m1 & lt);
-        }
-        __syncthreads();
-        if (threadIdx.x < SpatialQueued::NUM_CLASSES)
-            s_base[threadIdx.x] = s_count[threadIdx.x] ? atomicAdd(&counters[threadIdx.x], s_count[threadIdx.x]) : 0;
-        __syncthreads();
-#pragma unroll
-        for (uint32_t d = 0; d < 2; d++)
-            if (cls[d] != NO_ITEM)
-                queue[(size_t)cls[d] * capacity + s_base[cls[d]] + offs[d]] = x | (y << 16) | (d << 31);
-    }
-
-    // ---------------------------------------------------------------------------------------------------------------
-    // shift: persistent blocks drain the queue of one class
-    // ---------------------------------------------------------------------------------------------------------------
-    // THREADS x MINB fixes the register budget (65536 / (THREADS * MINB) per thread) and the warps resident per SM
-    template<int CASE, bool REPLAY, int THREADS, int MINB>
-    __global__ void __launch_bounds__(THREADS, MINB) k_shift(SceneDev sc, FrameView f, RptParams prm,
-        const zr_rpt_reservoir* __restrict__ resIn, const uint16_t* __restrict__ neighbor, const uint32_t* __restrict__ queue,
-        uint32_t* __restrict__ counters, uint32_t cls, ShiftResult* __restrict__ out)
-    {
-        __shared__ uint32_t s_base;
-        const uint32_t total = counters[cls];
-        for (;;)
-        {
-            __syncthreads();
-            if (threadIdx.x == 0) s_base = atomicAdd(&counters[8 + cls], (uint32_t)THREADS);
-            __syncthreads();
-            const uint32_t base = s_base;
-            if (base >= total) break;
-            const bool act = base + threadIdx.x < total;
-            // item -> whose sample (src), shifted to which primary vertex (px, py; coat parameters read at cx, cy -- the reference
-            // reads the centre pixel's coat there, Reconnect_CtS.hlsl:100), replayed from which (rx, ry)
-            int x = 0, y = 0, px = 0, py = 0, cx = 0, cy = 0, rx = 0, ry = 0;
-            uint32_t dir = 0;
-            size_t src = 0;
-            if (act)
-            {
-                const uint32_t item = __ldg(&queue[base + threadIdx.x]);
-                x = (int)(item & 0xffff); y = (int)((item >> 16) & 0x7fff); dir = item >> 31;
-                int nx = 0, ny = 0;
-                NeighborOf(f, neighbor, x, y, nx, ny);
-                if (dir == 0) { src = (size_t)y * f.W + x; px = nx; py = ny; cx = x; cy = y; rx = nx; ry = ny; }
-                else { src = (size_t)ny * f.W + nx; px = x; py = y; cx = x; cy = y; rx = x; ry = y; }
-            }
-            Reservoir r = Reservoir::Init();
-            Pixel p, pr;
-            if (act)
-            {
-                zr_rpt_reservoir rec;
-                LoadRecord(&resIn[src], rec);
-                r = Reservoir::Load_NonReconnection(rec);
-                r.rc.x_k_in_motion = false;
-                r.Load_Reconnection(rec);
-                p = LoadPixel(f, sc, f.core, f.coat, px, py, false, cx, cy);
-            }
-            OffsetPathContext ctx = OffsetPathContext::Init();
-            if (REPLAY)
-            {
-                if (act)
-                    pr = LoadPixel(f, sc, f.core, f.coat, rx, ry, false, rx, ry);
-                ZR_PHASE();
-                ctx = Replay_kGt2_Sync(act, sc, pr.pos, pr.normal, pr.eta_next, pr.surface, r.rc, prm.alpha_min);
-                if (act)
-                    ctx = ctx.Quantize();
-            }
-            const OffsetPath shift = Shift2_Sync<CASE>(act, sc, p.pos, p.normal, p.eta_next, p.surface, r.rc, &ctx, prm.alpha_min);
-            if (act)
-            {
-                ShiftResult* o = &out[(size_t)y * f.W + x];
-                if (dir == 0)
-                    *reinterpret_cast<float2*>(&o->ctsTargetLum) = f2(Math::Luminance(shift.target), shift.partialJacobian);
-                else
-                {
-                    // the merge accepts the shifted sample only for 1e-5 < J / J_n < 100, so a Jacobian that is not positive is
-                    // as good as zero; positive ones carry the "x_{k-1} transmissive" bit of the shifted path in the sign
-                    const float J = shift.partialJacobian;
-                    const float Jenc = J > 0 ? (shift.surfKMin1Tramsmissive ? -J : J) : 0.0f;
-                    st128(o, make_uint4(asuint(shift.target.x), asuint(shift.target.y), asuint(shift.target.z), asuint(Jenc)));
-                }
-            }
-        }
+        const uint32_t item[2] = { x | (y << 16), x | (y << 16) | (1u << 31) };
+        AppendItems(cls, item, queue, counters, capacity, s_count, s_base);
     }
 
     // ---------------------------------------------------------------------------------------------------------------
@@ -395,28 +291,6 @@ namespace
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-namespace
-{
-    // persistent blocks: as many as are resident at once; a block whose queue is empty leaves at its first claim
-    template<int THREADS, int MINB>
-    void LaunchShifts(const SpatialQueued& q, const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn,
-        const uint16_t* neighbor, cudaStream_t stream)
-    {
-        const uint32_t grid = (uint32_t)q.numSMs * MINB;
-#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS) \
-        k_shift<CASE, REPLAY, THREADS, MINB><<<grid, THREADS, 0, stream>>>(sc, f, prm, resIn, neighbor, q.d_queue + (size_t)(CLS) * q.capacity, \
-            q.d_counters, CLS, q.d_shift); \
-        zr::count_launch()
-        ZR_LAUNCH_SHIFT(1, false, 0);
-        ZR_LAUNCH_SHIFT(1, true, 1);
-        ZR_LAUNCH_SHIFT(2, false, 2);
-        ZR_LAUNCH_SHIFT(2, true, 3);
-        ZR_LAUNCH_SHIFT(3, false, 4);
-        ZR_LAUNCH_SHIFT(3, true, 5);
-#undef ZR_LAUNCH_SHIFT
-    }
-}
-
 void SpatialQueued::Release()
 {
     if (d_queue) cudaFree(d_queue);
@@ -450,7 +324,6 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
     ZR_CUDA(cudaGetDevice(&dev));
     ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
     ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
-    if (const char* e = getenv("ZETARAY_B200_SHIFT_CFG")) shiftConfig = atoi(e);      // measurement switch (block size x register budget)
     ready = true;
     return ZR_OK;
 }
@@ -470,14 +343,7 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
     }
     {
         ZR_PROF("k_shift", stream);
-        switch (shiftConfig)
-        {
-        case 1: LaunchShifts<256, 2>(*this, sc, f, prm, resIn, neighbor, stream); break;
-        case 2: LaunchShifts<512, 1>(*this, sc, f, prm, resIn, neighbor, stream); break;
-        case 3: LaunchShifts<256, 4>(*this, sc, f, prm, resIn, neighbor, stream); break;
-        case 4: LaunchShifts<128, 4>(*this, sc, f, prm, resIn, neighbor, stream); break;
-        default: LaunchShifts<512, 2>(*this, sc, f, prm, resIn, neighbor, stream); break;
-        }
+        LaunchShifts<false>(numSMs, sc, f, prm, resIn, nullptr, neighbor, d_queue, capacity, d_counters, d_shift, stream);
         zr::prof_after();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return zr::cuda_fail(e, "k_shift launch");

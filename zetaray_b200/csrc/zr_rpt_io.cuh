@@ -72,5 +72,52 @@ namespace
         }
     }
 
+    // -------------------------------------------------------------------------------------------
+    // shared lookups of the temporal pass (motion-vector reprojection, plane test, x_k between the two frames' instance transforms)
+    // -------------------------------------------------------------------------------------------
+    ZR_D bool PrevPixel(const FrameView& f, int x, int y, int& ppx, int& ppy)
+    {
+        const float2 renderDim = f2((float)f.W, (float)f.H);
+        const float2 motionVec = unpack_snorm16x2(__ldg(&f.me[(size_t)y * f.W + x].x));
+        const float2 currUV = f2((float)x + 0.5f, (float)y + 0.5f) / renderDim;
+        const float2 prevUV = currUV - motionVec;
+        const float2 pp = prevUV * renderDim;
+        ppx = (int)pp.x; ppy = (int)pp.y;
+        return !(prevUV.x < 0.0f || prevUV.y < 0.0f || prevUV.x > 1.0f || prevUV.y > 1.0f);
+    }
+
+    ZR_D bool PlaneHeuristic(float3 prevPos, float3 normal, float3 pos, float linearDepth, float th)
+    {
+        return fabsf(dot(normal, prevPos - pos)) <= th * linearDepth;
+    }
+
+    ZR_D void XkToPrev(const SceneDev& sc, Reconnection& rc)
+    {
+        const zr_mesh_instance md = LoadInstance(sc, rc.meshIdx);
+        const float4 q_curr = normalize(Math::DecodeNormalized4(md.Rotation));
+        const float3 T = f3(md.Translation[0], md.Translation[1], md.Translation[2]);
+        const float3 x_local = Math::InverseTransformTRS(rc.x_k, T, q_curr, h3(md.Scale));
+        const float3 prevTranslation = T - h3(md.dTranslation);
+        const float4 q_prev = normalize(Math::DecodeNormalized4(md.PrevRotation));
+        rc.x_k = Math::TransformTRS(x_local, prevTranslation, q_prev, h3(md.PrevScale));
+    }
+    ZR_D void XkToCurr(const SceneDev& sc, Reconnection& rc)
+    {
+        const zr_mesh_instance md = LoadInstance(sc, rc.meshIdx);
+        const float3 T = f3(md.Translation[0], md.Translation[1], md.Translation[2]);
+        const float3 dT = h3(md.dTranslation);
+        const float3 prevTranslation = T - dT;
+        const float4 q_prev = normalize(Math::DecodeNormalized4(md.PrevRotation));
+        const float3 prevScale = h3(md.PrevScale), scale = h3(md.Scale);
+        const float3 x_local = Math::InverseTransformTRS(rc.x_k, prevTranslation, q_prev, prevScale);
+        const float4 q_curr = normalize(Math::DecodeNormalized4(md.Rotation));
+        rc.x_k = Math::TransformTRS(x_local, T, q_curr, scale);
+        const float4 dRot = f4(q_prev.x - q_curr.x, q_prev.y - q_curr.y, q_prev.z - q_curr.z, q_prev.w - q_curr.w);
+        const float3 dScale = prevScale - scale;
+        rc.x_k_in_motion = dot(dT, dT) > 0;
+        rc.x_k_in_motion = rc.x_k_in_motion || dot(dRot, dRot) > 0;
+        rc.x_k_in_motion = rc.x_k_in_motion || dot(dScale, dScale) > 0;
+    }
+
 }
 } // namespace zr

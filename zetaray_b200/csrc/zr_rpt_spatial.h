@@ -36,7 +36,6 @@ struct SpatialQueued
     CUtensorMap mapRes[2];                      // the two reservoir planes as [H][W] x 64 B, 32x32-pixel boxes
     const void* mapBase[2] = { nullptr, nullptr };
     int numSMs = 0;
-    int shiftConfig = 0;                        // k_shift block size x register budget (0 = 512 threads x 64 registers)
     bool ready = false;
 
     zr_status Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* res0, const zr_rpt_reservoir* res1);
@@ -44,5 +43,15 @@ struct SpatialQueued
     // resIn must be one of the two planes given to Resize
     zr_status Run(const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn, zr_rpt_reservoir* resOut,
         const float4* target, float4* finalImg, const uint16_t* neighbor, const uint16_t* threadMap, cudaStream_t stream);
+};
+
+// Temporal reuse through the same queues, counters and shift-result plane (the two passes never overlap in a frame).
+struct TemporalQueued
+{
+    uint8_t* d_flags = nullptr;     // per pixel: bit 0 = temporal reuse valid, bit 1 = the replay's tighter plane test passed
+    zr_status Resize(uint32_t w, uint32_t h);
+    void Release();
+    zr_status Run(SpatialQueued& q, const SceneDev& sc, const FrameView& f, const RptParams& prm, zr_rpt_reservoir* resCurr,
+        const zr_rpt_reservoir* resPrev, float4* target, float4* finalImg, cudaStream_t stream);
 };
 } // namespace zr
