@@ -203,9 +203,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--expensive-first", action="store_true",
-                    help="launch the lighting kernels' thread blocks most-expensive-tile-first instead of in plain order (measured: no gain)")
-    ap.add_argument("--halo", default="p2p", choices=["p2p", "allgather"], help="transport of the strip halos (N > 1)")
     ap.add_argument("--single-stream", action="store_true", help="record DirectLighting on the main stream instead of a second one")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -237,8 +234,7 @@ def main():
 
     # Multi-GPU: ONE 1080p frame is split into horizontal strips, one per GPU (strong scaling). Strip
     # boundaries come from the per-band SM-cycle cost measured during the unsharded warm-up frames; reservoir / final
-    # halos move with one NCCL all-gather per exchange point (zetaray_b200/sharding.py); the finished strips are
-    # all-gathered every frame so the image is complete on every rank before the next frame starts.
+    # halos move between neighbouring strips at four exchange points per frame; the finished strips are gathered on rank 0.
     from zetaray_b200.sharding import ShardedFrame, StripPlan
     flat = FlatScene.load(os.path.join(ROOT, "tests", "golden", "cornell_emissive.npz"))     # the reference's cornell_emissive.gltf, flattened
     scene = Scene(flat)
@@ -250,7 +246,7 @@ def main():
     seq = FrameSequence(W, H)
     fi = _lib.FrameInputs()
     fi.scene = scene.handle
-    sharded = ShardedFrame(passes, gb, W, H, rank, world)
+    sharded = ShardedFrame(passes, gb, W, H, 0, 1)       # the stand-alone passes: per-kernel timing pass at N == 1
 
     # DirectLighting and IndirectLighting both depend only on the G-buffer (two independent render-graph nodes in the
     # reference, PathTracer.cpp:149-323), so DirectLighting is recorded on a second stream and joined before Compositing.
@@ -258,20 +254,18 @@ def main():
     st_side = st if side is None else C.c_void_p(side.cuda_stream)
     ev_g, ev_d = torch.cuda.Event(), torch.cuda.Event()
 
-    # N == 1: the native frame driver (zr_renderer, csrc/renderer.cu) -- one C-ABI call per frame, second stream inside.
-    # N > 1: the strip-sharded frame (zetaray_b200/sharding.py) over the same passes.
-    from zetaray_b200.passes import Renderer
-    renderer = Renderer(scene, W, H, two_streams=not args.single_stream) if world == 1 else None
+    # The native frame driver (zr_renderer, csrc/renderer.cu): one C-ABI call per frame, second stream inside. N > 1: the same
+    # renderer strip-sharded (zr_renderer_set_shard) with the halo bands moved by zr_comm -- grouped NCCL send / recv issued from
+    # C++ on the producing stream -- and the finished image gathered on rank 0.
+    from zetaray_b200.passes import Renderer, Comm
+    renderer = Renderer(scene, W, H, two_streams=not args.single_stream)
+    comm = Comm.from_torch() if world > 1 else None
 
     def frame(fc):
-        if renderer is not None:
-            renderer.Render(fc, st)
-            return
-        sharded.render(fi, fc, stream, st, side, st_side, ev_g, ev_d)
-        sharded.gather_output(stream)
+        renderer.Render(fc, st)
 
     def output_image():
-        return renderer.GetOutput() if renderer is not None else taa.GetOutput()
+        return renderer.GetOutput()
 
     def barrier():
         torch.cuda.synchronize()
@@ -282,14 +276,22 @@ def main():
     # ---- warm-up: unsharded frames bring temporal + spatial reuse to steady state (frame >= 3) and measure the cost
     # of every 32-row band; then the strips are cut and the same number of sharded warm-up frames follows ----
     plan_info = None
+    plan = None
     if world > 1:
-        sharded.begin_cost_measurement()
+        tiles_x = (W + 31) // 32
+        cost = torch.zeros(tiles_x * StripPlan.num_units(H), dtype=torch.int64, device="cuda")
+        renderer.direct.SetCostMap(cost.data_ptr()); renderer.indirect.SetCostMap(cost.data_ptr())
     for _ in range(args.warmup):
         frame(seq.next())
     if world > 1:
-        costs = sharded.end_cost_measurement(schedule=args.expensive_first)
+        torch.cuda.synchronize()
+        renderer.direct.SetCostMap(0); renderer.indirect.SetCostMap(0)
+        c = cost.to(torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)                       # identical plan on every rank
+        tiles = [float(v) for v in c.tolist()]
+        costs = [sum(tiles[b * tiles_x:(b + 1) * tiles_x]) for b in range(StripPlan.num_units(H))]
         plan = StripPlan.balanced(H, world, costs)
-        sharded.shard(plan, halo_mode=args.halo)
+        renderer.SetShard(comm, plan.bounds, gather_output=True)
         sc = plan.strip_costs(costs)
         plan_info = {"bounds": plan.bounds, "strip_cost_max_over_mean": round(max(sc) / (sum(sc) / world), 3)}
         for _ in range(args.warmup):
@@ -354,18 +356,23 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = W * H * n_e2e / (float(t2.item()) * 1e-3) / 1e6
-    halo_bytes = 0 if sharded.halo is None or not sharded.halo.calls else sharded.halo.bytes_sent // max(1, sharded.halo.calls)
+    halo_bytes = 0
+    if comm is not None:
+        sent, calls = comm.stats()
+        halo_bytes = sent // max(1, calls)
 
     # ---- per-kernel timing (CUDA events on the launching stream around every launch) ----
     kern = {}
     nprof = 5
-    if renderer is not None:        # the stand-alone passes have not rendered yet: bring them to steady state first
-        for _ in range(3):
+    if world == 1:                  # stand-alone passes on ONE stream, so a kernel's events do not include waiting for the other stream
+        for _ in range(3):          # (they have not rendered yet: bring them to steady state first)
             sharded.render(fi, seq.next(), stream)
     check(lib.zr_profile_enable(1))
-    for _ in range(nprof):          # every rank renders (the frame holds collectives) and times its own launches;
-        sharded.render(fi, seq.next(), stream)      # single stream here, so a kernel's events do not include waiting for the other stream
-        sharded.gather_output(stream)
+    for _ in range(nprof):          # N > 1: every rank renders (the frame holds collectives) and times its own launches
+        if world == 1:
+            sharded.render(fi, seq.next(), stream)
+        else:
+            frame(seq.next())
     if True:
         buf = C.create_string_buffer(8192)
         check(lib.zr_profile_collect(buf, 8192))
@@ -390,10 +397,17 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         tot = sum(kern.values())
-        y0, y1 = (0, H) if sharded.plan is None else sharded.plan.rows(rank)      # rank 0's strip
+        y0, y1 = (0, H) if plan is None else plan.rows(rank)      # rank 0's strip
         own_rows = y1 - y0
         # pixels that carry a surface (the lighting kernels move only the 4-byte flag word of the others: sky, light sources)
-        core = gb.download()[0]        # the per-kernel timing frames above rendered into `gb` (sharded.render)
+        if world == 1:
+            core = gb.download()[0]        # the per-kernel timing frames above rendered into `gb` (sharded.render)
+        else:
+            g = _lib.GBuffer()
+            check(lib.zr_renderer_get_gbuffer(renderer.handle, 0, C.byref(g)))
+            core = np.zeros((W * H, 4), dtype=np.uint32)
+            check(lib.zr_memcpy_d2h(core.ctypes.data_as(C.c_void_p), C.c_void_p(g.d_core), C.c_size_t(core.nbytes), None))
+            check(lib.zr_stream_synchronize(None))
         fl = core[:, 3].reshape(H, W)[y0:y1] & 0xff
         surf = int((((fl >> 2) & 1) == 0).sum() - ((((fl >> 2) & 1) == 0) & (((fl >> 1) & 1) == 1)).sum())
         px_all = W * own_rows
@@ -450,8 +464,8 @@ def main():
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": [W, H], "spp": 1, "bounces": 3, "restir_pt": "temporal + 1 spatial pass",
-                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halos, %s)" % (world, args.halo) if world > 1 else "single GPU",
-                       "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2, "block_order": "expensive tiles first" if args.expensive_first else "plain",
+                       "restir_di": "temporal + pairwise-MIS spatial", "parallelism": "1 frame / %d horizontal strips (32-row halos, grouped NCCL send/recv from C++, image gathered on rank 0)" % world if world > 1 else "single GPU",
+                       "strips": plan_info, "kernel_ms_per_frame_by_rank": rank_kernel_ms, "halo_bytes_per_exchange_per_rank": halo_bytes, "streams": 1 if side is None else 2, 
                        "l2": "per-frame working set ~0.8 GB >> 126 MB L2 (no flush needed)"},
             "e2e": {"value": round(e2e_value, 3), "unit": "Mpaths/s", "h2d_bytes_per_step": C.sizeof(_lib.FrameConstants),
                     "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},

@@ -604,6 +604,23 @@ ZR_API zr_status zr_profile_collect(char* buf, size_t buf_size);
 /* number of kernels this library launched since load (for bench.py's gpu_launches) */
 ZR_API uint64_t zr_kernel_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Strip-sharded frames across GPUs (the reference is single-GPU). One process per GPU; zr_comm carries the halo bands
+ * between neighbouring strips with grouped NCCL send / recv issued from C++ on the producing stream (csrc/comm.cu).
+ * Rank 0 calls zr_comm_unique_id and distributes the 256 bytes (any out-of-band channel: torch.distributed broadcast, MPI, a file);
+ * every rank then calls zr_comm_create with the same bytes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct zr_comm zr_comm;
+ZR_API zr_status zr_comm_unique_id(void* out256);
+ZR_API zr_status zr_comm_create(const void* id256, int rank, int world, zr_comm** out);
+ZR_API void zr_comm_destroy(zr_comm* c);
+ZR_API zr_status zr_comm_rank(zr_comm* c, int* rank, int* world);
+ZR_API zr_status zr_comm_stats(zr_comm* c, uint64_t* bytes_sent, uint64_t* calls);
+/* bounds[world + 1]: strip q owns rows [bounds[q], bounds[q + 1]); which_comm: 0 = main stream, 1 = second stream */
+ZR_API zr_status zr_comm_exchange_halos(zr_comm* c, int which_comm, const uint32_t* bounds, uint32_t halo_rows, const zr_image2d* planes,
+    int n_planes, void* stream);
+ZR_API zr_status zr_comm_gather_rows(zr_comm* c, const uint32_t* bounds, const zr_image2d* plane, int root, void* stream);
+
 /* ---- The frame (ZetaRenderer/Default: DefaultRenderer.cpp:304-520, PathTracer.cpp:149-563) ----
  * Owns the double-buffered G-buffers and one object of every pass and runs a frame in the reference's order:
  * (frame 1: emissive power + alias table) -> presampling if enabled -> GBufferRT -> DirectLighting || IndirectLighting
@@ -615,6 +632,11 @@ ZR_API zr_status zr_renderer_create(const zr_renderer_desc* desc, zr_scene* scen
 ZR_API zr_status zr_renderer_render(zr_renderer* r, const zr_frame_constants* frame, void* stream);
 /* optional SVGF stage between Compositing and TAA (BASELINE config 3); *out_pass (may be NULL) receives the pass for set_params */
 ZR_API zr_status zr_renderer_set_denoiser(zr_renderer* r, int enable, zr_svgf_pass** out_pass);
+/* Strip-sharded frame: this renderer computes rows [bounds[rank], bounds[rank + 1]) only (bounds: multiples of 32 except the last;
+ * ReSTIR PT integrator); halo bands move through `comm` at the four exchange points of a frame, the finished image is gathered on
+ * rank 0 (gather_output != 0). comm == NULL returns to the whole frame. History must be complete when the cut happens: render the
+ * warm-up frames unsharded on every rank. */
+ZR_API zr_status zr_renderer_set_shard(zr_renderer* r, zr_comm* comm, const uint32_t* bounds, int gather_output);
 ZR_API zr_status zr_renderer_get_output(zr_renderer* r, zr_image2d* out);      /* TAA output, RGBA16F */
 ZR_API zr_status zr_renderer_get_passes(zr_renderer* r, zr_gbuffer_pass** gbuffer, zr_direct_pass** direct,
     zr_indirect_pass** indirect, zr_compositing_pass** compositing, zr_taa_pass** taa);

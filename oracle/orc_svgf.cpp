@@ -10,7 +10,7 @@
 //                   blend colour and the first two luminance moments with alpha = max(1 / N, 0.2), N = history length <= 32;
 //                   variance = max(0, m2 - m1^2), replaced by the 3x3 spatial estimate while N < 4
 //   a-trous passes  step 1, 2, 4, 8, 16; B3-spline taps (5x5, radius 2) or the 3x3 binomial (radius 1);
-//                   w = h_i h_j * max(0, 1 - |dz| / (sigma_z z_c step)) * max(0, 1 - k_n (1 - n.n_c)) * max(0, 1 - |dl| / (sigma_l sqrt(var_c) + 1e-4));
+//                   w = h_i h_j * max(0, 1 - |dz| / (sigma_z z_c step)) * max(0, k_n n.n_c + (1 - k_n)) * max(0, 1 - |dl| / (sigma_l sqrt(var_c) + 1e-4));
 //                   colour' = sum w c / sum w, variance' = sum w^2 var / (sum w)^2, taps in row-major order, centre first
 // Storage: colour + variance as 4 x binary16 (variance in alpha), guide = {view depth f32, oct32 normal}.
 #include "orc_gbuffer.h"
@@ -152,6 +152,7 @@ extern "C"
                 const float lc = Math::Luminance(cc);
                 const float invZ = 1.0f / (prm.sigma_z * zc * (float)s);
                 const float invL = 1.0f / fmaf(prm.sigma_l, sqrtf(fmaxf(varc, 0.0f)), 1e-4f);
+                const float oneMinusK = 1.0f - prm.k_n;
                 const float w0 = hk[R] * hk[R];
                 float3 sumC = cc * w0;
                 float sumV = (w0 * w0) * varc, sumW = w0;
@@ -168,7 +169,8 @@ extern "C"
                         unpack_cv(in[t], ct, vart);
                         const float lt = Math::Luminance(ct);
                         const float wz = fmaf(-fabsf(zt - zc), invZ, 1.0f);
-                        const float wn = fmaf(dot(nt, nc) - 1.0f, prm.k_n, 1.0f);
+                        const float ndot = fmaf(nt.x, nc.x, fmaf(nt.y, nc.y, nt.z * nc.z));
+                        const float wn = fmaf(ndot, prm.k_n, oneMinusK);
                         const float wl = fmaf(-fabsf(lt - lc), invL, 1.0f);
                         float w = (hk[i + R] * hk[j + R]) * fmaxf(wz, 0.0f);
                         w = w * fmaxf(wn, 0.0f);

@@ -14,6 +14,7 @@
 // The renderer owns the double-buffered G-buffers (DefaultRendererImpl.h:111-121) and the pass objects; callers reach
 // the passes through zr_renderer_get_*_pass to set parameters, exactly like the reference's UI callbacks do.
 #include <cuda_runtime.h>
+#include <vector>
 #include "../../include/zr_abi.h"
 #include "zr_common.cuh"
 
@@ -35,6 +36,23 @@ struct zr_renderer
     cudaStream_t side = nullptr;            // DirectLighting runs here when twoStreams
     cudaEvent_t evGBuffer = nullptr, evDirect = nullptr;
     bool twoStreams = true;
+    // strip-sharded frames
+    zr_comm* comm = nullptr;                // not owned
+    int rank = 0, world = 1;
+    std::vector<uint32_t> bounds;
+    bool gatherOutput = true;
+    static constexpr uint32_t HALO = 32;
+    struct HookCtx { zr_renderer* r; int whichComm; } hookMain{ this, 0 }, hookSide{ this, 1 };
+    zr_status hookStatus = ZR_OK;
+    static void HaloHook(void* user, const zr_image2d* planes, int n, void* stream)
+    {
+        HookCtx* h = (HookCtx*)user;
+        zr_renderer* r = h->r;
+        // DirectLighting runs on the second stream when twoStreams: it gets its own communicator
+        const int which = (r->twoStreams && stream == (void*)r->side) ? 1 : 0;
+        const zr_status s = zr_comm_exchange_halos(r->comm, which, r->bounds.data(), HALO, planes, n, stream);
+        if (s != ZR_OK) r->hookStatus = s;
+    }
 
     void Release()
     {
@@ -136,12 +154,22 @@ extern "C"
             ZR_CUDA(cudaEventRecord(r->evDirect, r->side));
             ZR_CUDA(cudaStreamWaitEvent(stream, r->evDirect, 0));
         }
+        if (r->hookStatus != ZR_OK) { s = r->hookStatus; r->hookStatus = ZR_OK; return s; }
         zr_image2d di, ind, comp;
         s = zr_direct_pass_get_output(r->direct, ZR_DIRECT_FINAL, &di);
         if (s != ZR_OK) return s;
         s = r->integrator != ZR_INTEGRATOR_RESTIR_PT ? zr_gi_pass_get_output(r->gi, ZR_GI_FINAL, &ind)
                                                      : zr_indirect_pass_get_output(r->indirect, ZR_INDIRECT_FINAL, &ind);
         if (s != ZR_OK) return s;
+        if (r->comm && r->world > 1)
+        {
+            // the firefly stencil and TAA read the finals / the history one to two rows beyond the strip
+            zr_image2d planes[3] = { di, ind, zr_image2d{} };
+            s = zr_taa_pass_get_output(r->taa, &planes[2]);
+            if (s != ZR_OK) return s;
+            s = zr_comm_exchange_halos(r->comm, 0, r->bounds.data(), zr_renderer::HALO, planes, 3, stream);
+            if (s != ZR_OK) return s;
+        }
         s = zr_compositing_pass_render(r->compositing, &in, di.d_ptr, ind.d_ptr, stream);
         if (s != ZR_OK) return s;
         s = zr_compositing_pass_get_output(r->compositing, &comp);
@@ -155,6 +183,14 @@ extern "C"
         }
         s = zr_taa_pass_render(r->taa, &in, comp.d_ptr, stream);
         if (s != ZR_OK) return s;
+        if (r->comm && r->world > 1 && r->gatherOutput)
+        {
+            zr_image2d img;
+            s = zr_taa_pass_get_output(r->taa, &img);
+            if (s != ZR_OK) return s;
+            s = zr_comm_gather_rows(r->comm, r->bounds.data(), &img, 0, stream);
+            if (s != ZR_OK) return s;
+        }
         r->framesRendered++;
         return ZR_OK;
     }
@@ -192,6 +228,52 @@ extern "C"
         if (enable && !r->svgf) s = zr_svgf_pass_create(r->width, r->height, &r->svgf);
         if (!enable && r->svgf) { zr_svgf_pass_destroy(r->svgf); r->svgf = nullptr; }
         if (out_pass) *out_pass = r->svgf;
+        return s;
+    }
+    zr_status zr_renderer_set_shard(zr_renderer* r, zr_comm* comm, const uint32_t* bounds, int gather_output)
+    {
+        if (!r) return ZR_ERR_INVALID_ARG;
+        zr_status s = ZR_OK;
+        if (!comm)
+        {
+            r->comm = nullptr; r->world = 1; r->rank = 0; r->bounds.clear();
+            s = zr_gbuffer_pass_set_rows(r->gbufferPass, 0, r->height);
+            if (s == ZR_OK) s = zr_direct_pass_set_rows(r->direct, 0, r->height);
+            if (s == ZR_OK) s = zr_indirect_pass_set_rows(r->indirect, 0, r->height);
+            if (s == ZR_OK) s = zr_compositing_pass_set_rows(r->compositing, 0, r->height);
+            if (s == ZR_OK) s = zr_taa_pass_set_rows(r->taa, 0, r->height);
+            if (s == ZR_OK) s = zr_direct_pass_set_halo_exchange(r->direct, nullptr, nullptr);
+            if (s == ZR_OK) s = zr_indirect_pass_set_halo_exchange(r->indirect, nullptr, nullptr);
+            return s;
+        }
+        if (!bounds) { zr::set_error("zr_renderer_set_shard: bounds missing"); return ZR_ERR_INVALID_ARG; }
+        if (r->integrator != ZR_INTEGRATOR_RESTIR_PT || r->svgf)
+        {
+            zr::set_error("zr_renderer_set_shard: sharded frames support the ReSTIR PT integrator without the SVGF stage");
+            return ZR_ERR_UNSUPPORTED;
+        }
+        int rank = 0, world = 1;
+        s = zr_comm_rank(comm, &rank, &world);
+        if (s != ZR_OK) return s;
+        if (bounds[0] != 0 || bounds[world] != r->height) { zr::set_error("zr_renderer_set_shard: bounds must cover [0, height)"); return ZR_ERR_INVALID_ARG; }
+        for (int q = 0; q < world; q++)
+            if (bounds[q + 1] <= bounds[q] || (q + 1 < world && bounds[q + 1] % 32 != 0))
+            {
+                zr::set_error("zr_renderer_set_shard: strip bounds must increase and be multiples of 32 rows");
+                return ZR_ERR_INVALID_ARG;
+            }
+        r->comm = comm; r->rank = rank; r->world = world; r->gatherOutput = gather_output != 0;
+        r->bounds.assign(bounds, bounds + world + 1);
+        const uint32_t y0 = bounds[rank], y1 = bounds[rank + 1], H = r->height;
+        const uint32_t g0 = y0 > zr_renderer::HALO ? y0 - zr_renderer::HALO : 0, g1 = y1 + zr_renderer::HALO < H ? y1 + zr_renderer::HALO : H;
+        s = zr_gbuffer_pass_set_rows(r->gbufferPass, g0, g1);            // the G-buffer halo is re-rendered locally
+        if (s == ZR_OK) s = zr_direct_pass_set_rows(r->direct, y0, y1);
+        if (s == ZR_OK) s = zr_indirect_pass_set_rows(r->indirect, y0, y1);
+        // the TAA neighbourhood reads the composited signal one row beyond the strip
+        if (s == ZR_OK) s = zr_compositing_pass_set_rows(r->compositing, y0 > 0 ? y0 - 1 : 0, y1 + 1 < H ? y1 + 1 : H);
+        if (s == ZR_OK) s = zr_taa_pass_set_rows(r->taa, y0, y1);
+        if (s == ZR_OK) s = zr_direct_pass_set_halo_exchange(r->direct, world > 1 ? zr_renderer::HaloHook : nullptr, &r->hookSide);
+        if (s == ZR_OK) s = zr_indirect_pass_set_halo_exchange(r->indirect, world > 1 ? zr_renderer::HaloHook : nullptr, &r->hookMain);
         return s;
     }
     zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi)

@@ -571,11 +571,11 @@ namespace
     // -------------------------------------------------------------------------------------------
     __global__ void __launch_bounds__(256) k_sort(FrameView f, int mode, uint32_t spatialFlag, const zr_rpt_reservoir* __restrict__ resCurr,
         const zr_rpt_reservoir* __restrict__ resPrev, const uint16_t* __restrict__ neighbor, uint16_t* __restrict__ threadMap,
-        uint32_t dispX, uint32_t dispY)
+        uint32_t dispX, uint32_t dispY, uint32_t tileRow0)
     {
         enum { SUCCESS = 0, INVALID_PIXEL = 1, NOT_FOUND = 2, EMPTY = 4 };
         __shared__ unsigned long long s_warp[8];
-        const uint32_t Gx = blockIdx.x, Gy = blockIdx.y, Gidx = threadIdx.x;
+        const uint32_t Gx = blockIdx.x, Gy = blockIdx.y + tileRow0, Gidx = threadIdx.x;      // only the tile rows of the owned strip are launched
         const uint32_t GTx = Gidx & 15, GTy = Gidx >> 4;
         const bool againstEdge = (Gx == dispX - 1) || (Gy == dispY - 1);
         const bool lastGroup = (Gx == dispX - 1) && (Gy == dispY - 1);
@@ -1092,7 +1092,8 @@ struct zr_indirect_pass
                 {
                     const uint32_t sx = (width + 31) / 32, sy = (height + 31) / 32;
                     ZR_PROF("k_sort", stream);
-                    k_sort<<<dim3(sx, sy), 256, 0, stream>>>(f, 3, 1u, rin, nullptr, d_neighbor, d_threadMap[1], sx, sy);
+                    const uint32_t ty0 = prm.rowBegin / 32, ty1 = (prm.rowEnd + 31) / 32;
+                    k_sort<<<dim3(sx, ty1 - ty0), 256, 0, stream>>>(f, 3, 1u, rin, nullptr, d_neighbor, d_threadMap[1], sx, sy, ty0);
                     ZR_LAUNCH_CHECK();
                 }
                 if (execution == ZR_RPT_EXEC_QUEUED)

@@ -66,7 +66,7 @@ namespace
         unsigned long long bar[2];
     };
 
-    __global__ void __launch_bounds__(1024, 1) k_spatial_merge(const __grid_constant__ CUtensorMap mapIn, FrameView f, RptParams prm,
+    __global__ void __launch_bounds__(1024, 1) k_spatial_merge(const CUtensorMap* __restrict__ pMapIn, FrameView f, RptParams prm,
         const zr_rpt_reservoir* __restrict__ resIn, zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target,
         float4* __restrict__ finalImg, const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap,
         const ShiftResult* __restrict__ shiftRes, uint32_t tilesX, uint32_t tileRow0, uint32_t numTiles)
@@ -89,7 +89,7 @@ namespace
             const uint32_t tx = tile % tilesX, ty = tileRow0 + tile / tilesX;
             uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar[stage]);
             tma::MbarArriveExpectTx(bar, TILE_BYTES);
-            tma::Load2D(&sm.rec[stage][0][0], &mapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
+            tma::Load2D(&sm.rec[stage][0][0], pMapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
         };
         if (t == 0 && blockIdx.x < numTiles)
             issue(blockIdx.x, 0);
@@ -296,7 +296,8 @@ void SpatialQueued::Release()
     if (d_queue) cudaFree(d_queue);
     if (d_counters) cudaFree(d_counters);
     if (d_shift) cudaFree(d_shift);
-    d_queue = nullptr; d_counters = nullptr; d_shift = nullptr;
+    if (d_maps) cudaFree(d_maps);
+    d_queue = nullptr; d_counters = nullptr; d_shift = nullptr; d_maps = nullptr;
     ready = false;
 }
 
@@ -320,6 +321,10 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
             return ZR_ERR_CUDA;
         }
     }
+    // the maps are read from global memory, one address per plane, written once here
+    ZR_CUDA(cudaMalloc(&d_maps, 2 * sizeof(CUtensorMap)));
+    ZR_CUDA(cudaMemcpy(d_maps, mapRes, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    ZR_CUDA(cudaDeviceSynchronize());
     int dev = 0;
     ZR_CUDA(cudaGetDevice(&dev));
     ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
@@ -354,7 +359,7 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
         const uint32_t numTiles = tilesX * (tileRow1 - tileRow0);
         const uint32_t grid = numTiles < (uint32_t)numSMs ? numTiles : (uint32_t)numSMs;
         ZR_PROF("k_spatial_merge", stream);
-        k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(mapRes[plane], f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
+        k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(d_maps + plane, f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
             d_shift, tilesX, tileRow0, numTiles);
         ZR_LAUNCH_CHECK();
     }

@@ -14,6 +14,7 @@
 #include "zr_common.cuh"
 #include "zr_tma.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace zr
 {
@@ -114,7 +115,11 @@ namespace
     {
         static constexpr int TU = P == 2 ? 32 : 64;                 // lattice columns of the output tile (x P phases each)
         static constexpr int TV = 16;
-        static constexpr int ROW = (TU + 2 * R) * P;                // staged elements per lattice row
+        // apron columns left and right. A TMA box must start on a 16-byte boundary in global memory: with 8-byte pixels the step-1
+        // map needs an EVEN start column, so its apron is 2 even for the 3x3 taps (an odd start is an illegal-instruction fault,
+        // r2i); in the lattice maps the innermost dimension is the 16-byte phase pair, so any lattice column will do.
+        static constexpr int AX = P == 2 ? R : 2;
+        static constexpr int ROW = (TU + 2 * AX) * P;               // staged elements per lattice row
         static constexpr int SV = TV + 2 * R;
         static constexpr int NS = ROW * SV;
         static constexpr int OUT = TU * P * TV;                     // 1024
@@ -122,14 +127,16 @@ namespace
         static constexpr int OFF_RAWC = 0;
         static constexpr int OFF_RAWG = OFF_RAWC + ((NS * 8 + 127) / 128) * 128;
         static constexpr int OFF_OUT = OFF_RAWG + ((NS * 8 + 127) / 128) * 128;
-        static constexpr int OFF_F = OFF_OUT + OUT * 8;             // 9 float planes of NS
+        static constexpr int OFF_F = OFF_OUT + OUT * 8;             // expanded box: 2 x float4 + 1 float per staged pixel
         static constexpr int OFF_BAR = OFF_F + 9 * NS * 4;
         static constexpr int BYTES = ((OFF_BAR + 8 + 127) / 128) * 128;
     };
 
     template<int R, int P, bool LAST>
-    __global__ void __launch_bounds__(512, 2) k_svgf_atrous(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapGuide,
-        const __grid_constant__ CUtensorMap mapOut, float4* __restrict__ outF, uint32_t W, uint32_t H, uint32_t step, uint32_t tilesU,
+    // The tensor maps are read from global memory (one address per (pass, plane), uploaded once when the pass is sized) instead of
+    // travelling as 3 x 128 bytes of __grid_constant__ parameters with each of the five launches.
+    __global__ void __launch_bounds__(512, 2) k_svgf_atrous(const CUtensorMap* __restrict__ pMapIn, const CUtensorMap* __restrict__ pMapGuide,
+        const CUtensorMap* __restrict__ pMapOut, float4* __restrict__ outF, uint32_t W, uint32_t H, uint32_t step, uint32_t tilesU,
         SvgfParamsDev prm)
     {
         using T = AtrousTile<R, P>;
@@ -137,9 +144,10 @@ namespace
         uint2* rawC = reinterpret_cast<uint2*>(smem + T::OFF_RAWC);
         uint2* rawG = reinterpret_cast<uint2*>(smem + T::OFF_RAWG);
         uint2* outT = reinterpret_cast<uint2*>(smem + T::OFF_OUT);
-        float* fp = reinterpret_cast<float*>(smem + T::OFF_F);
-        float* s_r = fp, *s_g = fp + T::NS, *s_b = fp + 2 * T::NS, *s_var = fp + 3 * T::NS, *s_lum = fp + 4 * T::NS, *s_z = fp + 5 * T::NS,
-            *s_nx = fp + 6 * T::NS, *s_ny = fp + 7 * T::NS, *s_nz = fp + 8 * T::NS;
+        // expanded box: {r, g, b, variance}, {depth, normal}, luminance -- two 128-bit and one 32-bit shared-memory load per tap
+        float4* s_cv = reinterpret_cast<float4*>(smem + T::OFF_F);
+        float4* s_zn = s_cv + T::NS;
+        float* s_lum = reinterpret_cast<float*>(s_zn + T::NS);
         uint64_t* bar = reinterpret_cast<uint64_t*>(smem + T::OFF_BAR);
         const uint32_t t = threadIdx.x;
         const int tu = (int)(blockIdx.x % tilesU), tv = (int)(blockIdx.x / tilesU);
@@ -157,13 +165,13 @@ namespace
             tma::MbarArriveExpectTx(bar, 2u * T::NS * 8u);
             if (P == 2)
             {
-                tma::Load4D(rawC, &mapIn, bar, 2 * pair, u0 - R, py, v0 - R);
-                tma::Load4D(rawG, &mapGuide, bar, 2 * pair, u0 - R, py, v0 - R);
+                tma::Load4D(rawC, pMapIn, bar, 2 * pair, u0 - T::AX, py, v0 - R);
+                tma::Load4D(rawG, pMapGuide, bar, 2 * pair, u0 - T::AX, py, v0 - R);
             }
             else
             {
-                tma::Load2D(rawC, &mapIn, bar, u0 - R, v0 - R);
-                tma::Load2D(rawG, &mapGuide, bar, u0 - R, v0 - R);
+                tma::Load2D(rawC, pMapIn, bar, u0 - T::AX, v0 - R);
+                tma::Load2D(rawG, pMapGuide, bar, u0 - T::AX, v0 - R);
             }
         }
         tma::MbarWait(bar, 0);
@@ -172,8 +180,8 @@ namespace
         {
             const int sv = e / T::ROW, col = e % T::ROW;
             int x, y;
-            if (P == 2) { x = (u0 - R + (col >> 1)) * (int)step + 2 * pair + (col & 1); y = (v0 - R + sv) * (int)step + py; }
-            else { x = u0 - R + col; y = v0 - R + sv; }
+            if (P == 2) { x = (u0 - T::AX + (col >> 1)) * (int)step + 2 * pair + (col & 1); y = (v0 - R + sv) * (int)step + py; }
+            else { x = u0 - T::AX + col; y = v0 - R + sv; }
             const bool inImg = x >= 0 && y >= 0 && x < (int)W && y < (int)H;
             float3 c = f3(0); float var = 0, z = FLT_MAX_; float3 n = f3(0);
             if (inImg)
@@ -183,8 +191,9 @@ namespace
                 z = asfloat(g.x);
                 n = Math::DecodeUnitVector(Math::DecodeUNorm2(g.y));
             }
-            s_r[e] = c.x; s_g[e] = c.y; s_b[e] = c.z; s_var[e] = var; s_lum[e] = Math::Luminance(c); s_z[e] = z;
-            s_nx[e] = n.x; s_ny[e] = n.y; s_nz[e] = n.z;
+            s_cv[e] = f4(c.x, c.y, c.z, var);
+            s_zn[e] = f4(z, n.x, n.y, n.z);
+            s_lum[e] = Math::Luminance(c);
         }
         __syncthreads();
         constexpr float h5[5] = { 1.0f / 16, 1.0f / 4, 3.0f / 8, 1.0f / 4, 1.0f / 16 };
@@ -194,17 +203,19 @@ namespace
         {
             const int o = (int)t + k * 512;
             const int ov = o / (T::TU * P), ocol = o % (T::TU * P);
-            const int ci = (ov + R) * T::ROW + ocol + R * P;
-            const float zc = s_z[ci];
+            const int ci = (ov + R) * T::ROW + ocol + T::AX * P;
+            const float4 cvc = s_cv[ci], znc = s_zn[ci];
+            const float zc = znc.x;
             uint2 packed = rawC[ci];
-            float4 res = f4(s_r[ci], s_g[ci], s_b[ci], s_var[ci]);
+            float4 res = cvc;
             if (zc != FLT_MAX_)
             {
-                const float3 cc = f3(s_r[ci], s_g[ci], s_b[ci]);
-                const float varc = s_var[ci], lc = s_lum[ci];
-                const float3 nc = f3(s_nx[ci], s_ny[ci], s_nz[ci]);
+                const float3 cc = f3(cvc.x, cvc.y, cvc.z);
+                const float varc = cvc.w, lc = s_lum[ci];
+                const float3 nc = f3(znc.y, znc.z, znc.w);
                 const float invZ = 1.0f / (prm.sigma_z * zc * (float)step);
                 const float invL = 1.0f / fmaf(prm.sigma_l, sqrtf(fmaxf(varc, 0.0f)), 1e-4f);
+                const float oneMinusK = 1.0f - prm.k_n;
                 const float w0 = (R == 2 ? h5[2] : h3[1]) * (R == 2 ? h5[2] : h3[1]);
                 float3 sumC = cc * w0;
                 float sumV = (w0 * w0) * varc, sumW = w0;
@@ -216,14 +227,16 @@ namespace
                         if (i == 0 && j == 0) continue;
                         const int ti = ci + j * T::ROW + i * P;
                         const float hw = (R == 2 ? h5[i + R] : h3[i + R]) * (R == 2 ? h5[j + R] : h3[j + R]);
-                        const float wz = fmaf(-fabsf(s_z[ti] - zc), invZ, 1.0f);
-                        const float wn = fmaf(dot(f3(s_nx[ti], s_ny[ti], s_nz[ti]), nc) - 1.0f, prm.k_n, 1.0f);
+                        const float4 cvt = s_cv[ti], znt = s_zn[ti];
+                        const float wz = fmaf(-fabsf(znt.x - zc), invZ, 1.0f);
+                        const float ndot = fmaf(znt.y, nc.x, fmaf(znt.z, nc.y, znt.w * nc.z));
+                        const float wn = fmaf(ndot, prm.k_n, oneMinusK);
                         const float wl = fmaf(-fabsf(s_lum[ti] - lc), invL, 1.0f);
                         float w = hw * fmaxf(wz, 0.0f);
                         w = w * fmaxf(wn, 0.0f);
                         w = w * fmaxf(wl, 0.0f);
-                        sumC = f3(fmaf(w, s_r[ti], sumC.x), fmaf(w, s_g[ti], sumC.y), fmaf(w, s_b[ti], sumC.z));
-                        sumV = fmaf(w * w, s_var[ti], sumV);
+                        sumC = f3(fmaf(w, cvt.x, sumC.x), fmaf(w, cvt.y, sumC.y), fmaf(w, cvt.z, sumC.z));
+                        sumV = fmaf(w * w, cvt.w, sumV);
                         sumW = sumW + w;
                     }
                 const float3 oc = sumC / sumW;
@@ -248,8 +261,8 @@ namespace
             __syncthreads();
             if (t == 0)
             {
-                if (P == 2) tma::Store4D(&mapOut, outT, 2 * pair, u0, py, v0);
-                else tma::Store2D(&mapOut, outT, u0, v0);
+                if (P == 2) tma::Store4D(pMapOut, outT, 2 * pair, u0, py, v0);
+                else tma::Store2D(pMapOut, outT, u0, v0);
                 tma::StoreCommit();
                 tma::StoreWaitAll();
             }
@@ -274,6 +287,8 @@ struct zr_svgf_pass
     zr_svgf_params params{};
     // tensor maps: [pass][plane]; load boxes depend on the radius, store boxes do not
     CUtensorMap mapCvLoad[MAX_PASSES][2], mapCvStore[MAX_PASSES][2], mapGuideLoad[MAX_PASSES][2];
+    CUtensorMap* d_maps = nullptr;      // device copy: [kind 0 = cv load, 1 = cv store, 2 = guide load][pass][plane]
+    const CUtensorMap* DevMap(int kind, int k, int plane) const { return d_maps + ((kind * MAX_PASSES + k) * 2 + plane); }
     bool mapsReady = false;
 
     static void Defaults(zr_svgf_params* p) { p->sigma_z = 0.02f; p->k_n = 16.0f; p->sigma_l = 4.0f; p->radius = 2; p->num_passes = 5; }
@@ -286,7 +301,8 @@ struct zr_svgf_pass
             d_cv[i] = nullptr; d_guide[i] = nullptr; d_hist[i] = nullptr;
         }
         if (d_out) cudaFree(d_out);
-        d_out = nullptr; mapsReady = false;
+        if (d_maps) cudaFree(d_maps);
+        d_out = nullptr; d_maps = nullptr; mapsReady = false;
     }
 
     zr_status EncodeMaps()
@@ -303,7 +319,7 @@ struct zr_svgf_pass
                 {
                     const uint64_t dims[2] = { pitch, rows };
                     const uint64_t strides[1] = { (uint64_t)pitch * 8 };
-                    const uint32_t boxL[2] = { 64 + 2 * R, 16 + 2 * R }, boxS[2] = { 64, 16 };
+                    const uint32_t boxL[2] = { 64 + 2 * 2, 16 + 2 * R }, boxS[2] = { 64, 16 };       // AtrousTile<R, 1>::AX == 2
                     ok = ok && tma::EncodeWords(&mapCvLoad[k][pl], d_cv[pl], 2, dims, strides, boxL);
                     ok = ok && tma::EncodeWords(&mapGuideLoad[k][pl], d_guide[pl], 2, dims, strides, boxL);
                     ok = ok && tma::EncodeWords(&mapCvStore[k][pl], d_cv[pl], 2, dims, strides, boxS);
@@ -325,6 +341,13 @@ struct zr_svgf_pass
                 }
             }
         }
+        // no kernel may still be using the old maps, and the new ones are in place before the next launch
+        ZR_CUDA(cudaDeviceSynchronize());
+        if (!d_maps) ZR_CUDA(cudaMalloc(&d_maps, sizeof(CUtensorMap) * 3 * MAX_PASSES * 2));
+        CUtensorMap host[3][MAX_PASSES][2];
+        memcpy(host[0], mapCvLoad, sizeof(mapCvLoad)); memcpy(host[1], mapCvStore, sizeof(mapCvStore)); memcpy(host[2], mapGuideLoad, sizeof(mapGuideLoad));
+        ZR_CUDA(cudaMemcpy(d_maps, host, sizeof(host), cudaMemcpyHostToDevice));
+        ZR_CUDA(cudaDeviceSynchronize());
         mapsReady = true;
         return ZR_OK;
     }
@@ -374,9 +397,9 @@ struct zr_svgf_pass
         using namespace zr;
         const uint32_t s = 1u << k;
         const SvgfParamsDev prm{ params.sigma_z, params.k_n, params.sigma_l };
-        const CUtensorMap& mIn = mapCvLoad[k][inPlane];
-        const CUtensorMap& mG = mapGuideLoad[k][cur];
-        const CUtensorMap& mOut = mapCvStore[k][1 - inPlane];
+        const CUtensorMap* mIn = DevMap(0, k, inPlane);
+        const CUtensorMap* mG = DevMap(2, k, cur);
+        const CUtensorMap* mOut = DevMap(1, k, 1 - inPlane);
         ZR_PROF("k_svgf_atrous", stream);
         if (s == 1)
         {
@@ -395,6 +418,11 @@ struct zr_svgf_pass
             else k_svgf_atrous<R, 2, false><<<grid, 512, T::BYTES, stream>>>(mIn, mG, mOut, d_out, width, height, s, tilesU, prm);
         }
         ZR_LAUNCH_CHECK();
+        if (getenv("ZR_SVGF_DEBUG"))
+        {
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { set_error("k_svgf_atrous pass %d (step %u, radius %d, last %d): %s", k, s, R, (int)last, cudaGetErrorString(e)); return ZR_ERR_CUDA; }
+        }
         return ZR_OK;
     }
 

@@ -35,6 +35,7 @@ struct SpatialQueued
     size_t capacity = 0;
     CUtensorMap mapRes[2];                      // the two reservoir planes as [H][W] x 64 B, 32x32-pixel boxes
     const void* mapBase[2] = { nullptr, nullptr };
+    CUtensorMap* d_maps = nullptr;              // device copy of mapRes (the kernel reads the descriptor from global memory)
     int numSMs = 0;
     bool ready = false;
 

@@ -393,6 +393,46 @@ class _Borrowed:
             check(lib.zr_svgf_pass_default_params(C.byref(self.params)))
 
 
+class Comm:
+    """zr_comm: halo transport between strips (NCCL, bound inside the library). `Comm.from_torch()` distributes the id through an
+    initialised torch.distributed process group; any other out-of-band channel works with Comm.unique_id() / Comm(id, rank, world)."""
+
+    def __init__(self, id256, rank, world):
+        self.handle = C.c_void_p()
+        self.rank, self.world = rank, world
+        buf = (C.c_ubyte * 256).from_buffer_copy(bytes(id256))
+        check(lib.zr_comm_create(buf, int(rank), int(world), C.byref(self.handle)))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 256)()
+        check(lib.zr_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.zeros(256, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8).clone()
+        t = t.to(dev)
+        dist.broadcast(t, 0, group=group)
+        return cls(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def stats(self):
+        b, c = C.c_uint64(), C.c_uint64()
+        check(lib.zr_comm_stats(self.handle, C.byref(b), C.byref(c)))
+        return b.value, c.value
+
+    def close(self):
+        if self.handle:
+            lib.zr_comm_destroy(self.handle)
+            self.handle = None
+
+
 class Renderer:
     """The frame driver (zr_renderer, csrc/renderer.cu): G-buffers + all passes, one Render(frame constants) per frame."""
 
@@ -418,6 +458,15 @@ class Renderer:
             h = C.c_void_p()
             check(lib.zr_renderer_get_gi_pass(self.handle, C.byref(h)))
             self.gi = _Borrowed(IndirectLightingGI, h)
+
+    def SetShard(self, comm, bounds, gather_output=True):
+        """Strip-sharded frame: this rank renders rows [bounds[rank], bounds[rank + 1]); None returns to the whole frame."""
+        if comm is None:
+            check(lib.zr_renderer_set_shard(self.handle, None, None, 0))
+            return
+        arr = (C.c_uint32 * len(bounds))(*[int(b) for b in bounds])
+        check(lib.zr_renderer_set_shard(self.handle, comm.handle, arr, int(gather_output)))
+        self._comm = comm
 
     def SetDenoiser(self, enable=True):
         """SVGF between Compositing and TAA (BASELINE config 3)."""
