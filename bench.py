@@ -361,6 +361,25 @@ def main():
         sent, calls = comm.stats()
         halo_bytes = sent // max(1, calls)
 
+    # ---- config 3 of BASELINE.json: the same frame with the SVGF denoise stage between Compositing and TAA (N == 1) ----
+    with_svgf = None
+    if world == 1:
+        renderer.SetDenoiser(True)
+        for _ in range(max(3, args.warmup)):
+            frame(seq.next())
+        fcs3 = [seq.next() for _ in range(args.steps)]
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record(stream)
+        for fc in fcs3:
+            frame(fc)
+        e5.record(stream)
+        barrier()
+        ms3 = e4.elapsed_time(e5)
+        with_svgf = {"value": round(W * H * args.steps / (ms3 * 1e-3) / 1e6, 3), "unit": "Mpaths/s", "ms_per_step": round(ms3 / args.steps, 4),
+                     "what": "same frame + SVGF (temporal accumulation + 5 a-trous passes, 5x5 taps) between Compositing and TAA"}
+        renderer.SetDenoiser(False)
+
     # ---- per-kernel timing (CUDA events on the launching stream around every launch) ----
     kern = {}
     nprof = 5
@@ -471,7 +490,7 @@ def main():
                     "d2h_bytes_per_step": W * H * 8, "frames": n_e2e},
             "gpu_launches": int(launches),
             "clocks": _clock_summary(clocks),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "c1_alias_table": c1,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "c1_alias_table": c1, "with_svgf": with_svgf,
         }
         print(json.dumps(line))
     if world > 1:

@@ -470,10 +470,14 @@ typedef enum zr_indirect_stage
 {
     ZR_RPT_STAGE_ALL = 0, ZR_RPT_STAGE_PATHTRACE = 1, ZR_RPT_STAGE_TEMPORAL = 2, ZR_RPT_STAGE_SPATIAL = 3
 } zr_indirect_stage;
-/* execution model of the spatial reuse pass (same results): per-case shift queues + TMA-staged streaming merge (default), or the
- * fused kernel that does both shifts and the merge per pixel. Switch for measurements; ZETARAY_B200_SPATIAL=fused|queued sets the
- * initial value. */
-typedef enum zr_indirect_execution { ZR_RPT_EXEC_FUSED = 0, ZR_RPT_EXEC_QUEUED = 1 } zr_indirect_execution;
+/* execution model of the pass (same results in every mode):
+ *   QUEUED (default)  lock-step path generation (k_pathtrace) + temporal and spatial reuse through per-case shift queues and the
+ *                     TMA-staged streaming merge
+ *   FUSED             round 1: k_pathtrace + fused k_temporal / k_spatial (both shifts and the merge inline per pixel)
+ *   WAVEFRONT         QUEUED, but path generation as one launch per bounce over a compacted queue of live paths (rpt_wavefront.cu);
+ *                     measured slower than k_pathtrace on every scene, kept for measurement
+ * ZETARAY_B200_SPATIAL=fused|queued|wavefront sets the initial value. */
+typedef enum zr_indirect_execution { ZR_RPT_EXEC_FUSED = 0, ZR_RPT_EXEC_QUEUED = 1, ZR_RPT_EXEC_WAVEFRONT = 2 } zr_indirect_execution;
 ZR_API zr_status zr_indirect_pass_create(uint32_t width, uint32_t height, zr_indirect_pass** out);
 ZR_API zr_status zr_indirect_pass_set_execution(zr_indirect_pass* p, zr_indirect_execution mode);
 ZR_API zr_status zr_indirect_pass_resize(zr_indirect_pass* p, uint32_t width, uint32_t height);

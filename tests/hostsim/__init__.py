@@ -43,13 +43,3 @@ def load():
 def load_di():
     build()
     return C.CDLL(SO_DI)
-
-
-def load_variant(name, defines):
-    """A host build of the same sources with experiment switches of the device headers turned on (e.g. the register-ordered
-    traversal, -DZR_TRAVERSE_REGISTER_ORDER), so that a variant prepared for a GPU A/B is already known to be correct."""
-    so = _build(os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "libhostsim_%s.so" % name), False, defines)
-    lib = C.CDLL(so)
-    lib.hostsim_validate.restype = C.c_uint64
-    return lib
-

@@ -107,16 +107,3 @@ def test_zero_area_triangles():
             assert k < n and needle[k], (seed, i, k)          # the brute-force answer of every differing ray is a needle
             assert not (got[i, 0] < ref[i, 0]), (seed, i)     # and the BVH never reports something nearer than brute force
     assert bad < total // 500
-
-
-def test_register_ordered_traversal_variant(monkeypatch):
-    """The opt-in traversal ordering (zr_scene.cuh, -DZR_TRAVERSE_REGISTER_ORDER: children ordered in scalar registers instead of
-    dynamically indexed arrays; prepared for a GPU A/B, not the default) gives the same answers as brute force."""
-    from tests import test_bvh_host
-    lib = hostsim.load_variant("regorder", ["ZR_TRAVERSE_REGISTER_ORDER"])
-    monkeypatch.setattr(hostsim, "load", lambda: lib)
-    for kind in KINDS:
-        test_random_soups(kind)
-    for name, make, cam, nrays in test_bvh_host.CASES[:4]:
-        test_bvh_host.test_builder_and_traversal_against_brute_force(name, make, cam, nrays)
-

@@ -26,7 +26,7 @@ def _diff_report(name, a, b, fields=None):
     return "%s differs at %d/%d entries; first idx %d got %s want %s" % (name, len(d), len(a), d[0], a[d[0]], b[d[0]])
 
 
-def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, cam_path=None, accumulate=False, presample=None):
+def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, cam_path=None, accumulate=False, presample=None, execution=None):
     import torch
     from zetaray_b200 import lib, check, _lib
     from zetaray_b200.passes import Scene, GBuffers, GBufferRT, IndirectLighting, download_image
@@ -41,6 +41,8 @@ def _run(which, w, h, nframes, params=None, jitter=True, dof=False, dump=None, c
     gb = GBuffers(w, h)
     gpass = GBufferRT()
     ind = IndirectLighting(w, h)
+    if execution is not None:
+        ind.SetExecution(execution)
     if params:
         for k, v in params.items():
             setattr(R.params, k, v)
@@ -144,6 +146,19 @@ def test_rpt_accumulate_and_two_spatial_passes():
     problems, _ = _run("glossy", 256, 144, 4, accumulate=True)
     assert not problems, "\n".join(problems)
     problems, _ = _run("cornell", 256, 144, 4, params=dict(num_spatial_passes=2))
+    assert not problems, "\n".join(problems)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("execution", [0, 2])
+def test_rpt_execution_models_agree_with_the_oracle(execution):
+    # the default (queued reuse passes) runs in every other test; here the round-1 fused kernels (0) and wavefront path generation
+    # (2): glass + 6 bounces so that the wave-wide Russian roulette crosses the launch boundary, two spatial passes, moving camera
+    path = lambda f: (0.03 * f, 1.2 + 0.02 * f, -4.043 + 0.05 * f)
+    problems, _ = _run("glass", 256, 144, 4, params=dict(max_non_tr_bounces=5, max_glossy_tr_bounces=6, num_spatial_passes=2),
+                       cam_path=path, execution=execution)
+    assert not problems, "\n".join(problems)
+    problems, _ = _run("glossy", 333, 187, 3, execution=execution)
     assert not problems, "\n".join(problems)
 
 

@@ -17,11 +17,8 @@
 // translation unit -- in either formulation, empty stack or early return -- ptxas lays k_rgi out so that warps run the traversal with
 // 6.9 instead of 12.4 active lanes (30.0 G instead of 16.7 G warp instructions, 116 ms instead of 60 ms on the 300 k-triangle atrium),
 // although the atrium's ReSTIR GI frame contains no degenerate ray at all. The other kernels are unaffected and the path tracer needs
-// the cut (3.5 s -> 0.12 s on the tunnel), so only this unit opts out until the reconvergence difference is understood with
-// ncu's source view (next round). Cost: a zero-direction ray (2-3 per 14 400 pixels on scenes with glass) sweeps the tree here.
-#ifndef ZR_RGI_WITH_DEGENERATE_CUT      /* A/B switch: -DZR_RGI_WITH_DEGENERATE_CUT builds this unit with the cut again */
+// the cut (3.5 s -> 0.12 s on the tunnel), so only this unit opts out. Cost: a zero-direction ray (2-3 per 14 400 pixels on scenes with glass) sweeps the tree here.
 #define ZR_NO_DEGENERATE_RAY_EARLY_OUT
-#endif
 #include "zr_pixel.cuh"
 #include "zr_rpt.cuh"       // ZR_PHASE
 #include "zr_schedule.h"

@@ -41,25 +41,6 @@ namespace
     // -------------------------------------------------------------------------------------------
     // PathTrace
     // -------------------------------------------------------------------------------------------
-    struct PrevHit { float alpha_lobe; float3 wi; float pdf; BSDF::LOBE lobe; };
-
-    ZR_D void MaybeSetCase2OrCase3(int pathVertex, float3 pos, float3 normal, float t, uint32_t ID, uint32_t meshIdx,
-        const BSDF::ShadingData& surface, const PrevHit& prevHit, const DirectLightingEstimate& ls, uint32_t seed_nee,
-        Reconnection& rc, float alpha_min)
-    {
-        const float alpha_lobe_direct = BSDF::LobeAlpha(surface, ls.lobe);
-        if (rc.Empty() && CanReconnect(prevHit.alpha_lobe, alpha_lobe_direct, prevHit.lobe, ls.lobe, alpha_min))
-        {
-            rc.SetCase2(pathVertex, pos, t, normal, ID, meshIdx, prevHit.wi, prevHit.lobe, prevHit.pdf, ls.wi, ls.lobe,
-                ls.pdf_solidAngle, ls.lt, ls.pdf_light, ls.le, seed_nee, ls.dwdA);
-        }
-        if (rc.Empty() && (alpha_lobe_direct >= alpha_min))
-        {
-            rc.SetCase3(pathVertex + 1, ls.pos, ls.lt, ls.lobe, ls.ID, ls.le, ls.normal, ls.pdf_solidAngle, ls.pdf_light,
-                ls.dwdA, ls.wi, ls.twoSided, seed_nee);
-        }
-    }
-
 #ifndef ZR_PT_THREADS
 #define ZR_PT_THREADS 1024
 #endif
@@ -907,6 +888,7 @@ struct zr_indirect_pass
     // spatial reuse: per-case shift queues + TMA-staged streaming merge (rpt_spatial.cu) by default, the fused kernel on request
     zr::SpatialQueued spatialQueued;
     zr::TemporalQueued temporalQueued;
+    zr::WavefrontPT wavefront;
     int execution = ZR_RPT_EXEC_QUEUED;
     zr_status UpdateSchedules()
     {
@@ -936,6 +918,7 @@ struct zr_indirect_pass
         schedPathTrace.Release(); schedTemporal.Release(); schedSpatial.Release();
         spatialQueued.Release();
         temporalQueued.Release();
+        wavefront.Release();
         if (d_target) cudaFree(d_target); if (d_final) cudaFree(d_final); if (d_neighbor) cudaFree(d_neighbor);
         d_target = d_final = nullptr; d_neighbor = nullptr;
     }
@@ -956,6 +939,8 @@ struct zr_indirect_pass
         zr_status st = spatialQueued.Resize(w, h, d_res[0], d_res[1]);
         if (st != ZR_OK) return st;
         st = temporalQueued.Resize(w, h);
+        if (st != ZR_OK) return st;
+        st = wavefront.Resize(w, h);
         if (st != ZR_OK) return st;
         return ResetTemporal();
     }
@@ -1050,7 +1035,14 @@ struct zr_indirect_pass
         const uint32_t rows = prm.rowEnd - prm.rowBegin;
 
         int cur = currTemporalIdx;
+        if (execution == ZR_RPT_EXEC_WAVEFRONT && !d_costMap)
         {
+            st = wavefront.Run(in->scene->dev, f, prm, d_res[cur], d_target, d_final, stream);
+            if (st != ZR_OK) return st;
+        }
+        else
+        {
+            // the lock-step kernel (also while a cost map is being measured: it accounts the cycles of its blocks per tile)
             const uint32_t dispX = (width + 15) / 16, dispY = (height + 7) / 8;
             ZR_PROF("k_pathtrace", stream);
             k_pathtrace<<<schedPathTrace.count, ZR_PT_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_target, d_final, dispX, dispY,
@@ -1059,7 +1051,7 @@ struct zr_indirect_pass
         }
         if (doTemporal && lastStage != ZR_RPT_STAGE_PATHTRACE)
         {
-            if (execution == ZR_RPT_EXEC_QUEUED)
+            if (execution != ZR_RPT_EXEC_FUSED)
             {
                 st = temporalQueued.Run(spatialQueued, in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_target, d_final, stream);
                 if (st != ZR_OK) return st;
@@ -1096,7 +1088,7 @@ struct zr_indirect_pass
                     k_sort<<<dim3(sx, ty1 - ty0), 256, 0, stream>>>(f, 3, 1u, rin, nullptr, d_neighbor, d_threadMap[1], sx, sy, ty0);
                     ZR_LAUNCH_CHECK();
                 }
-                if (execution == ZR_RPT_EXEC_QUEUED)
+                if (execution != ZR_RPT_EXEC_FUSED)
                 {
                     st = spatialQueued.Run(in->scene->dev, f, prm, rin, rout, d_target, d_final, d_neighbor, d_threadMap[1], stream);
                     if (st != ZR_OK) return st;
@@ -1131,7 +1123,7 @@ extern "C"
         zr_indirect_pass* p = new zr_indirect_pass();
         zr_indirect_pass::Defaults(&p->params);
         if (const char* e = getenv("ZETARAY_B200_SPATIAL"))      // A/B switch for measurements: "fused" | "queued"
-            p->execution = std::string(e) == "fused" ? ZR_RPT_EXEC_FUSED : ZR_RPT_EXEC_QUEUED;
+            p->execution = std::string(e) == "fused" ? ZR_RPT_EXEC_FUSED : (std::string(e) == "wavefront" ? ZR_RPT_EXEC_WAVEFRONT : ZR_RPT_EXEC_QUEUED);
         zr_status s = p->OnWindowResized(width, height);
         if (s != ZR_OK) { p->Release(); delete p; return s; }
         *out = p;
@@ -1228,7 +1220,7 @@ extern "C"
     }
     zr_status zr_indirect_pass_set_execution(zr_indirect_pass* p, zr_indirect_execution mode)
     {
-        if (!p || (mode != ZR_RPT_EXEC_FUSED && mode != ZR_RPT_EXEC_QUEUED)) { zr::set_error("zr_indirect_pass_set_execution: bad args"); return ZR_ERR_INVALID_ARG; }
+        if (!p || (mode != ZR_RPT_EXEC_FUSED && mode != ZR_RPT_EXEC_QUEUED && mode != ZR_RPT_EXEC_WAVEFRONT)) { zr::set_error("zr_indirect_pass_set_execution: bad args"); return ZR_ERR_INVALID_ARG; }
         p->execution = (int)mode;
         return ZR_OK;
     }

@@ -94,6 +94,30 @@ namespace
         if (t == 0 && blockIdx.x < numTiles)
             issue(blockIdx.x, 0);
 
+        // Software pipeline across tiles: the first-level loads of a tile (flag word, neighbour code, target; thread-map entry of the
+        // thread position this thread plays in phase 2) are issued one iteration ahead and carried in registers, so that at the top of
+        // an iteration the dependent gathers (neighbour record, shift results) go out at once.
+        uint32_t pfFlags = 0xff, pfNb = 0xffff, pfMap = 0x8000;
+        float4 pfTg = f4(0, 0, 0, 0);
+        auto prefetch = [&](uint32_t tile)
+        {
+            const uint32_t tX = tile % tilesX, tY = tileRow0 + tile / tilesX;
+            const uint32_t px = tX * 32 + lane, py = tY * 32 + warp;
+            pfFlags = 0xff; pfNb = 0xffff; pfMap = 0x8000;      // invalid | emissive, no neighbour, thread position without a pixel
+            if (px < f.W && py < f.H && py >= prm.rowBegin && py < prm.rowEnd)
+            {
+                const size_t i = (size_t)py * f.W + px;
+                pfFlags = __ldg(&f.core[i].w) & 0xff;
+                pfNb = __ldg(&neighbor[i]);
+                pfTg = __ldg(&target[i]);
+            }
+            const uint32_t sx = tX * 32 + (warp & 3) * 8 + (lane & 7), sy = tY * 32 + (warp >> 2) * 4 + (lane >> 3);
+            if (sx < f.W && sy < f.H)
+                pfMap = prm.sortSpatial ? __ldg(&threadMap[(size_t)sy * f.W + sx]) : (31u | (31u << 7));
+        };
+        if (blockIdx.x < numTiles)
+            prefetch(blockIdx.x);
+
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, it++)
         {
@@ -109,22 +133,23 @@ namespace
             const int x = (int)(tileX * 32 + lane), y = (int)(tileY * 32 + warp);
             const bool inImage = (uint32_t)x < f.W && (uint32_t)y < f.H;
             const size_t idx = inImage ? (size_t)y * f.W + x : 0;
-            bool act = inImage && y >= (int)prm.rowBegin && y < (int)prm.rowEnd;
-            if (act)
+            bool act = false;
             {
-                const GFlags flags = FlagsAt(f.core, f.W, x, y);
-                if (flags.invalid || flags.emissive) act = false;
+                const GFlags flags = DecodeFlags(pfFlags);
+                act = !(flags.invalid || flags.emissive);       // out-of-strip / out-of-image pixels were prefetched as invalid
             }
             int nx = 0, ny = 0;
             bool hasN = false;
-            float4 tg = f4(0, 0, 0, 0);
+            const float4 tg = pfTg;
+            const uint32_t mapEnc = pfMap;
             uint4 sh0 = make_uint4(0, 0, 0, 0);
             float2 sh1 = f2(0, 0);
             uint4 n0 = make_uint4(Reconnection::EMPTY, 0, 0, 0), n1 = make_uint4(0, 0, 0, 0);
             if (act)
             {
-                tg = __ldg(&target[idx]);
-                hasN = NeighborOf(f, neighbor, x, y, nx, ny);
+                const uint32_t ox = pfNb & 0xff, oy = pfNb >> 8;
+                hasN = ox != 0xff;
+                nx = (int)ox - 32 + x; ny = (int)oy - 32 + y;
                 if (hasN)
                 {
                     const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
@@ -134,6 +159,8 @@ namespace
                     sh1 = __ldg(reinterpret_cast<const float2*>(&sp[1]));
                 }
             }
+            if (tile + gridDim.x < numTiles)
+                prefetch(tile + gridDim.x);
             sm.visited[t] = 0;
             tma::MbarWait(reinterpret_cast<uint64_t*>(&sm.bar[stage]), parity);
 
@@ -225,13 +252,9 @@ namespace
                 const int sx = (int)(tileX * 32 + (warp & 3) * 8 + (lane & 7)), sy = (int)(tileY * 32 + (warp >> 2) * 4 + (lane >> 3));
                 bool on = (uint32_t)sx < f.W && (uint32_t)sy < f.H;
                 int lx = sx - (int)(tileX * 32), ly = sy - (int)(tileY * 32);
-                if (on && prm.sortSpatial)
-                {
-                    const uint16_t enc = __ldg(&threadMap[(size_t)sy * f.W + sx]);
-                    if (enc & (1u << 15)) on = false;
-                    lx += (int)(enc & 0x3f) - 31;
-                    ly += (int)((enc >> 7) & 0x3f) - 31;
-                }
+                if (mapEnc & (1u << 15)) on = false;        // error bit (or a position outside the image: prefetched as such)
+                lx += (int)(mapEnc & 0x3f) - 31;
+                ly += (int)((mapEnc >> 7) & 0x3f) - 31;
                 if (on && ((uint32_t)lx >= 32u || (uint32_t)ly >= 32u)) on = false;      // cannot happen: the sort permutes within a tile
                 const uint32_t lp = on ? (uint32_t)(ly * 32 + lx) : 0;
                 const float v0 = on ? sm.val[0][lp] : 0.0f, v1 = on ? sm.val[1][lp] : 0.0f;

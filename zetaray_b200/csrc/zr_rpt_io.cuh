@@ -119,5 +119,25 @@ namespace
         rc.x_k_in_motion = rc.x_k_in_motion || dot(dScale, dScale) > 0;
     }
 
+    // ---- path generation helpers shared by the fused (rpt.cu) and the wavefront (rpt_wavefront.cu) kernels ----
+    struct PrevHit { float alpha_lobe; float3 wi; float pdf; BSDF::LOBE lobe; };
+
+    ZR_D void MaybeSetCase2OrCase3(int pathVertex, float3 pos, float3 normal, float t, uint32_t ID, uint32_t meshIdx,
+        const BSDF::ShadingData& surface, const PrevHit& prevHit, const DirectLightingEstimate& ls, uint32_t seed_nee,
+        Reconnection& rc, float alpha_min)
+    {
+        const float alpha_lobe_direct = BSDF::LobeAlpha(surface, ls.lobe);
+        if (rc.Empty() && CanReconnect(prevHit.alpha_lobe, alpha_lobe_direct, prevHit.lobe, ls.lobe, alpha_min))
+        {
+            rc.SetCase2(pathVertex, pos, t, normal, ID, meshIdx, prevHit.wi, prevHit.lobe, prevHit.pdf, ls.wi, ls.lobe,
+                ls.pdf_solidAngle, ls.lt, ls.pdf_light, ls.le, seed_nee, ls.dwdA);
+        }
+        if (rc.Empty() && (alpha_lobe_direct >= alpha_min))
+        {
+            rc.SetCase3(pathVertex + 1, ls.pos, ls.lt, ls.lobe, ls.ID, ls.le, ls.normal, ls.pdf_solidAngle, ls.pdf_light,
+                ls.dwdA, ls.wi, ls.twoSided, seed_nee);
+        }
+    }
+
 }
 } // namespace zr

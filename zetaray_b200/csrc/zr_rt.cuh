@@ -85,11 +85,6 @@ ZR_D HitEmissive FindClosestEmissive(const SceneDev& sc, float3 pos, float3 norm
     ret.hit = false;
     ret.emissiveTriIdx = UINT32_MAX_;
     ret.t = 0; ret.geoIdx = 0; ret.primIdx = 0; ret.bary = f2(0, 0); ret.lightPos = f3(0);
-#ifdef ZR_SKIP_ZERO_WI_QUERIES     /* experiment switch (not the default): stop zero-direction rays at their source -- a failed BSDF sample
-                                      (pdf 0, wi = 0) on a transmissive surface is the one place they come from */
-    if (wi.x == 0.0f && wi.y == 0.0f && wi.z == 0.0f)
-        return ret;
-#endif
     bool wiBackface = dot(normal, wi) <= 0;
     if (wiBackface)
     {

@@ -110,19 +110,9 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
         // qlo[0] = n2.xy, qlo[1] = n2.zw, qlo[2] = n3.xy, qhi[0] = n3.zw, qhi[1] = n4.xy, qhi[2] = n4.zw
         const uint32_t q[12] = { n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w, n4.x, n4.y, n4.z, n4.w };
         // children are visited far-to-near pushed, so near ones pop first
-#ifdef ZR_TRAVERSE_REGISTER_ORDER
-        // Experimental ordering (not the default; built as a variant for A/B): up to four surviving
-        // children are kept in scalar registers and ordered by a 5-comparator network; a fifth and later child (1-6 % of the node
-        // visits) goes straight onto the stack. No dynamically indexed arrays, hence no local memory. The result of a query does
-        // not depend on the visiting order (hit rule), only its cost does.
-        float ct0 = -FLT_MAX_, ct1 = -FLT_MAX_, ct2 = -FLT_MAX_, ct3 = -FLT_MAX_;
-        uint32_t cn0 = 0, cn1 = 0, cn2 = 0, cn3 = 0;
-        int nPush = 0;
-#else
         float childT[8];
         uint32_t childNode[8];
         int nPush = 0;
-#endif
 #pragma unroll
         for (int c = 0; c < 8; c++)
         {
@@ -143,19 +133,9 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
             if (!(tn <= tf)) continue;
             if (meta & 0x20u)
             {
-#ifdef ZR_TRAVERSE_REGISTER_ORDER
-                const uint32_t cn = childBase + (meta & 0x1fu);
-                if (nPush == 0) { ct0 = tn; cn0 = cn; }
-                else if (nPush == 1) { ct1 = tn; cn1 = cn; }
-                else if (nPush == 2) { ct2 = tn; cn2 = cn; }
-                else if (nPush == 3) { ct3 = tn; cn3 = cn; }
-                else if (sp < BVH_STACK_ENTRIES) stack[sp++] = cn;
-                nPush++;
-#else
                 childT[nPush] = tn;
                 childNode[nPush] = childBase + (meta & 0x1fu);
                 nPush++;
-#endif
             }
             else
             {
@@ -188,16 +168,6 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
                 }
             }
         }
-#ifdef ZR_TRAVERSE_REGISTER_ORDER
-        // descending by entry distance (empty slots hold -FLT_MAX and sink to the end), then push far-to-near
-#define ZR_CE(ta, na, tb, nb) { const bool sw = tb > ta; const float tt = sw ? tb : ta; const uint32_t nn = sw ? nb : na; tb = sw ? ta : tb; nb = sw ? na : nb; ta = tt; na = nn; }
-        ZR_CE(ct0, cn0, ct1, cn1) ZR_CE(ct2, cn2, ct3, cn3) ZR_CE(ct0, cn0, ct2, cn2) ZR_CE(ct1, cn1, ct3, cn3) ZR_CE(ct1, cn1, ct2, cn2)
-#undef ZR_CE
-        if (nPush > 0 && sp < BVH_STACK_ENTRIES) stack[sp++] = cn0;
-        if (nPush > 1 && sp < BVH_STACK_ENTRIES) stack[sp++] = cn1;
-        if (nPush > 2 && sp < BVH_STACK_ENTRIES) stack[sp++] = cn2;
-        if (nPush > 3 && sp < BVH_STACK_ENTRIES) stack[sp++] = cn3;
-#else
         // push far-to-near (insertion sort, <= 8 entries)
         for (int i = 1; i < nPush; i++)
         {
@@ -208,7 +178,6 @@ ZR_F1 RayHit Traverse(const SceneDev& sc, float3 o, float3 d, float tmin, float 
         }
         for (int i = 0; i < nPush; i++)
             if (sp < BVH_STACK_ENTRIES) stack[sp++] = childNode[i];      // never drops: scene creation checked BvhBuild::maxStack
-#endif
     }
     return best;
 }
