@@ -104,25 +104,17 @@ extern "C"
         return f3(half_lo(p.x), half_hi(p.x), half_lo(p.y));
     }
 
-    // g_samLinearClamp SampleLevel on an RGBA16F image
-    static float3 SampleBilinearClamp(const uint2* img, int W, int H, float2 uv)
-    {
-        float px = uv.x * (float)W - 0.5f;
-        float py = uv.y * (float)H - 0.5f;
-        float fx0 = floorf(px), fy0 = floorf(py);
-        float fx = px - fx0, fy = py - fy0;
-        int x0 = (int)fx0, y0 = (int)fy0;
-        float3 c00 = LoadHalf4(img, W, H, x0, y0), c10 = LoadHalf4(img, W, H, x0 + 1, y0);
-        float3 c01 = LoadHalf4(img, W, H, x0, y0 + 1), c11 = LoadHalf4(img, W, H, x0 + 1, y0 + 1);
-        float3 top = c00 * (1.0f - fx) + c10 * fx;
-        float3 bot = c01 * (1.0f - fx) + c11 * fx;
-        return top * (1.0f - fy) + bot * fy;
-    }
-
+    // Common::SampleTextureCatmullRom (Common.hlsli:65-102): nine g_samLinearClamp SampleLevel taps on the RGBA16F history. By
+    // construction every tap lies either at a texel centre (texPos0 = texPos1 - 1, texPos3 = texPos1 + 2: the sampler returns that texel)
+    // or between the two middle texels at the fraction offset12 (texPos12 = texPos1 + offset12: the sampler's bilinear weight). That is
+    // what is restated here -- centre taps are the texel, the 1|2 taps blend the two middle texels with the float fraction offset12 (the
+    // hardware quantises it to 8 fractional bits; not modelled) -- instead of pushing the positions through uv = pos / texSize and back,
+    // whose rounding would turn exact texel centres into 4-texel blends with weights of 1e-7. Clamp addressing on the texel indices.
     static float3 SampleTextureCatmullRom(const uint2* img, int W, int H, float2 uv, float2 texSize)
     {
         float2 samplePos = uv * texSize;
-        float2 texPos1 = f2(floorf(samplePos.x - 0.5f) + 0.5f, floorf(samplePos.y - 0.5f) + 0.5f);
+        const float fx1 = floorf(samplePos.x - 0.5f), fy1 = floorf(samplePos.y - 0.5f);
+        float2 texPos1 = f2(fx1 + 0.5f, fy1 + 0.5f);
         float2 f = samplePos - texPos1;
         auto w0f = [](float f) { return f * (-0.5f + f * (1.0f - 0.5f * f)); };
         auto w1f = [](float f) { return 1.0f + f * f * (-2.5f + 1.5f * f); };
@@ -132,22 +124,20 @@ extern "C"
         float2 w2 = f2(w2f(f.x), w2f(f.y)), w3 = f2(w3f(f.x), w3f(f.y));
         float2 w12 = w1 + w2;
         float2 offset12 = w2 / (w1 + w2);
-        float2 texPos0 = texPos1 - 1.0f;
-        float2 texPos3 = texPos1 + 2.0f;
-        float2 texPos12 = texPos1 + offset12;
-        texPos0 = texPos0 / texSize;
-        texPos3 = texPos3 / texSize;
-        texPos12 = texPos12 / texSize;
+        const int ix = (int)fx1, iy = (int)fy1;       // texel under texPos1
+        auto T = [&](int i, int j) { return LoadHalf4(img, W, H, ix + i, iy + j); };
+        auto lerp = [](float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; };
+        const float ox = offset12.x, oy = offset12.y;
         float3 result = f3(0);
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos0.y)) * w0.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos0.y)) * w12.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos0.y)) * w3.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos12.y)) * w0.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos12.y)) * w12.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos12.y)) * w3.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos3.y)) * w0.x * w3.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos3.y)) * w12.x * w3.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos3.y)) * w3.x * w3.y;
+        result += T(-1, -1) * w0.x * w0.y;
+        result += lerp(T(0, -1), T(1, -1), ox) * w12.x * w0.y;
+        result += T(2, -1) * w3.x * w0.y;
+        result += lerp(T(-1, 0), T(-1, 1), oy) * w0.x * w12.y;
+        result += lerp(lerp(T(0, 0), T(1, 0), ox), lerp(T(0, 1), T(1, 1), ox), oy) * w12.x * w12.y;
+        result += lerp(T(2, 0), T(2, 1), oy) * w3.x * w12.y;
+        result += T(-1, 2) * w0.x * w3.y;
+        result += lerp(T(0, 2), T(1, 2), ox) * w12.x * w3.y;
+        result += T(2, 2) * w3.x * w3.y;
         return result;
     }
 

@@ -7,6 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libhostsim.so")
 SO_DI = os.path.join(HERE, "libhostsim_di.so")
+SO_IO = os.path.join(HERE, "libhostsim_io.so")
 _CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "zetaray_b200", "csrc")
 _INC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "include")
 
@@ -29,6 +30,7 @@ def _build(src, so, force, defines=()):
 
 def build(force=False):
     _build(os.path.join(HERE, "hostsim_di.cpp"), SO_DI, force)
+    _build(os.path.join(HERE, "hostsim_io.cpp"), SO_IO, force)
     return _build(os.path.join(HERE, "hostsim.cpp"), SO, force)
 
 
@@ -43,3 +45,10 @@ def load():
 def load_di():
     build()
     return C.CDLL(SO_DI)
+
+
+def load_io():
+    build()
+    lib = C.CDLL(SO_IO)
+    lib.hostsim_oct32_round_trip.restype = C.c_uint64
+    return lib

@@ -496,3 +496,58 @@ def test_restir_di_pairwise_mis(which):
             picked_neighbor += a[3] != int(res[y * w + x]["lightIdx"]) or a[0] != int(res[y * w + x]["bary"])
     print(which, "shaded", shaded, "result differs from the centre sample", picked_neighbor)
     assert shaded > 800 and picked_neighbor > 100
+
+
+def test_oct32_round_trip():
+    """The premise of CopyToNextFrame's short cut (zr_rpt_io.cuh): EncodeOct32u(DecodeOct32(c)) == c for EVERY 32-bit code whose two
+    UNORM16 halves lie strictly inside (0, 0xffff) -- all 2^32 codes are tried; the codes that do change are aliases on the fold
+    lines of the octahedron (one of their halves is 0 or 0xffff), which the short cut does not take."""
+    import os
+    io = hostsim.load_io()
+    boundary = C.c_uint64(0)
+    interior_changed = io.hostsim_oct32_round_trip(os.cpu_count() or 1, C.byref(boundary))
+    assert interior_changed == 0
+    assert 0 < boundary.value <= 4 * 65536
+
+
+@pytest.mark.parametrize("which", ["glossy", "glass", "tunnel"])
+def test_copy_to_next_frame_short_cut(which):
+    """CopyToNextFrame (the "reservoir did not change" copy of the merge kernels) moves the reconnection words of a record without
+    decoding them when RecordSurvivesRoundTrip says so; the bytes must equal Reservoir::Write(Reservoir::Load(record)) -- on every
+    record of oracle frame sequences, and on the same records with fold-line directions, NaN / inf radiance halves and garbage in the
+    words their case does not store (those take the slow path or are zeroed)."""
+    from tests import scene_util, rpt_util
+    io = hostsim.load_io()
+    w, h = 128, 72
+    R = rpt_util.OracleRenderer(scene_util.SCENES[which](), w, h)
+    cam = scene_util.CAMERAS.get(which)
+    seq = rpt_util.FrameSequence(w, h, cam_path=(lambda f: cam) if cam else None)
+    rng = np.random.default_rng(5)
+    fast_total = 0
+    for fr in range(3):
+        fc = seq.next()
+        R.gbuffer(fc); R.rpt(fc)
+        res = np.ascontiguousarray(R.curr_reservoirs())
+        n = len(res)
+        variants = [res]
+        v = res.copy()          # hostile variant: boundary directions, special halves, garbage in unused words
+        pick = rng.random(n)
+        v["w_k"] = np.where(pick < 0.2, v["w_k"] & np.uint32(0xffff0000), v["w_k"])
+        v["w_k"] = np.where((pick >= 0.2) & (pick < 0.4), v["w_k"] | np.uint32(0xffff0000), v["w_k"])
+        v["L_rg"] = np.where(pick > 0.9, np.uint32(0x7e017c00), v["L_rg"])       # {inf, NaN}
+        v["L_b"] = np.where(pick > 0.95, np.uint32(0xfc01), v["L_b"])
+        v["L_b"] = v["L_b"] | np.where(pick < 0.1, np.uint32(0xabcd0000), np.uint32(0))
+        for f in ("dwdA", "lightPdf"):
+            v[f] = np.where(pick < 0.5, v[f], rng.random(n).astype(np.float32))
+        for f in ("seed_nee", "meshIdx"):
+            v[f] = np.where(pick < 0.5, v[f], rng.integers(0, 2 ** 32, n, dtype=np.uint32))
+        variants.append(v)
+        for recs in variants:
+            recs = np.ascontiguousarray(recs)
+            for m_max in (0, 4, 10):
+                out = np.zeros(n, dtype=rpt_util.RES); ref = np.zeros(n, dtype=rpt_util.RES)
+                fast = C.c_uint32(0)
+                io.hostsim_probe_copy_to_next_frame(ptr(recs), n, m_max, ptr(out), ptr(ref), C.byref(fast))
+                assert out.tobytes() == ref.tobytes(), (which, fr, m_max)
+                fast_total += fast.value
+    assert fast_total > 1000        # the short cut is the common case on real records

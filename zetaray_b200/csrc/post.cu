@@ -204,24 +204,18 @@ namespace
         return f3(half_lo(p.x), half_hi(p.x), half_lo(p.y));
     }
 
-    ZR_D float3 SampleBilinearClamp(const uint2* __restrict__ img, int W, int H, float2 uv)
-    {
-        const float px = uv.x * (float)W - 0.5f;
-        const float py = uv.y * (float)H - 0.5f;
-        const float fx0 = floorf(px), fy0 = floorf(py);
-        const float fx = px - fx0, fy = py - fy0;
-        const int x0 = (int)fx0, y0 = (int)fy0;
-        const float3 c00 = LoadHalf4(img, W, H, x0, y0), c10 = LoadHalf4(img, W, H, x0 + 1, y0);
-        const float3 c01 = LoadHalf4(img, W, H, x0, y0 + 1), c11 = LoadHalf4(img, W, H, x0 + 1, y0 + 1);
-        const float3 top = c00 * (1.0f - fx) + c10 * fx;
-        const float3 bot = c01 * (1.0f - fx) + c11 * fx;
-        return top * (1.0f - fy) + bot * fy;
-    }
+    // Common::SampleTextureCatmullRom (Common.hlsli:65-102) on the RGBA16F history. The reference's nine bilinear taps lie at texel
+    // centres (texPos0, texPos3: the sampler returns the texel) or between the two middle texels at the fraction offset12 (texPos12), so
+    // they cover a 4 x 4 texel footprint: 16 loads (clamp addressing), the 1|2 taps blended with offset12, then the nine weighted taps
+    // in the reference's order (oracle/orc_post.cpp restates exactly this).
+    ZR_D float3 HalfRGB(uint2 p) { return f3(half_lo(p.x), half_hi(p.x), half_lo(p.y)); }
+    ZR_D float3 Lerp3(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
 
     ZR_D float3 SampleTextureCatmullRom(const uint2* __restrict__ img, int W, int H, float2 uv, float2 texSize)
     {
         const float2 samplePos = uv * texSize;
-        const float2 texPos1 = f2(floorf(samplePos.x - 0.5f) + 0.5f, floorf(samplePos.y - 0.5f) + 0.5f);
+        const float fx1 = floorf(samplePos.x - 0.5f), fy1 = floorf(samplePos.y - 0.5f);
+        const float2 texPos1 = f2(fx1 + 0.5f, fy1 + 0.5f);
         const float2 f = samplePos - texPos1;
         const float2 w0 = f2(f.x * (-0.5f + f.x * (1.0f - 0.5f * f.x)), f.y * (-0.5f + f.y * (1.0f - 0.5f * f.y)));
         const float2 w1 = f2(1.0f + f.x * f.x * (-2.5f + 1.5f * f.x), 1.0f + f.y * f.y * (-2.5f + 1.5f * f.y));
@@ -229,22 +223,32 @@ namespace
         const float2 w3 = f2(f.x * f.x * (-0.5f + 0.5f * f.x), f.y * f.y * (-0.5f + 0.5f * f.y));
         const float2 w12 = w1 + w2;
         const float2 offset12 = w2 / (w1 + w2);
-        float2 texPos0 = texPos1 - 1.0f;
-        float2 texPos3 = texPos1 + 2.0f;
-        float2 texPos12 = texPos1 + offset12;
-        texPos0 = texPos0 / texSize;
-        texPos3 = texPos3 / texSize;
-        texPos12 = texPos12 / texSize;
+        const int ix = (int)fx1, iy = (int)fy1;
+        int cx[4]; size_t row[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            const int tx = ix - 1 + k, ty = iy - 1 + k;
+            cx[k] = tx < 0 ? 0 : (tx > W - 1 ? W - 1 : tx);
+            row[k] = (size_t)(ty < 0 ? 0 : (ty > H - 1 ? H - 1 : ty)) * W;
+        }
+        uint2 t[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                t[j][i] = __ldg(&img[row[j] + cx[i]]);
+        const float ox = offset12.x, oy = offset12.y;
         float3 result = f3(0);
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos0.y)) * w0.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos0.y)) * w12.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos0.y)) * w3.x * w0.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos12.y)) * w0.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos12.y)) * w12.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos12.y)) * w3.x * w12.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos0.x, texPos3.y)) * w0.x * w3.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos12.x, texPos3.y)) * w12.x * w3.y;
-        result += SampleBilinearClamp(img, W, H, f2(texPos3.x, texPos3.y)) * w3.x * w3.y;
+        result += HalfRGB(t[0][0]) * w0.x * w0.y;
+        result += Lerp3(HalfRGB(t[0][1]), HalfRGB(t[0][2]), ox) * w12.x * w0.y;
+        result += HalfRGB(t[0][3]) * w3.x * w0.y;
+        result += Lerp3(HalfRGB(t[1][0]), HalfRGB(t[2][0]), oy) * w0.x * w12.y;
+        result += Lerp3(Lerp3(HalfRGB(t[1][1]), HalfRGB(t[1][2]), ox), Lerp3(HalfRGB(t[2][1]), HalfRGB(t[2][2]), ox), oy) * w12.x * w12.y;
+        result += Lerp3(HalfRGB(t[1][3]), HalfRGB(t[2][3]), oy) * w3.x * w12.y;
+        result += HalfRGB(t[3][0]) * w0.x * w3.y;
+        result += Lerp3(HalfRGB(t[3][1]), HalfRGB(t[3][2]), ox) * w12.x * w3.y;
+        result += HalfRGB(t[3][3]) * w3.x * w3.y;
         return result;
     }
 
@@ -260,13 +264,39 @@ namespace
         return histSample;
     }
 
+    // TAA.hlsl:29-189. A block owns 32 x 8 pixels. The 3 x 3 neighbourhood is staged once per tile: every pixel of the 34 x 10 halo'd tile is
+    // clamped to >= 0 and gets its tone-mapping weight 1 / (1 + luminance) ONCE (the per-tap form costs eight IEEE divisions per output
+    // pixel), depth beside it; the taps then run out of shared memory in the reference's order with the reference's arithmetic.
     __global__ void __launch_bounds__(256) k_taa(const float* __restrict__ depthPlane,
         const uint2* __restrict__ motionEmissive, const float4* __restrict__ signal,
         const uint2* __restrict__ prevOut, uint2* __restrict__ out, PostParams p)
     {
-        const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-        const int y = (int)p.rowBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
+        constexpr int SW = 34, SH = 10;
+        __shared__ float4 s_c[SH * SW];     // {max(rgb, 0), 1 / (1 + luminance)}
+        __shared__ float s_d[SH * SW];
         const int W = (int)p.W, H = (int)p.H;
+        const int bx = blockIdx.x * 32, by = (int)p.rowBegin + blockIdx.y * 8;
+        if (p.temporalIsValid)
+        {
+            for (int e = (int)threadIdx.x; e < SW * SH; e += 256)
+            {
+                const int gx = bx + e % SW - 1, gy = by + e / SW - 1;
+                float4 v = f4(0, 0, 0, 0);
+                float d = FLT_MAX_;
+                if (gx >= 0 && gy >= 0 && gx < W && gy < H)
+                {
+                    const size_t n = (size_t)gy * W + gx;
+                    const float4 c4 = __ldg(&signal[n]);
+                    const float3 c = max3(f3(c4.x, c4.y, c4.z), 0.0f);
+                    v = f4(c.x, c.y, c.z, 1.0f / (1.0f + Math::Luminance(c)));
+                    d = __ldg(&depthPlane[n]);
+                }
+                s_c[e] = v; s_d[e] = d;
+            }
+            __syncthreads();
+        }
+        const int lx = (int)(threadIdx.x & 31), ly = (int)(threadIdx.x >> 5);
+        const int x = bx + lx, y = by + ly;
         if (x >= W || y >= (int)p.rowEnd) return;
         const size_t idx = (size_t)y * W + x;
         const float depth = __ldg(&depthPlane[idx]);
@@ -293,16 +323,16 @@ namespace
                 if (i == 0 && j == 0) continue;
                 const int nx = x + i, ny = y + j;
                 if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
-                const size_t n = (size_t)ny * W + nx;
-                const float4 c4 = __ldg(&signal[n]);
-                const float3 neighborColor = max3(f3(c4.x, c4.y, c4.z), 0.0f);
+                const int sidx = (ly + 1 + j) * SW + lx + 1 + i;
+                const float4 c4 = s_c[sidx];
+                const float3 neighborColor = f3(c4.x, c4.y, c4.z);
                 float weight = Mitchell1D((float)i, 0.33f, 0.33f) * Mitchell1D((float)j, 0.33f, 0.33f);
-                weight *= 1.0f / (1.0f + Math::Luminance(neighborColor));
+                weight *= c4.w;
                 reconstructed += neighborColor * weight;
                 weightSum += weight;
                 firstMoment += neighborColor;
                 secondMoment += neighborColor * neighborColor;
-                const float neighborDepth = __ldg(&depthPlane[n]);
+                const float neighborDepth = s_d[sidx];
                 if (neighborDepth < closestDepth) { closestDepth = neighborDepth; cdx = i; cdy = j; }
                 numNeighbors += 1;
             }

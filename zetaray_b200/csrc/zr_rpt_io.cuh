@@ -53,9 +53,34 @@ namespace
         }
     }
 
+    // Reservoir::Write(Reservoir::Load(rec)) leaves the reconnection words of a record unchanged whenever its two lossy fields
+    // survive the round trip: the octahedral direction (EncodeOct32u(DecodeOct32(c)) == c for every code c whose two UNORM16
+    // halves are not 0 / 0xffff -- checked for all 2^32 codes by tests/test_device_source_vs_oracle.py::test_oct32_round_trip;
+    // the 131071 exceptions are aliases on the fold lines of the octahedron) and the three radiance halves (half -> float -> half
+    // is the identity except for NaN payloads). Everything else is moved bit for bit by Load_Reconnection / Write.
+    ZR_D bool RecordSurvivesRoundTrip(const zr_rpt_reservoir& in)
+    {
+        const uint32_t wx = in.w_k & 0xffff, wy = in.w_k >> 16;
+        const bool interior = wx != 0 && wx != 0xffff && wy != 0 && wy != 0xffff;
+        const uint32_t r = in.L_rg & 0x7fff, g = (in.L_rg >> 16) & 0x7fff, b = in.L_b & 0x7fff;
+        return interior && r <= 0x7c00 && g <= 0x7c00 && b <= 0x7c00;
+    }
+
     ZR_D void CopyToNextFrame(const zr_rpt_reservoir& in, zr_rpt_reservoir* __restrict__ outPtr, Reservoir r_curr, uint32_t M_max)
     {
-        if (!r_curr.rc.Empty())
+        if (!r_curr.rc.Empty() && RecordSurvivesRoundTrip(in))
+        {
+            // same bytes as the decode + encode below, without the octahedral / half conversions
+            zr_rpt_reservoir out = in;
+            out.meta = r_curr.PackMeta(M_max);
+            out.w_sum = Math::Sanitize(r_curr.w_sum);
+            out.W = Math::Sanitize(r_curr.W);
+            out.L_b = in.L_b & 0xffff;
+            if (r_curr.rc.IsCase1()) { out.lightPdf = 0; out.dwdA = 0; out.seed_nee = 0; }
+            else if (!r_curr.rc.IsCase2()) { out.dwdA = 0; out.seed_nee = 0; out.meshIdx = 0; }
+            StoreRecord(outPtr, out);
+        }
+        else if (!r_curr.rc.Empty())
         {
             r_curr.Load_Reconnection(in);
             zr_rpt_reservoir out;
