@@ -47,7 +47,8 @@ enum
 ZR_API const char* zr_last_error(void);
 /* Library/ABI version: (major << 16) | minor. */
 /* (major << 16) | minor; additions bump the minor. 1.1 added zr_bvh_build_host, zr_renderer_set_integrator,
- * zr_renderer_get_gi_pass, zr_renderer_apply_scene_settings and zr_gi_pass_set_method. */
+ * zr_renderer_get_gi_pass, zr_renderer_apply_scene_settings and zr_gi_pass_set_method; 1.2 the SVGF pass, zr_comm, the strip-sharded
+ * renderer (zr_renderer_set_shard) and zr_gi_pass_set_rows / set_halo_exchange. */
 ZR_API uint32_t zr_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -531,6 +532,10 @@ ZR_API zr_status zr_gi_pass_set_params(zr_gi_pass* p, const zr_gi_params* params
  * ReSTIR GI run on this pass object (both read cb_ReSTIR_GI in the reference); ReSTIR PT is zr_indirect_pass. */
 typedef enum zr_integrator { ZR_INTEGRATOR_PATH_TRACING = 0, ZR_INTEGRATOR_RESTIR_GI = 1, ZR_INTEGRATOR_RESTIR_PT = 2 } zr_integrator;
 ZR_API zr_status zr_gi_pass_set_method(zr_gi_pass* p, zr_integrator method);     /* default RESTIR_GI; a change drops the history */
+/* multi-GPU: rows [y0, y1) this rank owns; the hook runs once per frame on the reservoirs just written (next frame's temporal
+ * candidates, searched up to 16 px around the reprojected pixel) */
+ZR_API zr_status zr_gi_pass_set_rows(zr_gi_pass* p, uint32_t y0, uint32_t y1);
+ZR_API zr_status zr_gi_pass_set_halo_exchange(zr_gi_pass* p, zr_halo_exchange_fn fn, void* user);
 ZR_API zr_status zr_gi_pass_render(zr_gi_pass* p, const zr_frame_inputs* in, void* stream);
 ZR_API zr_status zr_gi_pass_get_output(zr_gi_pass* p, zr_gi_output id, zr_image2d* out);
 ZR_API void zr_gi_pass_destroy(zr_gi_pass* p);
@@ -637,7 +642,8 @@ ZR_API zr_status zr_renderer_render(zr_renderer* r, const zr_frame_constants* fr
 /* optional SVGF stage between Compositing and TAA (BASELINE config 3); *out_pass (may be NULL) receives the pass for set_params */
 ZR_API zr_status zr_renderer_set_denoiser(zr_renderer* r, int enable, zr_svgf_pass** out_pass);
 /* Strip-sharded frame: this renderer computes rows [bounds[rank], bounds[rank + 1]) only (bounds: multiples of 32 except the last;
- * ReSTIR PT integrator); halo bands move through `comm` at the four exchange points of a frame, the finished image is gathered on
+ * any integrator, without the SVGF stage); halo bands move through `comm` at the exchange points of a frame (ReSTIR PT: four, ReSTIR
+ * GI: three, path tracer: two), the finished image is gathered on
  * rank 0 (gather_output != 0). comm == NULL returns to the whole frame. History must be complete when the cut happens: render the
  * warm-up frames unsharded on every rank. */
 ZR_API zr_status zr_renderer_set_shard(zr_renderer* r, zr_comm* comm, const uint32_t* bounds, int gather_output);

@@ -880,14 +880,6 @@ namespace
                 for (int l = 0; l < 32; l++) v[l] = lanes[l].active ? lanes[l].r.w_sum * (lanes[l].rs.rc.Empty() ? 1.0f : 0.0f) : 0.0f;
                 float waveSum3 = WaveSum32(v);
                 float waveSumAcc = waveSum2 + waveSum3;
-                for (int l = 0; l < 32; l++)
-                {
-                    L& s = lanes[l];
-                    if (!s.active) continue;
-                    float waveAvgExclusive = (waveSum - lanes[l].r.w_sum) / 32.0f;   // still the first average
-                    // note: the first average used the pre-LoadWSum w_sum of this lane
-                    (void)waveAvgExclusive;
-                }
                 // The reference computes waveAvgExclusive once, before LoadWSum (Reconnect_StC.hlsl:221-222);
                 // keep each lane's value from that point.
                 float avgEx[32];

@@ -98,7 +98,7 @@ def _worker(rank, world, port, W, H, warm, frames, out_dir):
         dist.destroy_process_group()
 
 
-def _worker_native(rank, world, port, W, H, warm, frames, out_dir):
+def _worker_native(rank, world, port, W, H, warm, frames, out_dir, integrator="pt"):
     """The native path: zr_renderer_set_shard + zr_comm (NCCL issued from C++), two streams, against an unsharded renderer."""
     import torch
     import torch.distributed as dist
@@ -116,6 +116,8 @@ def _worker_native(rank, world, port, W, H, warm, frames, out_dir):
         scene = Scene(scene_util.glossy_cornell())
         A = Renderer(scene, W, H, two_streams=False)        # unsharded reference on this GPU
         B = Renderer(scene, W, H, two_streams=True)
+        if integrator == "gi":          # ReSTIR GI: zr_gi_pass_set_rows + its reservoir-halo hook (BASELINE config 4 runs this way)
+            A.SetMethod(Renderer.RESTIR_GI); B.SetMethod(Renderer.RESTIR_GI)
         comm = Comm.from_torch()
         seq = rpt_util.FrameSequence(W, H)
         for _ in range(warm):
@@ -130,7 +132,9 @@ def _worker_native(rank, world, port, W, H, warm, frames, out_dir):
             torch.cuda.synchronize()
             for name, get, dt, comps in (
                     ("direct final", lambda r: r.direct.GetOutput(0), np.float32, 4),
-                    ("indirect final", lambda r: r.indirect.GetOutput(0), np.float32, 4),
+                    ("indirect final", (lambda r: r.gi.GetOutput(0)) if integrator == "gi" else (lambda r: r.indirect.GetOutput(0)), np.float32, 4),
+                    ("indirect reservoirs", (lambda r: r.gi.GetOutput(1)) if integrator == "gi" else (lambda r: r.indirect.GetOutput(1)), np.uint32,
+                     12 if integrator == "gi" else 16),
                     ("direct reservoirs", lambda r: r.direct.GetOutput(1), np.uint32, 8),
                     ("composited", lambda r: r.compositing.GetOutput(), np.float32, 4),
                     ("taa", lambda r: r.taa.GetOutput(), np.uint16, 4)):
@@ -144,7 +148,7 @@ def _worker_native(rank, world, port, W, H, warm, frames, out_dir):
                 full_b = _rows(B.GetOutput(), np.uint16, 4, 0, H)
                 assert np.array_equal(full_a, full_b), "frame %d: image gathered on rank 0 differs from the unsharded one" % f
         sent, calls = comm.stats()
-        assert calls >= 4 * frames and sent > 0
+        assert calls >= (3 if integrator == "gi" else 4) * frames and sent > 0
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("%s" % plan.bounds)
     finally:
         dist.destroy_process_group()
@@ -157,6 +161,16 @@ def test_native_sharded_renderer_equals_unsharded(tmp_path, world):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     mp.spawn(_worker_native, args=(world, _free_port(), 416, 296, 3, 4, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / ("ok%d" % r)) for r in range(world))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_native_sharded_restir_gi_equals_unsharded(tmp_path, world):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    mp.spawn(_worker_native, args=(world, _free_port(), 416, 296, 3, 4, str(tmp_path), "gi"), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / ("ok%d" % r)) for r in range(world))
 
 

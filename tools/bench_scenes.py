@@ -6,6 +6,11 @@ Informational: bench.py's headline stays the metric's own configuration (Cornell
     python tools/bench_scenes.py tunnel      # C5: 3840x2160, ReSTIR PT 5 bounces, 2 spatial passes, ReSTIR DI
     python tools/bench_scenes.py cornell     # the headline workload through the same code, for comparison
 
+Under torchrun (WORLD_SIZE > 1) the frame is strip-sharded across the ranks through the native renderer (zr_renderer_set_shard + zr_comm,
+uniform strips), timed as the maximum over ranks, and rank 0 prints the line:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 tools/bench_scenes.py atrium 10
+
 Prints one JSON line: whole-frame ms (CUDA events, two streams), Mpaths/s, per-kernel ms (single-stream profiling pass),
 scene / BVH statistics and the host decisions the renderer made (presampling, LVG)."""
 import ctypes as C
@@ -17,7 +22,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 from zetaray_b200 import lib, check, procedural  # noqa: E402
-from zetaray_b200.passes import Scene, Renderer  # noqa: E402
+from zetaray_b200.passes import Scene, Renderer, Comm  # noqa: E402
 from zetaray_b200.camera import FrameSequence  # noqa: E402
 from zetaray_b200.scene import FlatScene  # noqa: E402
 
@@ -39,6 +44,11 @@ def main():
     detail = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     cfg = CONFIGS[name]
     w, h = cfg["res"]
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t0 = time.perf_counter()
     if name == "cornell":
         flat = FlatScene.load(os.path.join(ROOT, "tests", "golden", "cornell_emissive.npz"))
@@ -72,6 +82,45 @@ def main():
     for _ in range(5):
         r.Render(seq.next(), st)
     torch.cuda.synchronize()
+    if world > 1:
+        # every rank holds a complete history now; cut the frame into uniform strips and bring the sharded frame to steady state
+        from zetaray_b200.sharding import StripPlan
+        comm = Comm.from_torch()
+        plan = StripPlan.uniform(h, world)
+        r.SetShard(comm, plan.bounds, gather_output=True)
+        for _ in range(4):
+            r.Render(seq.next(), st)
+        torch.cuda.synchronize()
+        fcs = [seq.next() for _ in range(steps)]
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for fc in fcs:
+            r.Render(fc, st)
+        e1.record(stream)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        check(lib.zr_profile_enable(1))
+        n = 5
+        for _ in range(n):
+            r.Render(seq.next(), st)
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(8192)
+        check(lib.zr_profile_collect(buf, 8192)); check(lib.zr_profile_enable(0))
+        mine = {k: round(float(tt) / n, 4) for k, c, tt in (x.split(":") for x in buf.value.decode().split(";") if x)}
+        sums = [None] * world
+        dist.all_gather_object(sums, round(sum(mine.values()), 3))
+        sent, calls = comm.stats()
+        if rank == 0:
+            out.update({"n_gpus": world, "strips": plan.bounds, "ms_per_frame": round(ms, 3), "mpaths_per_s": round(w * h / (ms * 1e-3) / 1e6, 2),
+                        "kernels_ms_per_frame": dict(sorted(mine.items(), key=lambda kv: -kv[1])), "kernel_ms_per_frame_by_rank": sums,
+                        "halo_bytes_per_exchange_per_rank": sent // max(1, calls),
+                        "parallelism": "1 frame / %d uniform horizontal strips, 32-row halos by grouped NCCL send/recv from C++, image gathered on rank 0" % world})
+            print(json.dumps(out))
+        dist.destroy_process_group()
+        return
     l0 = lib.zr_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fcs = [seq.next() for _ in range(steps)]

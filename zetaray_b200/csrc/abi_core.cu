@@ -59,7 +59,7 @@ namespace zr
 extern "C"
 {
     const char* zr_last_error(void) { return zr::g_err; }
-    uint32_t zr_abi_version(void) { return (1u << 16) | 1u; }     // 1.1: + zr_bvh_build_host, zr_renderer_set_integrator / get_gi_pass / apply_scene_settings, zr_gi_pass_set_method
+    uint32_t zr_abi_version(void) { return (1u << 16) | 2u; }     // 1.2: + SVGF pass, zr_comm, sharded renderer, zr_gi_pass_set_rows / set_halo_exchange; 1.1: + zr_bvh_build_host, zr_renderer_set_integrator / get_gi_pass / apply_scene_settings, zr_gi_pass_set_method
     uint64_t zr_kernel_launch_count(void) { return zr::g_launches.load(); }
 
     zr_status zr_profile_enable(int on)

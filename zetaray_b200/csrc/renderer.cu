@@ -54,6 +54,16 @@ struct zr_renderer
         if (s != ZR_OK) r->hookStatus = s;
     }
 
+    // the GI pass object is created lazily (first SetMethod): it follows the renderer's current strip
+    zr_status ApplyShardToGI()
+    {
+        if (!gi) return ZR_OK;
+        const bool sharded = comm && world > 1;
+        zr_status s = sharded ? zr_gi_pass_set_rows(gi, bounds[rank], bounds[rank + 1]) : zr_gi_pass_set_rows(gi, 0, height);
+        if (s == ZR_OK) s = zr_gi_pass_set_halo_exchange(gi, sharded ? HaloHook : nullptr, &hookMain);
+        return s;
+    }
+
     void Release()
     {
         if (gbufferPass) zr_gbuffer_pass_destroy(gbufferPass);
@@ -213,6 +223,7 @@ extern "C"
             if (!r->gi) s = zr_gi_pass_create(r->width, r->height, &r->gi);
             else s = zr_gi_pass_reset_temporal(r->gi);
             if (s == ZR_OK) s = zr_gi_pass_set_method(r->gi, method);
+            if (s == ZR_OK) s = r->ApplyShardToGI();
         }
         else
             s = zr_indirect_pass_reset_temporal(r->indirect);
@@ -244,12 +255,13 @@ extern "C"
             if (s == ZR_OK) s = zr_taa_pass_set_rows(r->taa, 0, r->height);
             if (s == ZR_OK) s = zr_direct_pass_set_halo_exchange(r->direct, nullptr, nullptr);
             if (s == ZR_OK) s = zr_indirect_pass_set_halo_exchange(r->indirect, nullptr, nullptr);
+            if (s == ZR_OK) s = r->ApplyShardToGI();
             return s;
         }
         if (!bounds) { zr::set_error("zr_renderer_set_shard: bounds missing"); return ZR_ERR_INVALID_ARG; }
-        if (r->integrator != ZR_INTEGRATOR_RESTIR_PT || r->svgf)
+        if (r->svgf)
         {
-            zr::set_error("zr_renderer_set_shard: sharded frames support the ReSTIR PT integrator without the SVGF stage");
+            zr::set_error("zr_renderer_set_shard: sharded frames run without the SVGF stage (its five a-trous passes reach 62 rows, beyond the 32-row halo)");
             return ZR_ERR_UNSUPPORTED;
         }
         int rank = 0, world = 1;
@@ -274,6 +286,7 @@ extern "C"
         if (s == ZR_OK) s = zr_taa_pass_set_rows(r->taa, y0, y1);
         if (s == ZR_OK) s = zr_direct_pass_set_halo_exchange(r->direct, world > 1 ? zr_renderer::HaloHook : nullptr, &r->hookSide);
         if (s == ZR_OK) s = zr_indirect_pass_set_halo_exchange(r->indirect, world > 1 ? zr_renderer::HaloHook : nullptr, &r->hookMain);
+        if (s == ZR_OK) s = r->ApplyShardToGI();
         return s;
     }
     zr_status zr_renderer_get_gi_pass(zr_renderer* r, zr_gi_pass** gi)

@@ -293,7 +293,11 @@ struct zr_gi_pass
     bool resetTemporalTextures = true;
     zr_gi_params params{};
     bool plainPathTracer = false;       // INTEGRATOR::PATH_TRACING instead of ReSTIR_GI (both read cb_ReSTIR_GI in the reference)
+    // strip-sharded frames: owned rows + the hook that makes the reservoirs just written coherent across strips (they are
+    // next frame's temporal candidates, searched up to 16 px around the reprojected pixel: ReSTIR_GI/Params.hlsli:45)
     uint32_t rowBegin = 0, rowEnd = 0xffffffffu;
+    zr_halo_exchange_fn exchange = nullptr;
+    void* exchangeUser = nullptr;
     zr::TileCosts tileCosts;
     zr::BlockSchedule sched;
 
@@ -388,6 +392,11 @@ struct zr_gi_pass
         ZR_PROF("k_rgi", stream);
         k_rgi<false><<<sched.count, ZR_RGI_THREADS, 0, stream>>>(in->scene->dev, f, prm, d_res[cur], d_res[1 - cur], d_final, dispX, dispY, sched.d_order);
         ZR_LAUNCH_CHECK();
+        if (exchange)
+        {
+            const zr_image2d plane{ d_res[cur], width, height, width * (uint32_t)sizeof(zr_rgi_reservoir), (uint32_t)sizeof(zr_rgi_reservoir) };
+            exchange(exchangeUser, &plane, 1, stream);
+        }
         isTemporalReservoirValid = true;
         currTemporalIdx = 1 - cur;
         resetTemporalTextures = false;
@@ -444,6 +453,18 @@ extern "C"
         if (plain == p->plainPathTracer) return ZR_OK;
         p->plainPathTracer = plain;
         return p->ResetTemporal();
+    }
+    zr_status zr_gi_pass_set_rows(zr_gi_pass* p, uint32_t y0, uint32_t y1)
+    {
+        if (!p || y0 >= y1 || y0 >= p->height) { zr::set_error("zr_gi_pass_set_rows: empty row range"); return ZR_ERR_INVALID_ARG; }
+        p->rowBegin = y0; p->rowEnd = y1;
+        return ZR_OK;
+    }
+    zr_status zr_gi_pass_set_halo_exchange(zr_gi_pass* p, zr_halo_exchange_fn fn, void* user)
+    {
+        if (!p) return ZR_ERR_INVALID_ARG;
+        p->exchange = fn; p->exchangeUser = user;
+        return ZR_OK;
     }
     zr_status zr_gi_pass_render(zr_gi_pass* p, const zr_frame_inputs* in, void* stream)
     {

@@ -36,7 +36,8 @@ namespace
             atomicAdd(&costMap[(size_t)(y >> 5) * ((W + 31) >> 5) + (x >> 5)], (unsigned long long)(clock64() - t0));
     }
 
-    __constant__ float c_disk512[1024];
+    // 512 x float2, indexed per pixel by a random offset: a __constant__ table would serialise the 32 different addresses of a warp
+    __device__ __align__(8) float c_disk512[1024];
 
     // -------------------------------------------------------------------------------------------
     // PathTrace
@@ -513,16 +514,28 @@ namespace
         float sinTheta, cosTheta;
         zr_sincosf(theta, &sinTheta, &cosTheta);
         int foundX = 0xffff, foundY = 0xffff;
+        // The three candidates are tested in order and the first that passes wins (ReSTIR_PT_SpatialSearch.hlsl:95-141); their G-buffer
+        // records are fetched together, so the kernel waits for one gather round trip instead of up to three dependent ones.
+        int sxs[3], sys[3];
+        bool inside[3];
+        uint4 cand[3];
+#pragma unroll
         for (uint32_t i = 0; i < 3; i++)
         {
             const uint32_t si = (offset + i) & 511;
-            const float2 sampleUV = f2(c_disk512[si * 2], c_disk512[si * 2 + 1]);
+            const float2 sampleUV = __ldg(reinterpret_cast<const float2*>(c_disk512) + si);
             float2 rotated = f2(dot(sampleUV, f2(cosTheta, -sinTheta)), dot(sampleUV, f2(sinTheta, cosTheta)));
             rotated = rotated * 15.0f;
-            const int sxp = (int)rintf((float)x + rotated.x), syp = (int)rintf((float)y + rotated.y);
-            if (sxp < 0 || syp < 0 || sxp >= (int)f.W || syp >= (int)f.H) continue;
-            if (sxp == (int)x && syp == (int)y) continue;
-            const uint4 sc4 = ld128(&f.core[(size_t)syp * f.W + sxp]);
+            sxs[i] = (int)rintf((float)x + rotated.x); sys[i] = (int)rintf((float)y + rotated.y);
+            inside[i] = !(sxs[i] < 0 || sys[i] < 0 || sxs[i] >= (int)f.W || sys[i] >= (int)f.H) && !(sxs[i] == (int)x && sys[i] == (int)y);
+            cand[i] = inside[i] ? ld128(&f.core[(size_t)sys[i] * f.W + sxs[i]]) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 3; i++)
+        {
+            if (foundX != 0xffff || !inside[i]) continue;
+            const int sxp = sxs[i], syp = sys[i];
+            const uint4 sc4 = cand[i];
             const GFlags sf = DecodeFlags(sc4.w & 0xff);
             if (sf.invalid || sf.emissive) continue;
             if (flags.metallic != sf.metallic) continue;
@@ -535,7 +548,6 @@ namespace
             if (!(fabsf(dot(normal, samplePos - pos)) <= 0.01f * viewDepth)) continue;
             if (dot(sampleNormal, normal) < 0.9f) continue;
             foundX = sxp; foundY = syp;
-            break;
         }
         uint32_t mx, my;
         if (foundX == 0xffff) { mx = 0xff; my = 0xff; }

@@ -69,9 +69,9 @@ namespace
     __global__ void __launch_bounds__(1024, 1) k_spatial_merge(const CUtensorMap* __restrict__ pMapIn, FrameView f, RptParams prm,
         const zr_rpt_reservoir* __restrict__ resIn, zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target,
         float4* __restrict__ finalImg, const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap,
-        const ShiftResult* __restrict__ shiftRes, uint32_t tilesX, uint32_t tileRow0, uint32_t numTiles)
+        const ShiftResult* __restrict__ shiftRes, uint32_t tilesX, uint32_t tileRow0, uint32_t numTiles, uint32_t swizzled)
     {
-        extern __shared__ __align__(128) unsigned char smemRaw[];
+        extern __shared__ __align__(1024) unsigned char smemRaw[];
         MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smemRaw);
         const zr_frame_constants& fc = f.fc;
         const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -89,7 +89,8 @@ namespace
             const uint32_t tx = tile % tilesX, ty = tileRow0 + tile / tilesX;
             uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar[stage]);
             tma::MbarArriveExpectTx(bar, TILE_BYTES);
-            tma::Load2D(&sm.rec[stage][0][0], pMapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
+            if (swizzled) tma::Load3D(&sm.rec[stage][0][0], pMapIn, bar, 0, (int32_t)(tx * 16), (int32_t)(ty * 32));
+            else tma::Load2D(&sm.rec[stage][0][0], pMapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
         };
         if (t == 0 && blockIdx.x < numTiles)
             issue(blockIdx.x, 0);
@@ -154,6 +155,9 @@ namespace
                 {
                     const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
                     n0 = __ldg(&nrec[0]); n1 = __ldg(&nrec[1]);
+                    // second half of the neighbour's record (read only if its sample is accepted, after the RNG draw): brought into L1 now so
+                    // that the slowest warp of the block does not add a second gather round trip before the barrier
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(nrec + 2));
                     const uint4* sp = reinterpret_cast<const uint4*>(&shiftRes[idx]);
                     sh0 = __ldg(&sp[0]);
                     sh1 = __ldg(reinterpret_cast<const float2*>(&sp[1]));
@@ -166,7 +170,10 @@ namespace
 
             zr_rpt_reservoir rec;
             {
-                uint4 v[4] = { sm.rec[stage][t][0], sm.rec[stage][t][1], sm.rec[stage][t][2], sm.rec[stage][t][3] };
+                // the record pair of pixels (2p, 2p + 1) is one 128-byte line; with the swizzled map its 16-byte chunk c sits at c ^ (p & 7)
+                const uint4* line = &sm.rec[stage][t & ~1u][0];
+                const uint32_t c0 = (t & 1u) * 4u, sw = swizzled ? ((t >> 1) & 7u) : 0u;
+                uint4 v[4] = { line[(c0 + 0) ^ sw], line[(c0 + 1) ^ sw], line[(c0 + 2) ^ sw], line[(c0 + 3) ^ sw] };
                 memcpy(&rec, v, 64);
             }
             Reservoir r_curr = Reservoir::Load_NonReconnection(rec);
@@ -335,10 +342,21 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
     ZR_CUDA(cudaMalloc(&d_shift, n * sizeof(ShiftResult)));
     ZR_CUDA(cudaMemset(d_shift, 0, n * sizeof(ShiftResult)));
     const zr_rpt_reservoir* planes[2] = { res0, res1 };
+    swizzled = (w % 2) == 0;
     for (int i = 0; i < 2; i++)
     {
         mapBase[i] = planes[i];
-        if (!tma::EncodePlane2D(&mapRes[i], planes[i], w, h, 64, (uint64_t)w * 64, 32, 32))
+        bool ok;
+        if (swizzled)
+        {
+            const uint64_t dims[3] = { 16, w / 2, h };
+            const uint64_t strides[2] = { 128, (uint64_t)w * 64 };
+            const uint32_t box[3] = { 16, 16, 32 };
+            ok = tma::EncodeWords(&mapRes[i], planes[i], 3, dims, strides, box, true);
+        }
+        else
+            ok = tma::EncodePlane2D(&mapRes[i], planes[i], w, h, 64, (uint64_t)w * 64, 32, 32);
+        if (!ok)
         {
             set_error("zr_indirect_pass: cuTensorMapEncodeTiled failed for the %ux%u reservoir plane", w, h);
             return ZR_ERR_CUDA;
@@ -383,7 +401,7 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
         const uint32_t grid = numTiles < (uint32_t)numSMs ? numTiles : (uint32_t)numSMs;
         ZR_PROF("k_spatial_merge", stream);
         k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(d_maps + plane, f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
-            d_shift, tilesX, tileRow0, numTiles);
+            d_shift, tilesX, tileRow0, numTiles, swizzled ? 1u : 0u);
         ZR_LAUNCH_CHECK();
     }
     return ZR_OK;

@@ -81,8 +81,8 @@ static zr_status upload(zr_scene* sc, const T* h, size_t n, const T** d)
 {
     void* p = nullptr;
     ZR_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    sc->allocs[sc->numAllocs++] = p;        // owned by the scene from here on: released by zr_scene_destroy on every error path
     if (n) ZR_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
-    sc->allocs[sc->numAllocs++] = p;
     *d = (const T*)p;
     return ZR_OK;
 }
@@ -94,6 +94,42 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
     {
         set_error("zr_scene_create: null input");
         return ZR_ERR_INVALID_ARG;
+    }
+    // Everything the kernels will index is checked here, on the host, in 64-bit arithmetic, before anything is allocated: a malformed
+    // description is an error code, not an out-of-bounds device read in k_world_tris and every lighting kernel.
+    {
+        uint64_t totalTris = 0;
+        for (uint32_t m = 0; m < desc->num_instances; m++)
+        {
+            const zr_mesh_instance& mi = desc->h_instances[m];
+            const uint64_t nt = desc->h_instance_num_tris[m];
+            if ((uint64_t)mi.BaseIdxOffset + 3 * nt > desc->num_indices)
+            {
+                set_error("zr_scene_create: instance %u indexes past the index buffer", m);
+                return ZR_ERR_INVALID_ARG;
+            }
+            if (mi.MatIdx >= desc->num_materials)
+            {
+                set_error("zr_scene_create: instance %u uses material %u of %u", m, (unsigned)mi.MatIdx, desc->num_materials);
+                return ZR_ERR_INVALID_ARG;
+            }
+            for (uint64_t i = 0; i < 3 * nt; i++)
+                if ((uint64_t)mi.BaseVtxOffset + desc->h_indices[mi.BaseIdxOffset + i] >= desc->num_vertices)
+                {
+                    set_error("zr_scene_create: instance %u, index %llu points past the vertex buffer", m, (unsigned long long)i);
+                    return ZR_ERR_INVALID_ARG;
+                }
+            if (mi.BaseEmissiveTriOffset != 0xffffffffu && (uint64_t)mi.BaseEmissiveTriOffset + nt > desc->num_emissives)
+            {
+                set_error("zr_scene_create: instance %u's emissive triangles [%u, %llu) lie past the %u emissive triangles", m,
+                    mi.BaseEmissiveTriOffset, (unsigned long long)(mi.BaseEmissiveTriOffset + nt), desc->num_emissives);
+                return ZR_ERR_INVALID_ARG;
+            }
+            totalTris += nt;
+        }
+        if (totalTris == 0) { set_error("zr_scene_create: scene has no triangles"); return ZR_ERR_INVALID_ARG; }
+        if (totalTris > 0x7fffffffull) { set_error("zr_scene_create: more than 2^31 triangles"); return ZR_ERR_INVALID_ARG; }
+        if (desc->num_emissives && !desc->h_emissives) { set_error("zr_scene_create: null emissive buffer"); return ZR_ERR_INVALID_ARG; }
     }
     zr_scene* sc = new zr_scene();
     zr_status st;
@@ -144,11 +180,13 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
 
     // world-space triangles on the device, then BVH on the host
     float* d_wt = nullptr;
-    ZR_CUDA(cudaMalloc(&d_wt, (size_t)total * 9 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_wt, (size_t)total * 9 * sizeof(float));
+    if (e != cudaSuccess) { zr_scene_destroy(sc); return cuda_fail(e, "world triangles (alloc)"); }
     k_world_tris<<<(total + 127) / 128, 128>>>(sc->dev, sc->dev.triMesh, sc->dev.meshFirstTri, total, d_wt);
     count_launch();
+    e = cudaGetLastError();
     std::vector<float> wt((size_t)total * 9);
-    cudaError_t e = cudaMemcpy(wt.data(), d_wt, wt.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(wt.data(), d_wt, wt.size() * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d_wt);
     if (e != cudaSuccess) { zr_scene_destroy(sc); return cuda_fail(e, "world triangles"); }
 
@@ -186,9 +224,10 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
     // alias table storage (built by zr_prelighting_render)
     if (desc->num_emissives)
     {
-        cudaMalloc(&sc->d_alias, (size_t)desc->num_emissives * sizeof(zr_alias_entry));
-        cudaMalloc(&sc->d_power, (size_t)(desc->num_emissives + 8) * sizeof(float));
-        cudaMalloc(&sc->d_aliasScratch, (size_t)desc->num_emissives * 2 * sizeof(uint32_t));
+        e = cudaMalloc(&sc->d_alias, (size_t)desc->num_emissives * sizeof(zr_alias_entry));
+        if (e == cudaSuccess) e = cudaMalloc(&sc->d_power, (size_t)(desc->num_emissives + 8) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&sc->d_aliasScratch, (size_t)desc->num_emissives * 2 * sizeof(uint32_t));
+        if (e != cudaSuccess) { zr_scene_destroy(sc); return cuda_fail(e, "alias table storage"); }
         sc->dev.aliasTable = sc->d_alias;
     }
     *out = sc;

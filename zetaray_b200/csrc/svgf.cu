@@ -232,9 +232,10 @@ namespace
                         const float ndot = fmaf(znt.y, nc.x, fmaf(znt.z, nc.y, znt.w * nc.z));
                         const float wn = fmaf(ndot, prm.k_n, oneMinusK);
                         const float wl = fmaf(-fabsf(s_lum[ti] - lc), invL, 1.0f);
-                        float w = hw * fmaxf(wz, 0.0f);
+                        // wz, wl <= 1 by construction (1 - |d| * inv, one rounding), so max(., 0) is a saturate: one FFMA.SAT each
+                        float w = hw * __saturatef(wz);
                         w = w * fmaxf(wn, 0.0f);
-                        w = w * fmaxf(wl, 0.0f);
+                        w = w * __saturatef(wl);
                         sumC = f3(fmaf(w, cvt.x, sumC.x), fmaf(w, cvt.y, sumC.y), fmaf(w, cvt.z, sumC.z));
                         sumV = fmaf(w * w, cvt.w, sumV);
                         sumW = sumW + w;

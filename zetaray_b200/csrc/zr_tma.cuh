@@ -45,7 +45,11 @@ namespace tma
     // General form: `rank` dimensions of 64-bit words, dims[0] innermost (contiguous); stridesBytes[i] is the byte stride of
     // dimension i + 1 (multiples of 16). Used for strided-lattice views of an image: {phase_x, u, phase_y, v} with pixel
     // x = u * step + phase_x, y = v * step + phase_y turns every sub-lattice of an a-trous pass into a dense box.
-    inline bool EncodeWords(CUtensorMap* map, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* stridesBytes, const uint32_t* box)
+    // swizzle128: CU_TENSOR_MAP_SWIZZLE_128B -- the innermost box extent must be 16 words (128 bytes) and the shared-memory tile 1024-byte
+    // aligned; the 16-byte chunk c of the 128-byte line L of the tile then lives at chunk c ^ (L & 7) of that line, which makes a warp's
+    // 128-bit reads of consecutive 64-byte records conflict-free.
+    inline bool EncodeWords(CUtensorMap* map, const void* base, uint32_t rank, const uint64_t* dims, const uint64_t* stridesBytes, const uint32_t* box,
+        bool swizzle128 = false)
     {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -63,8 +67,9 @@ namespace tma
         cuuint64_t d[5]; cuuint64_t st[4]; cuuint32_t b[5]; cuuint32_t es[5];
         for (uint32_t i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; if (box[i] == 0 || box[i] > 256) return false; }
         for (uint32_t i = 0; i + 1 < rank; i++) { st[i] = stridesBytes[i]; if (st[i] % 16) return false; }
+        if (swizzle128 && box[0] != 16) return false;
         return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, rank, const_cast<void*>(base), d, st, b, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
 
@@ -107,6 +112,11 @@ namespace tma
     {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
             :: "l"((uint64_t)map), "r"(SmemAddr(smem)), "r"(x0), "r"(y0) : "memory");
+    }
+    __device__ __forceinline__ void Load3D(void* smem, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2)
+    {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            :: "r"(SmemAddr(smem)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
     }
     __device__ __forceinline__ void Load4D(void* smem, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3)
     {

@@ -298,6 +298,13 @@ class IndirectLightingGI(_Pass):
         (PathTracer.hlsl) or ReSTIR GI."""
         check(lib.zr_gi_pass_set_method(self.handle, int(integrator)))
 
+    def SetRows(self, y0, y1):
+        check(lib.zr_gi_pass_set_rows(self.handle, y0, y1))
+
+    def SetHaloExchange(self, fn):
+        self._hook = fn
+        check(lib.zr_gi_pass_set_halo_exchange(self.handle, fn if fn is not None else _lib.HALO_EXCHANGE_FN(), None))
+
     def OnWindowResized(self, w, h):
         check(lib.zr_gi_pass_resize(self.handle, w, h))
 
