@@ -326,7 +326,7 @@ ZR_API zr_status zr_scene_trace_any(const zr_scene* scene, const float* d_rays, 
  * ------------------------------------------------------------------------------------------ */
 
 /* Math::AliasTable_Normalize + BuildAliasTable on the device. d_weights is normalised in place
- * (as the reference does to its readback buffer). d_scratch: 2*n u32. Bit-exact with the CPU
+ * (as the reference does to its readback buffer). d_scratch: 2*n + 16 u32. Bit-exact with the CPU
  * reference for 32-byte aligned input (the production case). */
 ZR_API zr_status zr_alias_table_build(float* d_weights, uint32_t n, zr_alias_entry* d_table,
     uint32_t* d_scratch, void* stream);

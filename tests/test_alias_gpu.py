@@ -29,7 +29,7 @@ def test_alias_build_bit_exact(oracle, n):
 
     d_w = dev(w)
     d_t = torch.zeros(n * 16, dtype=torch.uint8, device="cuda")
-    d_s = torch.zeros(2 * n * 4, dtype=torch.uint8, device="cuda")
+    d_s = torch.zeros((2 * n + 16) * 4, dtype=torch.uint8, device="cuda")       # 2n stack entries + 16 words of sums / counts
     check(lib.zr_alias_table_build(dptr(d_w), C.c_uint32(n), dptr(d_t), dptr(d_s), stream()))
     torch.cuda.synchronize()
     got = host(d_t, E16)

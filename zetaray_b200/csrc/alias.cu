@@ -296,12 +296,10 @@ zr_status alias_table_build(float* d_weights, uint32_t n, zr_alias_entry* d_tabl
         set_error("zr_alias_table_build: d_weights must be 32-byte aligned (reference parity, SURVEY 8a-1)");
         return ZR_ERR_INVALID_ARG;
     }
-    // scratch: [0, n) smaller stack, [n, 2n) larger stack; sums/counts live in a small side buffer
-    static thread_local float* d_small = nullptr;
-    if (!d_small)
-        ZR_CUDA(cudaMalloc(&d_small, 16 * sizeof(float)));
-    float* d_sums = d_small;
-    uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_small + 4);
+    // scratch: [0, n) smaller stack, [n, 2n) larger stack, [2n, 2n + 16) Kahan sums and partition counts -- all in the caller's buffer, so
+    // builds on different streams, devices or threads share nothing
+    float* d_sums = reinterpret_cast<float*>(d_scratch + 2 * (size_t)n);
+    uint32_t* d_counts = d_scratch + 2 * (size_t)n + 4;
 
     ZR_PROF("k_kahan_sum", stream);
     k_kahan_sum<<<1, SUM_THREADS, 0, stream>>>(d_weights, n, d_sums);

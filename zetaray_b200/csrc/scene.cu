@@ -226,7 +226,7 @@ zr_status scene_create(const zr_scene_desc* desc, zr_scene** out)
     {
         e = cudaMalloc(&sc->d_alias, (size_t)desc->num_emissives * sizeof(zr_alias_entry));
         if (e == cudaSuccess) e = cudaMalloc(&sc->d_power, (size_t)(desc->num_emissives + 8) * sizeof(float));
-        if (e == cudaSuccess) e = cudaMalloc(&sc->d_aliasScratch, (size_t)desc->num_emissives * 2 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&sc->d_aliasScratch, ((size_t)desc->num_emissives * 2 + 16) * sizeof(uint32_t));
         if (e != cudaSuccess) { zr_scene_destroy(sc); return cuda_fail(e, "alias table storage"); }
         sc->dev.aliasTable = sc->d_alias;
     }
