@@ -16,7 +16,6 @@
 #include "zr_rpt_spatial.h"
 #include "zr_rpt_shift.cuh"
 #include "zr_tma.cuh"
-#include <cstdlib>
 
 namespace zr
 {
@@ -317,301 +316,6 @@ namespace
             __syncthreads();        // the stage's records and the exchange arrays are free again
         }
     }
-
-    // ---------------------------------------------------------------------------------------------------------------
-    // merge, second form: the same three phases per 32x32 tile with 512 threads (two pixels each) and TWO co-resident blocks per SM, so
-    // that one tile's gathers and barriers overlap the other tile's arithmetic. What a pixel carries from phase 1 to phase 3 is parked
-    // in shared memory (32 bytes + the record slot) instead of registers; a pixel whose sample changed gets its new record written into
-    // its slot of the staged tile in phase 1, so phase 3 only decides between that record, the copy of the old one, and the cleared one.
-    // Same bytes as k_spatial_merge.
-    // ---------------------------------------------------------------------------------------------------------------
-    struct Merge2Smem
-    {
-        uint4 rec[1024][4];         // TMA destination; slots of changed pixels are overwritten in phase 1 (same chunk placement)
-        float4 stA[1024];           // {w_sum, W, target.x, target.y} after phase 1
-        float4 stB[1024];           // {target.z, bits, w_sum on entry, -}; bits = cls | changed << 2 | M << 8 | M_new << 16 | M_max << 24
-        float val[2][1024];         // in: [0] w_sum on entry, [1] term of the final sum; out (same slot, phase 2): the two wave sums
-        uint8_t visited[1024];
-        unsigned long long bar;
-    };
-
-    __global__ void __launch_bounds__(512, 2) k_spatial_merge2(const CUtensorMap* __restrict__ pMapIn, FrameView f, RptParams prm,
-        const zr_rpt_reservoir* __restrict__ resIn, zr_rpt_reservoir* __restrict__ resOut, const float4* __restrict__ target,
-        float4* __restrict__ finalImg, const uint16_t* __restrict__ neighbor, const uint16_t* __restrict__ threadMap,
-        const ShiftResult* __restrict__ shiftRes, uint32_t tilesX, uint32_t tileRow0, uint32_t numTiles, uint32_t swizzled)
-    {
-        extern __shared__ __align__(1024) unsigned char smemRaw[];
-        Merge2Smem& sm = *reinterpret_cast<Merge2Smem*>(smemRaw);
-        const zr_frame_constants& fc = f.fc;
-        const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar);
-        if (t == 0)
-        {
-            tma::MbarInit(bar, 1);
-            tma::FenceBarrierInit();
-        }
-        __syncthreads();
-        auto issue = [&](uint32_t tile)
-        {
-            const uint32_t tx = tile % tilesX, ty = tileRow0 + tile / tilesX;
-            tma::MbarArriveExpectTx(bar, 1024u * 64u);
-            if (swizzled) tma::Load3D(&sm.rec[0][0], pMapIn, bar, 0, (int32_t)(tx * 16), (int32_t)(ty * 32));
-            else tma::Load2D(&sm.rec[0][0], pMapIn, bar, (int32_t)(tx * 32 * 8), (int32_t)(ty * 32));
-        };
-        if (t == 0 && blockIdx.x < numTiles)
-            issue(blockIdx.x);
-        // 16-byte chunk c of pixel p's record: the pair (2q, 2q + 1) is one 128-byte line whose chunks sit at c ^ (q & 7) when swizzled
-        auto slot = [&](uint32_t p, uint32_t c) -> uint4& { return sm.rec[p & ~1u][(((p & 1u) * 4u + c) ^ (swizzled ? ((p >> 1) & 7u) : 0u))]; };
-
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, it++)
-        {
-            const uint32_t tileX = tile % tilesX, tileY = tileRow0 + tile / tilesX;
-            // first-level loads of both pixels and both thread positions of this thread: in flight while the tile arrives
-            uint32_t pfFlags[2], pfNb[2], pfMap[2];
-            float4 pfTg[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-            {
-                const uint32_t px = tileX * 32 + lane, py = tileY * 32 + warp + 16 * h;
-                pfFlags[h] = 0xff; pfNb[h] = 0xffff; pfTg[h] = f4(0, 0, 0, 0);
-                if (px < f.W && py < f.H && py >= prm.rowBegin && py < prm.rowEnd)
-                {
-                    const size_t i = (size_t)py * f.W + px;
-                    pfFlags[h] = __ldg(&f.core[i].w) & 0xff;
-                    pfNb[h] = __ldg(&neighbor[i]);
-                    pfTg[h] = __ldg(&target[i]);
-                }
-                const uint32_t v = warp + 16 * h;       // wave of the sorted dispatch this warp plays in phase 2
-                const uint32_t sx = tileX * 32 + (v & 3) * 8 + (lane & 7), sy = tileY * 32 + (v >> 2) * 4 + (lane >> 3);
-                pfMap[h] = 0x8000;
-                if (sx < f.W && sy < f.H)
-                    pfMap[h] = prm.sortSpatial ? __ldg(&threadMap[(size_t)sy * f.W + sx]) : (31u | (31u << 7));
-            }
-            tma::MbarWait(bar, it & 1);
-
-            // ---- phase 1 (pixel order) ----
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-            {
-                const uint32_t p = t + 512u * h;
-                const int x = (int)(tileX * 32 + lane), y = (int)(tileY * 32 + warp + 16 * h);
-                const bool inImage = (uint32_t)x < f.W && (uint32_t)y < f.H;
-                const size_t idx = inImage ? (size_t)y * f.W + x : 0;
-                const GFlags flags = DecodeFlags(pfFlags[h]);
-                const bool act = !(flags.invalid || flags.emissive);
-                int nx = 0, ny = 0;
-                bool hasN = false;
-                const float4 tg = pfTg[h];
-                uint4 sh0 = make_uint4(0, 0, 0, 0);
-                float2 sh1 = f2(0, 0);
-                uint4 n0 = make_uint4(Reconnection::EMPTY, 0, 0, 0), n1 = make_uint4(0, 0, 0, 0);
-                if (act)
-                {
-                    const uint32_t ox = pfNb[h] & 0xff, oy = pfNb[h] >> 8;
-                    hasN = ox != 0xff;
-                    nx = (int)ox - 32 + x; ny = (int)oy - 32 + y;
-                    if (hasN)
-                    {
-                        const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
-                        n0 = __ldg(&nrec[0]); n1 = __ldg(&nrec[1]);
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(nrec + 2));
-                        const uint4* sp = reinterpret_cast<const uint4*>(&shiftRes[idx]);
-                        sh0 = __ldg(&sp[0]);
-                        sh1 = __ldg(reinterpret_cast<const float2*>(&sp[1]));
-                    }
-                }
-                zr_rpt_reservoir rec;
-                {
-                    uint4 v[4] = { slot(p, 0), slot(p, 1), slot(p, 2), slot(p, 3) };
-                    memcpy(&rec, v, 64);
-                }
-                Reservoir r_curr = Reservoir::Load_NonReconnection(rec);
-                r_curr.target = f3(tg.x, tg.y, tg.z);
-                const float wsum0 = act ? r_curr.w_sum : 0.0f;
-                uint32_t M_max = prm.M_max_spatial;
-                M_max = !r_curr.rc.Empty() && r_curr.rc.lobe_k_min_1 == BSDF::GLOSSY_T ? (M_max < 4 ? M_max : 4) : M_max;
-                uint32_t cls = 0, M_new = 0;
-                bool changed = false;
-                if (act && !hasN)
-                    cls = 1;
-                else if (act)
-                {
-                    zr_rpt_reservoir recN;
-                    memset(&recN, 0, sizeof(recN));
-                    memcpy(&recN, &n0, 16); memcpy(reinterpret_cast<unsigned char*>(&recN) + 16, &n1, 16);
-                    Reservoir r_spatial = Reservoir::Load_NonReconnection(recN);
-                    if ((r_curr.w_sum != 0) && !r_curr.rc.Empty() && (r_spatial.M > 0))
-                    {
-                        const float target_spatial = sh1.x;
-                        if (target_spatial > 0)
-                        {
-                            const float selfJ = (r_curr.rc.IsCase3() && r_curr.rc.lobe_k_min_1 == BSDF::ALL) ? 1.0f : asfloat(rec.jacobian_or_seed_nee);
-                            const float targetLum_curr = r_curr.W > 0 ? r_curr.w_sum / r_curr.W : 0;
-                            const float jacobian = selfJ > 0 ? sh1.y / selfJ : 0;
-                            const float numerator = (float)r_curr.M * targetLum_curr;
-                            const float denom = numerator + (float)r_spatial.M * target_spatial * jacobian;
-                            const float m_curr = denom > 0 ? numerator / denom : 0;
-                            r_curr.w_sum *= m_curr;
-                        }
-                    }
-                    M_new = r_curr.M + r_spatial.M;
-                    if (r_spatial.rc.Empty())
-                        cls = 2;
-                    else
-                    {
-                        cls = 3;
-                        M_max = r_spatial.rc.x_k_in_motion ? (M_max < 4 ? M_max : 4) : M_max;
-                        r_spatial.rc.x_k_in_motion = false;
-                        const float nJ = (r_spatial.rc.IsCase3() && r_spatial.rc.lobe_k_min_1 == BSDF::ALL) ? 1.0f : asfloat(recN.jacobian_or_seed_nee);
-                        const float3 shTarget = f3(asfloat(sh0.x), asfloat(sh0.y), asfloat(sh0.z));
-                        const float shJ = fabsf(asfloat(sh0.w));
-                        const bool surfKMin1Tr = (sh0.w >> 31) != 0;
-                        const float targetLum_curr = Math::Luminance(shTarget);
-                        const float targetLum_spatial = r_spatial.W > 0 ? r_spatial.w_sum / r_spatial.W : 0;
-                        const float jacobian = nJ > 0 ? shJ / nJ : 0;
-                        if (targetLum_curr > 1e-6f && jacobian > 1e-5f && jacobian < 100)
-                        {
-                            const uint3 hh = RNG::PCG3d(make_uint3((uint32_t)x, (uint32_t)y, (uint32_t)y));
-                            RNG rng = RNG::Init(hh.x, hh.z, fc.FrameNum + 511);
-                            const float numerator = (float)r_spatial.M * targetLum_spatial;
-                            const float denom = numerator / jacobian + (float)r_curr.M * targetLum_curr;
-                            const float m_spatial = denom > 0 ? numerator / denom : 0;
-                            const float w_spatial = m_spatial * r_spatial.W * targetLum_curr;
-                            if (r_curr.Update(w_spatial, shTarget, r_spatial.rc, rng))
-                            {
-                                const uint4* nrec = reinterpret_cast<const uint4*>(&resIn[(size_t)ny * f.W + nx]);
-                                const uint4 n2 = __ldg(&nrec[2]), n3 = __ldg(&nrec[3]);
-                                memcpy(reinterpret_cast<unsigned char*>(&recN) + 32, &n2, 16);
-                                memcpy(reinterpret_cast<unsigned char*>(&recN) + 48, &n3, 16);
-                                r_spatial.Load_Reconnection(recN);
-                                r_curr.rc = r_spatial.rc;
-                                r_curr.rc.partialJacobian = shJ;
-                                changed = true;
-                            }
-                        }
-                        const float targetLum = Math::Luminance(r_curr.target);
-                        r_curr.W = targetLum > 0 ? r_curr.w_sum / targetLum : 0;
-                        r_curr.M = M_new;
-                        if (changed)
-                        {
-                            // the record this pixel writes unless the boiling filter clears it (phase 3)
-                            const uint32_t mmax = surfKMin1Tr ? (M_max < 4 ? M_max : 4) : M_max;
-                            zr_rpt_reservoir out;
-                            Reservoir tmp = r_curr;
-                            tmp.Write(out, mmax);
-                            uint4 v[4];
-                            memcpy(v, &out, 64);
-                            slot(p, 0) = v[0]; slot(p, 1) = v[1]; slot(p, 2) = v[2]; slot(p, 3) = v[3];
-                        }
-                    }
-                }
-                const uint32_t bits = cls | (changed ? 4u : 0u) | ((r_curr.M & 0xffu) << 8) | ((M_new & 0xffu) << 16) | ((M_max & 0xffu) << 24);
-                sm.stA[p] = f4(r_curr.w_sum, r_curr.W, r_curr.target.x, r_curr.target.y);
-                sm.stB[p] = f4(r_curr.target.z, asfloat(bits), wsum0, 0.0f);
-                sm.val[0][p] = wsum0;
-                sm.val[1][p] = act ? r_curr.w_sum : 0.0f;
-                sm.visited[p] = 0;
-            }
-            __syncthreads();
-
-            // ---- phase 2 (sorted thread order): each warp plays two waves of the reference's dispatch ----
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-            {
-                const uint32_t v = warp + 16 * h, mapEnc = pfMap[h];
-                bool on = !(mapEnc & (1u << 15));
-                int lx = (int)((v & 3) * 8 + (lane & 7)), ly = (int)((v >> 2) * 4 + (lane >> 3));
-                lx += (int)(mapEnc & 0x3f) - 31;
-                ly += (int)((mapEnc >> 7) & 0x3f) - 31;
-                if (on && ((uint32_t)lx >= 32u || (uint32_t)ly >= 32u)) on = false;
-                const uint32_t lp = on ? (uint32_t)(ly * 32 + lx) : 0;
-                const float v0 = on ? sm.val[0][lp] : 0.0f, v1 = on ? sm.val[1][lp] : 0.0f;
-                const uint32_t c = on ? (asuint(sm.stB[lp].y) & 3u) : 0u;
-                const float waveSum = WaveSum32(v0);
-                float waveAcc = WaveSum32(c == 1 ? v1 : 0.0f);
-                waveAcc += WaveSum32(c == 2 ? v1 : 0.0f);
-                const float total = waveAcc + WaveSum32(c == 3 ? v1 : 0.0f);
-                if (on)
-                {
-                    // in place: a pixel belongs to exactly one thread position, whose lane read its terms above
-                    sm.val[0][lp] = waveSum; sm.val[1][lp] = total;
-                    sm.visited[lp] = 1;
-                }
-            }
-            __syncthreads();
-
-            // ---- phase 3 (pixel order): boiling suppression, record, colour ----
-#pragma unroll 1
-            for (int h = 0; h < 2; h++)
-            {
-                const uint32_t p = t + 512u * h;
-                const float4 a = sm.stA[p], b = sm.stB[p];
-                const uint32_t bits = asuint(b.y), cls = bits & 3u;
-                if (cls == 0 || !sm.visited[p]) continue;
-                const int x = (int)(tileX * 32 + lane), y = (int)(tileY * 32 + warp + 16 * h);
-                const size_t idx = (size_t)y * f.W + x;
-                const bool changed = (bits & 4u) != 0;
-                const uint32_t M_new = (bits >> 16) & 0xffu, M_max = bits >> 24;
-                zr_rpt_reservoir rec;
-                {
-                    uint4 v[4] = { slot(p, 0), slot(p, 1), slot(p, 2), slot(p, 3) };
-                    memcpy(&rec, v, 64);
-                }
-                Reservoir r_curr = Reservoir::Load_NonReconnection(rec);       // the sample's tags: own record, or the new one if it changed
-                r_curr.w_sum = a.x; r_curr.W = a.y; r_curr.M = (bits >> 8) & 0xffu;
-                r_curr.target = f3(a.z, a.w, b.x);
-                const float wsum0 = b.z;
-                const float avgEx0 = (sm.val[0][p] - wsum0) / 32.0f;
-                if (cls == 1)
-                {
-                    if (prm.boilingSuppression) SuppressOutlier(avgEx0, r_curr);
-                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
-                    CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
-                }
-                else if (cls == 2)
-                {
-                    if (prm.boilingSuppression) SuppressOutlier(avgEx0, r_curr);
-                    const float targetLum = Math::Luminance(r_curr.target);
-                    r_curr.W = targetLum > 0 ? r_curr.w_sum / targetLum : 0;
-                    r_curr.M = M_new;
-                    CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
-                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
-                }
-                else
-                {
-                    if (prm.boilingSuppression)
-                        SuppressOutlier((sm.val[1][p] - r_curr.w_sum) / 32.0f, r_curr);
-                    if (changed)
-                    {
-                        if (r_curr.rc.Empty())
-                        {
-                            // cleared by the filter: header only (M = 0, so the M clamp plays no role)
-                            zr_rpt_reservoir out;
-                            r_curr.Write(out, M_max);
-                            StoreRecord(&resOut[idx], out);
-                        }
-                        else
-                        {
-                            StoreRecord(&resOut[idx], rec);
-                            // Reservoir::Write sanitises w_sum and W in place before the colour is formed (k_spatial_merge: Write, then colour)
-                            r_curr.w_sum = Math::Sanitize(r_curr.w_sum);
-                            r_curr.W = Math::Sanitize(r_curr.W);
-                        }
-                    }
-                    else
-                        CopyToNextFrame(rec, &resOut[idx], r_curr, M_max);
-                    WriteOutputColor(fc, finalImg, idx, r_curr.target * r_curr.W);
-                }
-            }
-            __syncthreads();        // every read of the tile and of the exchange arrays is done
-            if (t == 0 && tile + gridDim.x < numTiles)
-            {
-                tma::FenceProxyAsync();
-                issue(tile + gridDim.x);
-            }
-        }
-    }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -666,8 +370,6 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
     ZR_CUDA(cudaGetDevice(&dev));
     ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
     ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
-    ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Merge2Smem)));
-    if (const char* e = getenv("ZETARAY_B200_MERGE")) mergeForm = atoi(e) == 2 ? 2 : 1;     // A/B switch for measurements
     ready = true;
     return ZR_OK;
 }
@@ -696,19 +398,13 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
         const uint32_t tilesX = (width + 31) / 32;
         const uint32_t tileRow0 = prm.rowBegin / 32, tileRow1 = (prm.rowEnd + 31) / 32;
         const uint32_t numTiles = tilesX * (tileRow1 - tileRow0);
+        // A second form -- 512 threads x 2 co-resident blocks per SM, per-pixel state parked in shared memory between the phases -- was
+        // measured bit-identical and exactly as fast (profiles/r2p_merge_forms.json): the kernel waits for its global loads at 32 warps per
+        // SM in either form. Removed again.
+        const uint32_t grid = numTiles < (uint32_t)numSMs ? numTiles : (uint32_t)numSMs;
         ZR_PROF("k_spatial_merge", stream);
-        if (mergeForm == 2)
-        {
-            const uint32_t grid = numTiles < 2u * (uint32_t)numSMs ? numTiles : 2u * (uint32_t)numSMs;
-            k_spatial_merge2<<<grid, 512, sizeof(Merge2Smem), stream>>>(d_maps + plane, f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
-                d_shift, tilesX, tileRow0, numTiles, swizzled ? 1u : 0u);
-        }
-        else
-        {
-            const uint32_t grid = numTiles < (uint32_t)numSMs ? numTiles : (uint32_t)numSMs;
-            k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(d_maps + plane, f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
-                d_shift, tilesX, tileRow0, numTiles, swizzled ? 1u : 0u);
-        }
+        k_spatial_merge<<<grid, 1024, sizeof(MergeSmem), stream>>>(d_maps + plane, f, prm, resIn, resOut, target, finalImg, neighbor, threadMap,
+            d_shift, tilesX, tileRow0, numTiles, swizzled ? 1u : 0u);
         ZR_LAUNCH_CHECK();
     }
     return ZR_OK;

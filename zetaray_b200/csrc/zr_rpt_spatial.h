@@ -38,7 +38,6 @@ struct SpatialQueued
     CUtensorMap* d_maps = nullptr;              // device copy of mapRes (the kernel reads the descriptor from global memory)
     int numSMs = 0;
     bool ready = false;
-    int mergeForm = 1;                          // 1: 1024 threads x 1 block per SM; 2: 512 threads x 2 blocks per SM (rpt_spatial.cu)
     bool swizzled = false;                      // even widths: 3-D map {128-byte record pair, W / 2, H} with the 128-byte swizzle
 
     zr_status Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* res0, const zr_rpt_reservoir* res1);
