@@ -1,5 +1,6 @@
 # r2s: whole GPU suite on the final kernels, bench line, ncu launch list + full captures of the judged kernels
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 6 > gpurun_out/r2s_tests.log; cat gpurun_out/r2s_tests.log
 timeout 400 python bench.py --steps 20 --warmup 5 2>gpurun_out/r2s_bench.err | tail -n 1 > gpurun_out/r2s_bench.json
 python - <<PY
@@ -24,4 +25,9 @@ prof k_spatial_classify k_spatial_classify 3
 prof k_svgf_atrous_step1 k_svgf_atrous 5
 prof k_svgf_atrous_step4 k_svgf_atrous 7
 prof k_svgf_temporal k_svgf_temporal 2
+prof k_taa k_taa 3
+prof k_spatial_search k_spatial_search 3
+prof k_firefly k_firefly 3
+prof k_pathtrace k_pathtrace 3
+prof k_di_temporal k_di_temporal 3
 du -sh gpurun_out

@@ -16,6 +16,7 @@
 #include "zr_rpt_spatial.h"
 #include "zr_rpt_shift.cuh"
 #include "zr_tma.cuh"
+#include <cstdlib>
 
 namespace zr
 {
@@ -327,6 +328,14 @@ void SpatialQueued::Release()
     if (d_counters) cudaFree(d_counters);
     if (d_shift) cudaFree(d_shift);
     if (d_maps) cudaFree(d_maps);
+    for (int i = 0; i < 2; i++)
+    {
+        if (aux[i]) cudaStreamDestroy(aux[i]);
+        if (evJoin[i]) cudaEventDestroy(evJoin[i]);
+        aux[i] = nullptr; evJoin[i] = nullptr;
+    }
+    if (evFork) cudaEventDestroy(evFork);
+    evFork = nullptr;
     d_queue = nullptr; d_counters = nullptr; d_shift = nullptr; d_maps = nullptr;
     ready = false;
 }
@@ -370,6 +379,15 @@ zr_status SpatialQueued::Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* 
     ZR_CUDA(cudaGetDevice(&dev));
     ZR_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
     ZR_CUDA(cudaFuncSetAttribute(k_spatial_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    if (!getenv("ZETARAY_B200_SHIFT_ONE_STREAM"))        // A/B switch for measurements
+    {
+        for (int i = 0; i < 2; i++)
+        {
+            ZR_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            ZR_CUDA(cudaEventCreateWithFlags(&evJoin[i], cudaEventDisableTiming));
+        }
+        ZR_CUDA(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+    }
     ready = true;
     return ZR_OK;
 }
@@ -389,8 +407,9 @@ zr_status SpatialQueued::Run(const SceneDev& sc, const FrameView& f, const RptPa
     }
     {
         ZR_PROF("k_shift", stream);
-        LaunchShifts<false>(numSMs, sc, f, prm, resIn, nullptr, neighbor, d_queue, capacity, d_counters, d_shift, stream);
+        const zr_status ls = LaunchShifts<false>(*this, sc, f, prm, resIn, nullptr, neighbor, stream);
         zr::prof_after();
+        if (ls != ZR_OK) return ls;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return zr::cuda_fail(e, "k_shift launch");
     }

@@ -211,8 +211,9 @@ zr_status TemporalQueued::Run(SpatialQueued& q, const SceneDev& sc, const FrameV
     }
     {
         ZR_PROF("k_shift_temporal", stream);
-        LaunchShifts<true>(q.numSMs, sc, f, prm, resCurr, resPrev, nullptr, q.d_queue, q.capacity, q.d_counters, q.d_shift, stream);
+        const zr_status ls = LaunchShifts<true>(q, sc, f, prm, resCurr, resPrev, nullptr, stream);
         zr::prof_after();
+        if (ls != ZR_OK) return ls;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return zr::cuda_fail(e, "k_shift (temporal) launch");
     }

@@ -120,24 +120,43 @@ namespace
         }
     }
 
-    // one launch per class; a launch whose queue is empty costs a few microseconds (its blocks leave at the first claim)
+    // One launch per class; a launch whose queue is empty costs a few microseconds (its blocks leave at the first claim). The launches
+    // share nothing but read-only inputs -- each has its own queue and claim cursor, and the two items of a pixel write disjoint bytes of
+    // its ShiftResult -- so they go to three streams (fork / join by events around the stage): a persistent block leaves as soon as its
+    // queue is drained, which frees its slot for the next class's blocks. Measured on the strip-sharded frame, where every queue is a
+    // fraction of the machine.
     template<bool TEMPORAL>
-    void LaunchShifts(int numSMs, const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn,
-        const zr_rpt_reservoir* resPrev, const uint16_t* neighbor, const uint32_t* d_queue, size_t capacity, uint32_t* d_counters,
-        ShiftResult* d_shift, cudaStream_t stream)
+    zr_status LaunchShifts(SpatialQueued& q, const SceneDev& sc, const FrameView& f, const RptParams& prm, const zr_rpt_reservoir* resIn,
+        const zr_rpt_reservoir* resPrev, const uint16_t* neighbor, cudaStream_t stream)
     {
-        const uint32_t grid = (uint32_t)numSMs * SHIFT_MINBLOCKS;
-#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS) \
-        k_shift<CASE, REPLAY, TEMPORAL><<<grid, SHIFT_THREADS, 0, stream>>>(sc, f, prm, resIn, resPrev, neighbor, d_queue + (size_t)(CLS) * capacity, \
-            d_counters, CLS, d_shift); \
+        const uint32_t grid = (uint32_t)q.numSMs * SHIFT_MINBLOCKS;
+        const bool fork = q.aux[0] && q.aux[1];
+        cudaStream_t s1 = fork ? q.aux[0] : stream, s2 = fork ? q.aux[1] : stream;
+        if (fork)
+        {
+            ZR_CUDA(cudaEventRecord(q.evFork, stream));
+            ZR_CUDA(cudaStreamWaitEvent(s1, q.evFork, 0));
+            ZR_CUDA(cudaStreamWaitEvent(s2, q.evFork, 0));
+        }
+#define ZR_LAUNCH_SHIFT(CASE, REPLAY, CLS, STREAM) \
+        k_shift<CASE, REPLAY, TEMPORAL><<<grid, SHIFT_THREADS, 0, STREAM>>>(sc, f, prm, resIn, resPrev, neighbor, q.d_queue + (size_t)(CLS) * q.capacity, \
+            q.d_counters, CLS, q.d_shift); \
         zr::count_launch()
-        ZR_LAUNCH_SHIFT(1, false, 0);
-        ZR_LAUNCH_SHIFT(1, true, 1);
-        ZR_LAUNCH_SHIFT(2, false, 2);
-        ZR_LAUNCH_SHIFT(2, true, 3);
-        ZR_LAUNCH_SHIFT(3, false, 4);
-        ZR_LAUNCH_SHIFT(3, true, 5);
+        ZR_LAUNCH_SHIFT(1, false, 0, stream);
+        ZR_LAUNCH_SHIFT(2, false, 2, s1);
+        ZR_LAUNCH_SHIFT(3, false, 4, s2);
+        ZR_LAUNCH_SHIFT(1, true, 1, s1);
+        ZR_LAUNCH_SHIFT(2, true, 3, s2);
+        ZR_LAUNCH_SHIFT(3, true, 5, stream);
 #undef ZR_LAUNCH_SHIFT
+        if (fork)
+        {
+            ZR_CUDA(cudaEventRecord(q.evJoin[0], s1));
+            ZR_CUDA(cudaEventRecord(q.evJoin[1], s2));
+            ZR_CUDA(cudaStreamWaitEvent(stream, q.evJoin[0], 0));
+            ZR_CUDA(cudaStreamWaitEvent(stream, q.evJoin[1], 0));
+        }
+        return ZR_OK;
     }
 
     // block-aggregated append of up to two items per thread (cls[d] == NO_ITEM: none) to the per-class queues:

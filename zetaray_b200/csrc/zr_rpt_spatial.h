@@ -38,6 +38,10 @@ struct SpatialQueued
     CUtensorMap* d_maps = nullptr;              // device copy of mapRes (the kernel reads the descriptor from global memory)
     int numSMs = 0;
     bool ready = false;
+    // the six class launches of a shift stage are independent (own queue, own claim cursor, disjoint result bytes): they are spread over
+    // the caller's stream and two forked ones, so that short queues -- small classes, strip-sharded frames -- run side by side
+    cudaStream_t aux[2] = { nullptr, nullptr };
+    cudaEvent_t evFork = nullptr, evJoin[2] = { nullptr, nullptr };
     bool swizzled = false;                      // even widths: 3-D map {128-byte record pair, W / 2, H} with the 128-byte swizzle
 
     zr_status Resize(uint32_t w, uint32_t h, const zr_rpt_reservoir* res0, const zr_rpt_reservoir* res1);
