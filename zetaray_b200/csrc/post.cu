@@ -267,7 +267,8 @@ namespace
     // TAA.hlsl:29-189. A block owns 32 x 8 pixels. The 3 x 3 neighbourhood is staged once per tile: every pixel of the 34 x 10 halo'd tile is
     // clamped to >= 0 and gets its tone-mapping weight 1 / (1 + luminance) ONCE (the per-tap form costs eight IEEE divisions per output
     // pixel), depth beside it; the taps then run out of shared memory in the reference's order with the reference's arithmetic.
-    __global__ void __launch_bounds__(256) k_taa(const float* __restrict__ depthPlane,
+    // 5 blocks per SM = 48 registers: measured against 62 (4 blocks) and 40 (6 blocks), profiles/r2v_occupancy_ab.json
+    __global__ void __launch_bounds__(256, 5) k_taa(const float* __restrict__ depthPlane,
         const uint2* __restrict__ motionEmissive, const float4* __restrict__ signal,
         const uint2* __restrict__ prevOut, uint2* __restrict__ out, PostParams p)
     {
